@@ -1,0 +1,4 @@
+"""CPU oracle for the exact vector-search hot path -- TEST INFRASTRUCTURE ONLY.
+
+Importable only from tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs.
+"""
