@@ -1,0 +1,16 @@
+"""financial_rag_b200 -- B200-native exact vector search behind Financial-RAG's ChildVectorStore API.
+
+One hot path only: child-chunk similarity scan + top-k + cross-collection
+fusion, as hand-written sm_100a CUDA behind the C ABI of include/fr_index.h.  There is no CPU
+fallback: importing the compute entry points without libfrb200.so raises ImportError.
+"""
+from .child_store import B200ChildStore
+from .collection import B200Client, B200Collection, PersistentClient, reset_registry
+from .index import ShardIndex, canonical_space, merge_shards_device, rrf_fuse_device, rrf_fuse_host
+from .vector_store_factory import get_child_vector_store
+
+__all__ = [
+    "B200ChildStore", "B200Client", "B200Collection", "PersistentClient", "ShardIndex",
+    "canonical_space", "get_child_vector_store", "merge_shards_device", "reset_registry",
+    "rrf_fuse_device", "rrf_fuse_host",
+]

@@ -1,0 +1,78 @@
+"""Build recipe for libfrb200.so: hand-written sm_100a CUDA behind the C ABI of include/fr_index.h.
+
+In-tree build (the .so travels to the GPU box with the repo snapshot; nothing is JIT-compiled there).
+Run as ``python -m financial_rag_b200.build`` or through ``__graft_entry__.build()``.
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+OBJ = os.path.join(PKG, "_build")
+LIB = os.path.join(PKG, "libfrb200.so")
+SOURCES = ["api.cu", "scan_stream.cu", "merge_topk.cu", "ingest.cu", "rrf.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O3,-Wall",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libfrb200.so cannot be built (there is no CPU fallback)")
+
+
+def _stamp() -> str:
+    h = hashlib.sha1(" ".join(NVCC_FLAGS).encode())
+    for root in (CSRC, os.path.join(os.path.dirname(PKG), "include")):
+        for name in sorted(os.listdir(root)):
+            with open(os.path.join(root, name), "rb") as f:
+                h.update(name.encode())
+                h.update(f.read())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a and link libfrb200.so.  Returns the library path."""
+    os.makedirs(OBJ, exist_ok=True)
+    stamp_path = os.path.join(OBJ, "stamp")
+    stamp = _stamp()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp_path):
+        if open(stamp_path).read() == stamp:
+            return LIB
+    nvcc = _nvcc()
+    extra = ["-Xptxas", "-v"] if verbose else []
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            sys.stderr.write(r.stderr)
+        return obj
+
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(stamp_path, "w") as f:
+        f.write(stamp)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

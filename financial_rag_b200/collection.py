@@ -1,0 +1,276 @@
+"""Chroma-``Collection``-shaped object backed by a B200 ShardIndex.
+
+The reference talks to chromadb through exactly this surface:
+  * ``PersistentClient(path).get_or_create_collection(name, metadata={"hnsw:space": "cosine"})``
+        parent_child/chroma_child_store.py:32-34, parent_child/multivector_store.py:51-52
+  * ``col.upsert(ids, embeddings, metadatas)`` / ``col.delete(ids)`` / ``col.add(...)``
+        chroma_child_store.py:54-59, multivector_store.py:136-139
+  * ``col.query(query_embeddings=[...], n_results=k, include=[...])`` -> dict of lists of lists
+        chroma_child_store.py:63-67, multivector_store.py:151-154
+  * ``col.count()``   chroma_child_store.py:78
+so ``multivector_store.py`` and ``chroma_child_store.py`` run unchanged on top of it.
+
+Vectors live in HBM inside the ShardIndex; ids / metadata (the payload the reference stores as
+``{"parent_id", "snippet", "context"}``) stay on the host keyed by the int64 row key.  The GPU index
+must outlive the per-request store objects the reference constructs (rag_backend.py:611-643), so
+collections live in a process-global registry keyed by (persist_dir, name).
+"""
+from __future__ import annotations
+
+import os
+import threading
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .index import FR_MAX_K, ShardIndex, canonical_space
+
+_INT64_MAX = (1 << 63) - 1
+
+
+def _as_matrix(embeddings, dim: Optional[int]) -> np.ndarray:
+    """Accept list[list[float]], numpy, or torch tensors (retriever.py:87 passes tensors)."""
+    if hasattr(embeddings, "detach"):
+        embeddings = embeddings.detach().cpu().numpy()
+    elif isinstance(embeddings, (list, tuple)) and len(embeddings) and hasattr(embeddings[0], "detach"):
+        embeddings = [e.detach().cpu().numpy() for e in embeddings]
+    m = np.asarray(embeddings, dtype=np.float32)
+    if m.ndim == 1:
+        m = m[None, :]
+    if m.ndim == 3 and m.shape[1] == 1:  # [[tensor(1,d)]] from the local wrapper (local_embedder.py:187-191)
+        m = m[:, 0, :]
+    if m.ndim != 2:
+        raise ValueError(f"embeddings must be 2-D, got shape {m.shape}")
+    if dim is not None and m.shape[1] != dim:
+        raise ValueError(f"embedding dimension {m.shape[1]} does not match collection dimension {dim}")
+    return np.ascontiguousarray(m)
+
+
+class B200Collection:
+    def __init__(self, name: str, metadata: Optional[Dict[str, Any]] = None, *, dtype: Optional[str] = None,
+                 device: Optional[int] = None):
+        self.name = name
+        self.metadata = dict(metadata or {})
+        self.space = canonical_space(self.metadata.get("hnsw:space"))
+        self.dtype = dtype or os.getenv("B200_CHILD_DTYPE", "bf16")
+        self.device = int(os.getenv("B200_CHILD_DEVICE", "0")) if device is None else int(device)
+        self._index: Optional[ShardIndex] = None  # created at first upsert: the dimension is not known before
+        self._lock = threading.RLock()
+        self._key_of_id: Dict[str, int] = {}
+        self._payload: Dict[int, Dict[str, Any]] = {}  # key -> {"id", "metadata", "document"}
+        self._next_synthetic = -2  # -1 is FR_KEY_NONE; ids that are not int64 decimals get negative keys
+
+    # -- helpers -------------------------------------------------------------------------------
+    @property
+    def dim(self) -> Optional[int]:
+        return self._index.dim if self._index is not None else None
+
+    @property
+    def index(self) -> Optional[ShardIndex]:
+        return self._index
+
+    def _key_for(self, id_str: str) -> int:
+        k = self._key_of_id.get(id_str)
+        if k is not None:
+            return k
+        key = None
+        if id_str.isdigit() and str(int(id_str)) == id_str and int(id_str) <= _INT64_MAX:
+            key = int(id_str)  # Snowflake child ids (snowflake_id.py:27-49) map to themselves
+        if key is None:
+            key = self._next_synthetic
+            self._next_synthetic -= 1
+        self._key_of_id[id_str] = key
+        return key
+
+    def _ensure_index(self, dim: int) -> ShardIndex:
+        if self._index is None:
+            self._index = ShardIndex(dim=dim, space=self.space, dtype=self.dtype, device=self.device)
+        return self._index
+
+    # -- chromadb.Collection surface -------------------------------------------------------------
+    def count(self) -> int:
+        with self._lock:
+            return 0 if self._index is None else self._index.count()
+
+    def upsert(self, ids: Sequence[str], embeddings=None, metadatas: Optional[Sequence[Optional[dict]]] = None,
+               documents: Optional[Sequence[Optional[str]]] = None) -> None:
+        if embeddings is None:
+            raise ValueError("B200Collection needs explicit embeddings (the reference always passes them)")
+        ids = [str(i) for i in ids]
+        if not ids:
+            return
+        with self._lock:
+            m = _as_matrix(embeddings, self.dim)
+            if m.shape[0] != len(ids):
+                raise ValueError("ids and embeddings differ in length")
+            idx = self._ensure_index(m.shape[1])
+            keys = np.array([self._key_for(i) for i in ids], dtype=np.int64)
+            idx.upsert(m, keys)
+            for j, (i, k) in enumerate(zip(ids, keys.tolist())):
+                self._payload[k] = {
+                    "id": i,
+                    "metadata": dict(metadatas[j]) if metadatas is not None and metadatas[j] is not None else None,
+                    "document": documents[j] if documents is not None else None,
+                }
+
+    def add(self, ids: Sequence[str], embeddings=None, metadatas=None, documents=None) -> None:
+        """chromadb ``add`` leaves existing ids untouched; only new ids are inserted."""
+        ids = [str(i) for i in ids]
+        with self._lock:
+            m = _as_matrix(embeddings, self.dim) if embeddings is not None else None
+            keep = [j for j, i in enumerate(ids)
+                    if i not in self._key_of_id or self._key_of_id[i] not in self._payload]
+            first = {}
+            for j in keep:  # an id repeated inside one add keeps its first occurrence
+                first.setdefault(ids[j], j)
+            keep = sorted(first.values())
+            if not keep:
+                return
+            self.upsert(
+                [ids[j] for j in keep],
+                m[keep] if m is not None else None,
+                [metadatas[j] for j in keep] if metadatas is not None else None,
+                [documents[j] for j in keep] if documents is not None else None,
+            )
+
+    def delete(self, ids: Optional[Sequence[str]] = None, where: Optional[dict] = None) -> None:
+        with self._lock:
+            if self._index is None:
+                return
+            keys: List[int] = []
+            if ids is not None:
+                for i in ids:
+                    k = self._key_of_id.get(str(i))
+                    if k is not None and k in self._payload:
+                        keys.append(k)
+            elif where:
+                for k, p in self._payload.items():
+                    md = p.get("metadata") or {}
+                    if all(md.get(f) == v for f, v in where.items()):
+                        keys.append(k)
+            if keys:
+                self._index.delete(np.array(keys, dtype=np.int64))
+                for k in keys:
+                    p = self._payload.pop(k, None)
+                    if p is not None:
+                        self._key_of_id.pop(p["id"], None)
+
+    def get(self, ids: Optional[Sequence[str]] = None, include: Optional[Sequence[str]] = None,
+            where: Optional[dict] = None, limit: Optional[int] = None) -> Dict[str, Any]:
+        include = list(include) if include is not None else ["metadatas", "documents"]
+        with self._lock:
+            if ids is not None:
+                keys = [self._key_of_id[str(i)] for i in ids
+                        if str(i) in self._key_of_id and self._key_of_id[str(i)] in self._payload]
+            else:
+                keys = list(self._payload.keys())
+            if where:
+                keys = [k for k in keys
+                        if all((self._payload[k].get("metadata") or {}).get(f) == v for f, v in where.items())]
+            if limit is not None:
+                keys = keys[:limit]
+            out: Dict[str, Any] = {"ids": [self._payload[k]["id"] for k in keys]}
+            out["metadatas"] = [self._payload[k]["metadata"] for k in keys] if "metadatas" in include else None
+            out["documents"] = [self._payload[k]["document"] for k in keys] if "documents" in include else None
+            out["embeddings"] = None
+            return out
+
+    def query(self, query_embeddings=None, n_results: int = 10, include: Optional[Sequence[str]] = None,
+              **_unused) -> Dict[str, Any]:
+        """Batched exact k-NN.  Returns chromadb's dict-of-lists-of-lists
+        (consumed at chroma_child_store.py:65-67 and multivector_store.py:152-154)."""
+        if query_embeddings is None:
+            raise ValueError("query_embeddings is required (no embedding function is attached)")
+        include = list(include) if include is not None else ["metadatas", "documents", "distances"]
+        n_results = int(n_results)
+        if n_results < 1:
+            raise ValueError("n_results must be >= 1")
+        with self._lock:
+            q = _as_matrix(query_embeddings, self.dim)
+            b = q.shape[0]
+            ids: List[List[str]] = [[] for _ in range(b)]
+            dists: List[List[float]] = [[] for _ in range(b)]
+            metas: List[List[Optional[dict]]] = [[] for _ in range(b)]
+            docs: List[List[Optional[str]]] = [[] for _ in range(b)]
+            if self._index is not None and self._index.count() > 0:
+                if n_results > FR_MAX_K:
+                    raise ValueError(f"n_results = {n_results} exceeds FR_MAX_K = {FR_MAX_K}")
+                d, keys = self._index.search(q, n_results)
+                for i in range(b):
+                    for dist, key in zip(d[i].tolist(), keys[i].tolist()):
+                        if key == -1:
+                            break
+                        p = self._payload[key]
+                        ids[i].append(p["id"])
+                        dists[i].append(dist)
+                        metas[i].append(p["metadata"])
+                        docs[i].append(p["document"])
+            return {
+                "ids": ids,
+                "distances": dists if "distances" in include else None,
+                "metadatas": metas if "metadatas" in include else None,
+                "documents": docs if "documents" in include else None,
+                "embeddings": None,
+                "uris": None,
+                "data": None,
+                "included": include,
+            }
+
+    def close(self) -> None:
+        with self._lock:
+            if self._index is not None:
+                self._index.close()
+                self._index = None
+            self._key_of_id.clear()
+            self._payload.clear()
+
+
+# ---- process-global registry: (persist_dir, name) -> collection -------------------------------
+_REGISTRY: Dict[tuple, B200Collection] = {}
+_REGISTRY_LOCK = threading.Lock()
+
+
+class B200Client:
+    """Stand-in for ``chromadb.PersistentClient(path=...)`` (chroma_child_store.py:32)."""
+
+    def __init__(self, path: str = "."):
+        self.path = os.path.abspath(path)
+
+    def get_or_create_collection(self, name: str, metadata: Optional[Dict[str, Any]] = None, **kw) -> B200Collection:
+        key = (self.path, name)
+        with _REGISTRY_LOCK:
+            col = _REGISTRY.get(key)
+            if col is None:
+                col = B200Collection(name, metadata, **kw)
+                _REGISTRY[key] = col
+            return col
+
+    def get_collection(self, name: str) -> B200Collection:
+        with _REGISTRY_LOCK:
+            col = _REGISTRY.get((self.path, name))
+        if col is None:
+            raise ValueError(f"Collection {name} does not exist.")
+        return col
+
+    def list_collections(self) -> List[B200Collection]:
+        with _REGISTRY_LOCK:
+            return [c for (p, _), c in _REGISTRY.items() if p == self.path]
+
+    def delete_collection(self, name: str) -> None:
+        with _REGISTRY_LOCK:
+            col = _REGISTRY.pop((self.path, name), None)
+        if col is not None:
+            col.close()
+
+
+def PersistentClient(path: str = ".") -> B200Client:  # noqa: N802 - chromadb's spelling
+    return B200Client(path)
+
+
+def reset_registry() -> None:
+    """Drop every collection (tests)."""
+    with _REGISTRY_LOCK:
+        cols = list(_REGISTRY.values())
+        _REGISTRY.clear()
+    for c in cols:
+        c.close()

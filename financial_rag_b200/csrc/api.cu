@@ -1,0 +1,740 @@
+// C ABI of libfrb200.so (include/fr_index.h): host-side shard management around the kernels.
+//
+// One fr_index = one collection shard resident on one B200:
+//     corpus  [cap_rows][dim]  bf16 or fp32, row-major, rows in insertion order (+32 rows of pad
+//                              so the streaming kernel may read whole 32-row blocks)
+//     keys    [cap_rows]       int64, INT64_MIN marks a deleted row
+// plus grow-only scratch (query staging, per-CTA partial lists, result staging, pinned mirror).
+// Mirrors what ChromaChildStore asks of chromadb (parent_child/chroma_child_store.py:32-80).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/fr_index.h"
+#include "fr_common.cuh"
+#include "fr_kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define FR_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return fail(_e == cudaErrorMemoryAllocation ? FR_ENOMEM : FR_ECUDA, "%s failed: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(_e), __FILE__, __LINE__);                           \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// grow-only device / pinned buffers
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t need(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        size_t want = n + n / 4;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = n;
+            e = cudaMalloc(&p, want);
+        }
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t need(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMallocHost(&p, n + n / 4);
+        if (e == cudaSuccess) bytes = n + n / 4;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+int check_device(int device, int *sm_count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(FR_ENODEV, "no CUDA device available (%s); this backend has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(FR_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(FR_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(FR_ENODEV, "device %d is sm_%d%d; libfrb200 is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    return FR_OK;
+}
+
+constexpr int64_t PAD_ROWS = 32;
+
+}  // namespace
+
+namespace fr {
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace fr
+
+struct fr_index {
+    int dim = 0, metric = FR_COSINE, dtype = FR_BF16, device = 0, sm_count = 148;
+    int path = FR_PATH_AUTO;
+    int64_t rows = 0;      // physical rows, deleted ones included
+    int64_t cap_rows = 0;  // usable rows (allocation holds cap_rows + PAD_ROWS)
+    int64_t n_deleted = 0;
+    uint8_t *corpus = nullptr;
+    int64_t *keys = nullptr;
+    cudaStream_t stream = nullptr;   // host-path stream
+    cudaEvent_t last_use = nullptr;  // orders scratch reuse across caller streams
+    DevBuf q_raw, q_prep, q_keys, partials, out_dist, out_keys, stage_vecs, stage_keys, stage_rows;
+    PinBuf pin;
+    std::mutex mu;
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // one pair per profiled search
+    std::vector<cudaEvent_t> prof_pool;
+    int64_t prof_launches = 0;
+    std::unordered_map<int64_t, int64_t> keymap;  // key -> row (live rows only)
+    bool keymap_valid = true;
+
+    size_t row_bytes() const { return static_cast<size_t>(dim) * (dtype == FR_BF16 ? 2 : 4); }
+};
+
+namespace {
+
+int grow(fr_index *ix, int64_t need_rows, bool exact) {
+    if (need_rows <= ix->cap_rows) return FR_OK;
+    int64_t new_cap = need_rows;
+    if (!exact) {
+        const int64_t geo = ix->cap_rows + ix->cap_rows / 2;
+        if (geo > new_cap) new_cap = geo;
+        if (new_cap < 1024) new_cap = 1024;
+    }
+    uint8_t *nc = nullptr;
+    int64_t *nk = nullptr;
+    const size_t rb = ix->row_bytes();
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&nc), static_cast<size_t>(new_cap + PAD_ROWS) * rb);
+    if (e != cudaSuccess && new_cap != need_rows) {
+        cudaGetLastError();
+        new_cap = need_rows;
+        e = cudaMalloc(reinterpret_cast<void **>(&nc), static_cast<size_t>(new_cap + PAD_ROWS) * rb);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(FR_ENOMEM, "cannot allocate %lld rows x %zu B on device %d: %s", (long long)new_cap, rb,
+                    ix->device, cudaGetErrorString(e));
+    }
+    e = cudaMalloc(reinterpret_cast<void **>(&nk), static_cast<size_t>(new_cap + PAD_ROWS) * sizeof(int64_t));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(nc);
+        return fail(FR_ENOMEM, "cannot allocate key array for %lld rows: %s", (long long)new_cap, cudaGetErrorString(e));
+    }
+    // all earlier work on this shard must be finished before the old arrays go away
+    FR_CUDA(cudaDeviceSynchronize());
+    FR_CUDA(cudaMemsetAsync(nc + static_cast<size_t>(ix->rows) * rb, 0,
+                            static_cast<size_t>(new_cap + PAD_ROWS - ix->rows) * rb, ix->stream));
+    if (ix->rows > 0) {
+        FR_CUDA(cudaMemcpyAsync(nc, ix->corpus, static_cast<size_t>(ix->rows) * rb, cudaMemcpyDeviceToDevice, ix->stream));
+        FR_CUDA(cudaMemcpyAsync(nk, ix->keys, static_cast<size_t>(ix->rows) * sizeof(int64_t), cudaMemcpyDeviceToDevice,
+                                ix->stream));
+    }
+    FR_CUDA(cudaStreamSynchronize(ix->stream));
+    if (ix->corpus) cudaFree(ix->corpus);
+    if (ix->keys) cudaFree(ix->keys);
+    ix->corpus = nc;
+    ix->keys = nk;
+    ix->cap_rows = new_cap;
+    return FR_OK;
+}
+
+// stream `s` is about to touch the shard's scratch: wait for whoever used it last
+int begin_use(fr_index *ix, cudaStream_t s) {
+    FR_CUDA(cudaStreamWaitEvent(s, ix->last_use, 0));
+    return FR_OK;
+}
+int end_use(fr_index *ix, cudaStream_t s) {
+    FR_CUDA(cudaEventRecord(ix->last_use, s));
+    return FR_OK;
+}
+
+int rebuild_keymap(fr_index *ix) {
+    if (ix->keymap_valid) return FR_OK;
+    std::vector<int64_t> hk(static_cast<size_t>(ix->rows));
+    FR_CUDA(cudaDeviceSynchronize());
+    if (ix->rows > 0)
+        FR_CUDA(cudaMemcpy(hk.data(), ix->keys, hk.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    ix->keymap.clear();
+    ix->keymap.reserve(hk.size() * 2);
+    for (int64_t r = 0; r < ix->rows; ++r)
+        if (hk[r] != fr::KEY_TOMBSTONE) ix->keymap[hk[r]] = r;
+    ix->keymap_valid = true;
+    return FR_OK;
+}
+
+// Core of every search entry point: device queries in, merged lists out, all on stream `s`.
+int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *d_out_dist,
+                     uint64_t *d_out_packed, int64_t *d_out_keys, cudaStream_t s) {
+    if (B == 0) return FR_OK;
+    if (ix->path == FR_PATH_MMA)
+        return fail(FR_EUNSUP, "FR_PATH_MMA (tcgen05 scan) is not built into this library yet");
+    const size_t qbytes = static_cast<size_t>(B) * ix->dim * sizeof(float);
+    const float *q = d_queries;
+    if (ix->metric == FR_COSINE) {
+        FR_CUDA(ix->q_prep.need(qbytes));
+        FR_CUDA(ix->q_keys.need(static_cast<size_t>(B) * sizeof(int64_t)));
+        fr::IngestArgs ia{};
+        ia.src = d_queries;
+        ia.n = B;
+        ia.dim = ix->dim;
+        ia.normalize = true;
+        ia.bf16 = false;
+        ia.corpus = static_cast<uint8_t *>(ix->q_prep.p);
+        ia.keys = static_cast<int64_t *>(ix->q_keys.p);
+        ia.stream = s;
+        FR_CUDA(fr::launch_ingest(ia));
+        q = static_cast<const float *>(ix->q_prep.p);
+    }
+    fr::ScanArgs sa{};
+    sa.corpus = ix->corpus;
+    sa.keys_or_null = ix->n_deleted > 0 ? ix->keys : nullptr;
+    sa.queries = q;
+    sa.n_rows = ix->rows;
+    sa.dim = ix->dim;
+    sa.bf16 = ix->dtype == FR_BF16;
+    sa.l2 = ix->metric == FR_L2;
+    sa.k = k;
+    sa.nq_total = B;
+    sa.stream = s;
+    sa.grid = fr::scan_stream_plan_grid(sa, ix->sm_count);
+    FR_CUDA(ix->partials.need(static_cast<size_t>(sa.grid) * B * k * sizeof(uint64_t)));
+    sa.partials = static_cast<uint64_t *>(ix->partials.p);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ix->profile) {
+        for (cudaEvent_t *ev : {&ev0, &ev1}) {
+            if (!ix->prof_pool.empty()) {
+                *ev = ix->prof_pool.back();
+                ix->prof_pool.pop_back();
+            } else {
+                FR_CUDA(cudaEventCreate(ev));
+            }
+        }
+        FR_CUDA(cudaEventRecord(ev0, s));
+    }
+    const int64_t launches_before = fr_launch_count();
+    FR_CUDA(fr::launch_scan_stream(sa));
+    if (ix->profile) {
+        FR_CUDA(cudaEventRecord(ev1, s));
+        ix->prof_events.emplace_back(ev0, ev1);
+        ix->prof_launches += fr_launch_count() - launches_before;
+    }
+
+    fr::MergeArgs ma{};
+    ma.packed = sa.partials;
+    ma.P = sa.grid;
+    ma.shard_stride = static_cast<int64_t>(B) * k;
+    ma.B = B;
+    ma.k = k;
+    ma.shards = false;
+    ma.row_keys = ix->keys;
+    ma.l2 = sa.l2;
+    ma.out_dist = d_out_dist;
+    ma.out_packed = d_out_packed;
+    ma.out_keys = d_out_keys;
+    ma.stream = s;
+    FR_CUDA(fr::launch_merge_topk(ma));
+    return FR_OK;
+}
+
+int check_search_args(fr_index *ix, const void *q, int B, int k, const void *o1, const void *o2) {
+    if (!ix) return fail(FR_EINVAL, "index is NULL");
+    if (B < 0) return fail(FR_EINVAL, "B = %d is negative", B);
+    if (k < 1) return fail(FR_EINVAL, "k = %d must be >= 1", k);
+    if (k > FR_MAX_K) return fail(FR_EUNSUP, "k = %d exceeds FR_MAX_K = %d", k, FR_MAX_K);
+    if (B > 0 && (!q || !o1 || !o2)) return fail(FR_EINVAL, "NULL buffer");
+    return FR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fr_abi_version(void) { return FR_ABI_VERSION; }
+const char *fr_last_error(void) { return g_last_error.c_str(); }
+int64_t fr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int fr_index_create(int dim, int metric, int dtype, int device, int64_t reserve_rows, fr_index **out) {
+    if (!out) return fail(FR_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (dim < 8 || dim > FR_MAX_DIM || dim % 8 != 0)
+        return fail(FR_EINVAL, "dim = %d must be a multiple of 8 in [8, %d]", dim, FR_MAX_DIM);
+    if (metric != FR_COSINE && metric != FR_L2 && metric != FR_IP) return fail(FR_EINVAL, "unknown metric %d", metric);
+    if (dtype != FR_BF16 && dtype != FR_F32) return fail(FR_EINVAL, "unknown dtype %d", dtype);
+    if (reserve_rows < 0) return fail(FR_EINVAL, "reserve_rows is negative");
+    int sm = 0;
+    int rc = check_device(device, &sm);
+    if (rc != FR_OK) return rc;
+    DeviceGuard g(device);
+    if (!g.ok) return fail(FR_ECUDA, "cudaSetDevice(%d) failed", device);
+    fr_index *ix = new (std::nothrow) fr_index();
+    if (!ix) return fail(FR_ENOMEM, "host allocation failed");
+    ix->dim = dim;
+    ix->metric = metric;
+    ix->dtype = dtype;
+    ix->device = device;
+    ix->sm_count = sm;
+    cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->last_use, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ix->last_use, ix->stream);
+    if (e != cudaSuccess) {
+        delete ix;
+        return fail(FR_ECUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
+    }
+    rc = grow(ix, reserve_rows > 0 ? reserve_rows : 1024, true);
+    if (rc != FR_OK) {
+        fr_index_destroy(ix);
+        return rc;
+    }
+    *out = ix;
+    return FR_OK;
+}
+
+int fr_index_destroy(fr_index *ix) {
+    if (!ix) return FR_OK;
+    {
+        DeviceGuard g(ix->device);
+        cudaDeviceSynchronize();
+        if (ix->corpus) cudaFree(ix->corpus);
+        if (ix->keys) cudaFree(ix->keys);
+        DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist,
+                          &ix->out_keys, &ix->stage_vecs, &ix->stage_keys, &ix->stage_rows};
+        for (DevBuf *b : bufs) b->release();
+        ix->pin.release();
+        for (auto &pr : ix->prof_events) {
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        for (cudaEvent_t ev : ix->prof_pool) cudaEventDestroy(ev);
+        if (ix->last_use) cudaEventDestroy(ix->last_use);
+        if (ix->stream) cudaStreamDestroy(ix->stream);
+    }
+    delete ix;
+    return FR_OK;
+}
+
+int fr_index_reserve(fr_index *ix, int64_t rows) {
+    if (!ix) return fail(FR_EINVAL, "index is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    return grow(ix, rows, true);
+}
+
+int fr_index_set_option(fr_index *ix, const char *name, int64_t value) {
+    if (!ix || !name) return fail(FR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (std::strcmp(name, "profile") == 0) {
+        ix->profile = value != 0;
+        return FR_OK;
+    }
+    if (std::strcmp(name, "path") == 0) {
+        if (value < FR_PATH_AUTO || value > FR_PATH_MMA) return fail(FR_EINVAL, "path = %lld is not a FR_PATH_* value", (long long)value);
+        ix->path = static_cast<int>(value);
+        return FR_OK;
+    }
+    return fail(FR_EINVAL, "unknown option '%s'", name);
+}
+
+int fr_index_profile_read(fr_index *ix, double *out_scan_ms, int64_t *out_scan_launches, int64_t *out_searches) {
+    if (!ix || !out_scan_ms || !out_scan_launches || !out_searches) return fail(FR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    double total = 0.0;
+    for (auto &pr : ix->prof_events) {
+        FR_CUDA(cudaEventSynchronize(pr.second));
+        float ms = 0.0f;
+        FR_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        total += ms;
+        ix->prof_pool.push_back(pr.first);
+        ix->prof_pool.push_back(pr.second);
+    }
+    *out_scan_ms = total;
+    *out_scan_launches = ix->prof_launches;
+    *out_searches = static_cast<int64_t>(ix->prof_events.size());
+    ix->prof_events.clear();
+    ix->prof_launches = 0;
+    return FR_OK;
+}
+
+int fr_index_count(fr_index *ix, int64_t *out) {
+    if (!ix || !out) return fail(FR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    *out = ix->rows - ix->n_deleted;
+    return FR_OK;
+}
+
+int fr_index_rows(fr_index *ix, int64_t *out) {
+    if (!ix || !out) return fail(FR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    *out = ix->rows;
+    return FR_OK;
+}
+
+int fr_index_upsert(fr_index *ix, const float *vecs, const int64_t *keys, int64_t n) {
+    if (!ix) return fail(FR_EINVAL, "index is NULL");
+    if (n < 0) return fail(FR_EINVAL, "n is negative");
+    if (n == 0) return FR_OK;
+    if (!vecs || !keys) return fail(FR_EINVAL, "NULL buffer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    int rc = rebuild_keymap(ix);
+    if (rc != FR_OK) return rc;
+    // resolve target rows on the host: existing key -> its row (in place), new key -> append
+    std::vector<int64_t> target(static_cast<size_t>(n));
+    std::unordered_map<int64_t, int64_t> last_writer;  // row -> index of the last vector aimed at it
+    int64_t new_rows = ix->rows;
+    for (int64_t i = 0; i < n; ++i)
+        if (keys[i] == fr::KEY_TOMBSTONE) return fail(FR_EINVAL, "key INT64_MIN is reserved");
+    for (int64_t i = 0; i < n; ++i) {
+        auto it = ix->keymap.find(keys[i]);
+        int64_t row;
+        if (it != ix->keymap.end()) {
+            row = it->second;
+        } else {
+            row = new_rows++;
+            ix->keymap.emplace(keys[i], row);
+        }
+        target[i] = row;
+        auto lw = last_writer.find(row);
+        if (lw != last_writer.end()) {
+            target[lw->second] = -1;  // duplicate key inside this call: the last one wins
+            lw->second = i;
+        } else {
+            last_writer.emplace(row, i);
+        }
+    }
+    if (new_rows > 0xfffffff0ll) {
+        ix->keymap_valid = false;
+        return fail(FR_EUNSUP, "a shard holds at most 2^32-16 rows");
+    }
+    rc = grow(ix, new_rows, false);
+    if (rc != FR_OK) {
+        ix->keymap_valid = false;  // the map now names rows that were never written
+        return rc;
+    }
+    cudaStream_t s = ix->stream;
+    rc = begin_use(ix, s);
+    if (rc != FR_OK) return rc;
+    const int64_t CH = 1 << 16;
+    const size_t vb = static_cast<size_t>(ix->dim) * sizeof(float);
+    for (int64_t lo = 0; lo < n; lo += CH) {
+        const int64_t m = (n - lo < CH) ? (n - lo) : CH;
+        FR_CUDA(ix->stage_vecs.need(static_cast<size_t>(m) * vb));
+        FR_CUDA(ix->stage_keys.need(static_cast<size_t>(m) * sizeof(int64_t)));
+        FR_CUDA(ix->stage_rows.need(static_cast<size_t>(m) * sizeof(int64_t)));
+        FR_CUDA(cudaMemcpyAsync(ix->stage_vecs.p, vecs + lo * ix->dim, static_cast<size_t>(m) * vb, cudaMemcpyHostToDevice, s));
+        FR_CUDA(cudaMemcpyAsync(ix->stage_keys.p, keys + lo, static_cast<size_t>(m) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        FR_CUDA(cudaMemcpyAsync(ix->stage_rows.p, target.data() + lo, static_cast<size_t>(m) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        fr::IngestArgs ia{};
+        ia.src = static_cast<const float *>(ix->stage_vecs.p);
+        ia.src_keys = static_cast<const int64_t *>(ix->stage_keys.p);
+        ia.target_rows = static_cast<const int64_t *>(ix->stage_rows.p);
+        ia.n = m;
+        ia.dim = ix->dim;
+        ia.normalize = ix->metric == FR_COSINE;
+        ia.bf16 = ix->dtype == FR_BF16;
+        ia.corpus = ix->corpus;
+        ia.keys = ix->keys;
+        ia.stream = s;
+        FR_CUDA(fr::launch_ingest(ia));
+        FR_CUDA(cudaStreamSynchronize(s));  // staging buffers are reused by the next chunk
+    }
+    ix->rows = new_rows;
+    return end_use(ix, s);
+}
+
+int fr_index_delete(fr_index *ix, const int64_t *keys, int64_t n, int64_t *out_deleted) {
+    if (!ix) return fail(FR_EINVAL, "index is NULL");
+    if (out_deleted) *out_deleted = 0;
+    if (n < 0) return fail(FR_EINVAL, "n is negative");
+    if (n == 0) return FR_OK;
+    if (!keys) return fail(FR_EINVAL, "NULL buffer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    int rc = rebuild_keymap(ix);
+    if (rc != FR_OK) return rc;
+    std::vector<int64_t> rows;
+    for (int64_t i = 0; i < n; ++i) {
+        auto it = ix->keymap.find(keys[i]);
+        if (it == ix->keymap.end()) continue;
+        rows.push_back(it->second);
+        ix->keymap.erase(it);
+    }
+    if (!rows.empty()) {
+        cudaStream_t s = ix->stream;
+        rc = begin_use(ix, s);
+        if (rc != FR_OK) return rc;
+        FR_CUDA(ix->stage_rows.need(rows.size() * sizeof(int64_t)));
+        FR_CUDA(cudaMemcpyAsync(ix->stage_rows.p, rows.data(), rows.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        FR_CUDA(fr::launch_fill_keys(ix->keys, static_cast<const int64_t *>(ix->stage_rows.p),
+                                     static_cast<int64_t>(rows.size()), fr::KEY_TOMBSTONE, s));
+        FR_CUDA(cudaStreamSynchronize(s));
+        ix->n_deleted += static_cast<int64_t>(rows.size());
+        rc = end_use(ix, s);
+        if (rc != FR_OK) return rc;
+    }
+    if (out_deleted) *out_deleted = static_cast<int64_t>(rows.size());
+    return FR_OK;
+}
+
+int fr_index_append_device(fr_index *ix, const float *d_vecs, const int64_t *d_keys, int64_t first_key, int64_t n,
+                           void *stream) {
+    if (!ix) return fail(FR_EINVAL, "index is NULL");
+    if (n < 0) return fail(FR_EINVAL, "n is negative");
+    if (n == 0) return FR_OK;
+    if (!d_vecs) return fail(FR_EINVAL, "NULL buffer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (ix->rows + n > 0xfffffff0ll) return fail(FR_EUNSUP, "a shard holds at most 2^32-16 rows");
+    int rc = grow(ix, ix->rows + n, false);
+    if (rc != FR_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    rc = begin_use(ix, s);
+    if (rc != FR_OK) return rc;
+    fr::IngestArgs ia{};
+    ia.src = d_vecs;
+    ia.src_keys = d_keys;
+    ia.first_key = first_key;
+    ia.base_row = ix->rows;
+    ia.n = n;
+    ia.dim = ix->dim;
+    ia.normalize = ix->metric == FR_COSINE;
+    ia.bf16 = ix->dtype == FR_BF16;
+    ia.corpus = ix->corpus;
+    ia.keys = ix->keys;
+    ia.stream = s;
+    FR_CUDA(fr::launch_ingest(ia));
+    ix->rows += n;
+    ix->keymap_valid = false;  // rebuilt lazily from the device keys if upsert/delete is used later
+    ix->keymap.clear();
+    return end_use(ix, s);
+}
+
+int fr_index_get_rows(fr_index *ix, int64_t first_row, int64_t n, float *out_vecs, int64_t *out_keys) {
+    if (!ix) return fail(FR_EINVAL, "index is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (first_row < 0 || n < 0 || first_row + n > ix->rows)
+        return fail(FR_EINVAL, "rows [%lld, %lld) out of range (index holds %lld)", (long long)first_row,
+                    (long long)(first_row + n), (long long)ix->rows);
+    if (n == 0) return FR_OK;
+    DeviceGuard g(ix->device);
+    FR_CUDA(cudaDeviceSynchronize());
+    const size_t rb = ix->row_bytes();
+    if (out_vecs) {
+        if (ix->dtype == FR_F32) {
+            FR_CUDA(cudaMemcpy(out_vecs, ix->corpus + first_row * rb, static_cast<size_t>(n) * rb, cudaMemcpyDeviceToHost));
+        } else {
+            std::vector<uint16_t> tmp(static_cast<size_t>(n) * ix->dim);
+            FR_CUDA(cudaMemcpy(tmp.data(), ix->corpus + first_row * rb, tmp.size() * 2, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < tmp.size(); ++i) {
+                const uint32_t u = static_cast<uint32_t>(tmp[i]) << 16;
+                std::memcpy(&out_vecs[i], &u, 4);
+            }
+        }
+    }
+    if (out_keys)
+        FR_CUDA(cudaMemcpy(out_keys, ix->keys + first_row, static_cast<size_t>(n) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return FR_OK;
+}
+
+int fr_index_search(fr_index *ix, const float *queries, int B, int k, float *out_dist, int64_t *out_keys) {
+    int rc = check_search_args(ix, queries, B, k, out_dist, out_keys);
+    if (rc != FR_OK || B == 0) return rc;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t s = ix->stream;
+    const size_t qb = static_cast<size_t>(B) * ix->dim * sizeof(float);
+    const size_t db = static_cast<size_t>(B) * k * sizeof(float);
+    const size_t kb = static_cast<size_t>(B) * k * sizeof(int64_t);
+    const size_t db_al = (db + 15) & ~static_cast<size_t>(15);
+    FR_CUDA(ix->pin.need(qb + db_al + kb));
+    FR_CUDA(ix->q_raw.need(qb));
+    FR_CUDA(ix->out_dist.need(db));
+    FR_CUDA(ix->out_keys.need(kb));
+    rc = begin_use(ix, s);
+    if (rc != FR_OK) return rc;
+    uint8_t *pin = static_cast<uint8_t *>(ix->pin.p);
+    // results first so the int64 block stays 8-byte aligned
+    uint8_t *pin_keys = pin, *pin_dist = pin + kb, *pin_q = pin + kb + db_al;
+    std::memcpy(pin_q, queries, qb);
+    FR_CUDA(cudaMemcpyAsync(ix->q_raw.p, pin_q, qb, cudaMemcpyHostToDevice, s));
+    rc = search_on_stream(ix, static_cast<const float *>(ix->q_raw.p), B, k, static_cast<float *>(ix->out_dist.p),
+                          nullptr, static_cast<int64_t *>(ix->out_keys.p), s);
+    if (rc != FR_OK) return rc;
+    FR_CUDA(cudaMemcpyAsync(pin_dist, ix->out_dist.p, db, cudaMemcpyDeviceToHost, s));
+    FR_CUDA(cudaMemcpyAsync(pin_keys, ix->out_keys.p, kb, cudaMemcpyDeviceToHost, s));
+    rc = end_use(ix, s);
+    if (rc != FR_OK) return rc;
+    FR_CUDA(cudaStreamSynchronize(s));
+    std::memcpy(out_dist, pin_dist, db);
+    std::memcpy(out_keys, pin_keys, kb);
+    return FR_OK;
+}
+
+int fr_index_search_device(fr_index *ix, const float *d_queries, int B, int k, float *d_out_dist, int64_t *d_out_keys,
+                           void *stream) {
+    int rc = check_search_args(ix, d_queries, B, k, d_out_dist, d_out_keys);
+    if (rc != FR_OK || B == 0) return rc;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    rc = begin_use(ix, s);
+    if (rc != FR_OK) return rc;
+    rc = search_on_stream(ix, d_queries, B, k, d_out_dist, nullptr, d_out_keys, s);
+    if (rc != FR_OK) return rc;
+    return end_use(ix, s);
+}
+
+int fr_index_search_partial_device(fr_index *ix, const float *d_queries, int B, int k, uint64_t *d_out_packed,
+                                   int64_t *d_out_keys, void *stream) {
+    int rc = check_search_args(ix, d_queries, B, k, d_out_packed, d_out_keys);
+    if (rc != FR_OK || B == 0) return rc;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    rc = begin_use(ix, s);
+    if (rc != FR_OK) return rc;
+    rc = search_on_stream(ix, d_queries, B, k, nullptr, d_out_packed, d_out_keys, s);
+    if (rc != FR_OK) return rc;
+    return end_use(ix, s);
+}
+
+int fr_merge_shards_device(int device, int metric, const uint64_t *d_packed, const int64_t *d_keys,
+                           int64_t shard_stride_elems, int G, int B, int k, float *d_out_dist, int64_t *d_out_keys,
+                           void *stream) {
+    if (G < 1 || B < 0 || k < 1) return fail(FR_EINVAL, "bad G/B/k (%d/%d/%d)", G, B, k);
+    if (k > FR_MAX_K) return fail(FR_EUNSUP, "k = %d exceeds FR_MAX_K = %d", k, FR_MAX_K);
+    if (B == 0) return FR_OK;
+    if (!d_packed || !d_keys || !d_out_dist || !d_out_keys) return fail(FR_EINVAL, "NULL buffer");
+    if (shard_stride_elems < static_cast<int64_t>(B) * k) return fail(FR_EINVAL, "shard stride smaller than B*k");
+    int rc = check_device(device, nullptr);
+    if (rc != FR_OK) return rc;
+    DeviceGuard g(device);
+    fr::MergeArgs ma{};
+    ma.packed = d_packed;
+    ma.P = G;
+    ma.shard_stride = shard_stride_elems;
+    ma.B = B;
+    ma.k = k;
+    ma.shards = true;
+    ma.shard_keys = d_keys;
+    ma.l2 = metric == FR_L2;
+    ma.out_dist = d_out_dist;
+    ma.out_keys = d_out_keys;
+    ma.stream = static_cast<cudaStream_t>(stream);
+    FR_CUDA(fr::launch_merge_topk(ma));
+    return FR_OK;
+}
+
+int fr_rrf_fuse_device(int device, const int64_t *d_keys, int L, int B, int kp, int k_rrf, int k_out,
+                       double *d_out_score, int64_t *d_out_keys, void *stream) {
+    if (L < 1 || B < 0 || kp < 1 || k_out < 1 || k_rrf < 0) return fail(FR_EINVAL, "bad L/B/kp/k_rrf/k_out");
+    if (static_cast<int64_t>(L) * kp > 2048) return fail(FR_EUNSUP, "L*kp = %d exceeds 2048 candidates per query", L * kp);
+    if (B == 0) return FR_OK;
+    if (!d_keys || !d_out_score || !d_out_keys) return fail(FR_EINVAL, "NULL buffer");
+    int rc = check_device(device, nullptr);
+    if (rc != FR_OK) return rc;
+    DeviceGuard g(device);
+    fr::RrfArgs ra{d_keys, L, B, kp, k_rrf, k_out, d_out_score, d_out_keys, static_cast<cudaStream_t>(stream)};
+    FR_CUDA(fr::launch_rrf_fuse(ra));
+    return FR_OK;
+}
+
+int fr_rrf_fuse(int device, const int64_t *keys, int L, int B, int kp, int k_rrf, int k_out, double *out_score,
+                int64_t *out_keys) {
+    if (L < 1 || B < 0 || kp < 1 || k_out < 1 || k_rrf < 0) return fail(FR_EINVAL, "bad L/B/kp/k_rrf/k_out");
+    if (B == 0) return FR_OK;
+    if (!keys || !out_score || !out_keys) return fail(FR_EINVAL, "NULL buffer");
+    int rc = check_device(device, nullptr);
+    if (rc != FR_OK) return rc;
+    DeviceGuard g(device);
+    const size_t inb = static_cast<size_t>(L) * B * kp * sizeof(int64_t);
+    const size_t ob = static_cast<size_t>(B) * k_out * 8;
+    void *d_in = nullptr, *d_sc = nullptr, *d_k = nullptr;
+    cudaStream_t s = nullptr;
+    auto cleanup = [&]() {
+        if (d_in) cudaFree(d_in);
+        if (d_sc) cudaFree(d_sc);
+        if (d_k) cudaFree(d_k);
+        if (s) cudaStreamDestroy(s);
+    };
+    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&d_in, inb);
+    if (e == cudaSuccess) e = cudaMalloc(&d_sc, ob);
+    if (e == cudaSuccess) e = cudaMalloc(&d_k, ob);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, keys, inb, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(FR_ECUDA, "rrf staging failed: %s", cudaGetErrorString(e));
+    }
+    rc = fr_rrf_fuse_device(device, static_cast<const int64_t *>(d_in), L, B, kp, k_rrf, k_out,
+                            static_cast<double *>(d_sc), static_cast<int64_t *>(d_k), s);
+    if (rc == FR_OK) {
+        e = cudaMemcpyAsync(out_score, d_sc, ob, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_keys, d_k, ob, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = fail(FR_ECUDA, "rrf copy-back failed: %s", cudaGetErrorString(e));
+    }
+    cleanup();
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// Shared device helpers for the exact-scan kernels (sm_100a).
+//
+// Candidate encoding used by every kernel on the path: one uint64 "packed key"
+//     (order_bits(score) << 32) | (0xFFFFFFFF - local_row)
+// so a plain unsigned compare orders candidates by (score descending, row ascending) -- the
+// order the reference returns (ascending distance, ties in insertion order; SURVEY.md 8c,
+// observed in test_logs/query_trace_20250824_121349_f50cc515.json).  0 means "empty slot".
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fr {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+constexpr int64_t KEY_TOMBSTONE = INT64_MIN;
+
+__device__ __forceinline__ uint32_t order_bits(float s) {
+    uint32_t u = __float_as_uint(s);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unorder_bits(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ uint64_t pack_key(float score, uint32_t row) {
+    return (static_cast<uint64_t>(order_bits(score)) << 32) | static_cast<uint64_t>(0xffffffffu - row);
+}
+__device__ __forceinline__ float key_score(uint64_t key) {
+    return unorder_bits(static_cast<uint32_t>(key >> 32));
+}
+__device__ __forceinline__ uint32_t key_row(uint64_t key) {
+    return 0xffffffffu - static_cast<uint32_t>(key & 0xffffffffu);
+}
+// The float gate "score >= threshold_of(key)" : -inf while the list is not full.
+__device__ __forceinline__ float key_threshold(uint64_t kth_key) {
+    return kth_key ? key_score(kth_key) : -INFINITY;
+}
+
+// 128-bit streaming load: read-only path, do not allocate in L1 (each corpus byte is used once).
+__device__ __forceinline__ uint4 ld_stream_u4(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// A top-K list held by one warp in registers: entry i lives in lane (i & 31), slot (i >> 5).
+// Entries are sorted descending by packed key.  KPL slots per lane => capacity 32*KPL.
+template <int KPL>
+struct WarpTopK {
+    uint64_t e[KPL];
+
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) e[j] = 0ull;
+    }
+
+    // Warp-uniform `key`; every lane of the warp must call.  Keeps the best `k` (<= 32*KPL).
+    __device__ __forceinline__ void insert(uint64_t key, int k, int lane) {
+        int pos = 0;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) pos += __popc(__ballot_sync(FULL_MASK, e[j] > key));
+        if (pos >= k) return;  // uniform
+#pragma unroll
+        for (int j = KPL - 1; j >= 0; --j) {
+            uint64_t up = __shfl_up_sync(FULL_MASK, e[j], 1);
+            if (j > 0) {
+                uint64_t carry = __shfl_sync(FULL_MASK, e[j - 1], 31);
+                if (lane == 0) up = carry;
+            }
+            const int i = j * 32 + lane;
+            e[j] = (i < pos) ? e[j] : ((i == pos) ? key : up);
+        }
+    }
+
+    // entry k-1 (the current threshold), broadcast to the whole warp
+    __device__ __forceinline__ uint64_t kth(int k) const {
+        const int slot = (k - 1) >> 5, src = (k - 1) & 31;
+        uint64_t v = 0ull;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+            uint64_t t = __shfl_sync(FULL_MASK, e[j], src);
+            if (j == slot) v = t;
+        }
+        return v;
+    }
+
+    // store / load the whole list (32*KPL entries) to a buffer (shared or global)
+    __device__ __forceinline__ void store(uint64_t *dst, int lane) const {
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) dst[j * 32 + lane] = e[j];
+    }
+
+    // Merge a descending-sorted list `src[0..n)` (readable by all lanes) into this one.
+    __device__ __forceinline__ void merge_sorted(const uint64_t *src, int n, int k, int lane) {
+        uint64_t thr = kth(k);
+        for (int i = 0; i < n; ++i) {
+            const uint64_t key = src[i];      // same address for all lanes: broadcast
+            if (key == 0ull || key <= thr) break;  // sorted: nothing further can enter
+            insert(key, k, lane);
+            thr = kth(k);
+        }
+    }
+};
+
+// Merge the per-warp lists of one CTA.  `lists` = shared memory [nwarps][nq][32*KPL];
+// on return warp 0 holds the CTA-wide best k for every query.  All threads must call.
+template <int KPL, int NQ>
+__device__ __forceinline__ void cta_merge_lists(WarpTopK<KPL> (&tk)[NQ], uint64_t *lists, int nwarps,
+                                                int warp, int lane, int k) {
+    constexpr int CAP = 32 * KPL;
+#pragma unroll
+    for (int b = 0; b < NQ; ++b) tk[b].store(lists + (warp * NQ + b) * CAP, lane);
+    for (int stride = 1; stride < nwarps; stride <<= 1) {
+        __syncthreads();
+        const bool active = (warp % (2 * stride) == 0) && (warp + stride < nwarps);
+        if (active) {
+#pragma unroll
+            for (int b = 0; b < NQ; ++b)
+                tk[b].merge_sorted(lists + ((warp + stride) * NQ + b) * CAP, k < CAP ? k : CAP, k, lane);
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int b = 0; b < NQ; ++b) tk[b].store(lists + (warp * NQ + b) * CAP, lane);
+        }
+    }
+    __syncthreads();
+}
+
+}  // namespace fr

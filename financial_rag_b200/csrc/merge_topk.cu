@@ -1,0 +1,94 @@
+// K3 merge_topk -- merge sorted partial top-k lists into the final sorted top-k (sm_100a).
+//
+// Two uses on the path that replaces chromadb Collection.query
+// (parent_child/chroma_child_store.py:63):
+//   LOCAL : the per-CTA lists K1/K2 wrote for one shard  -> that shard's result
+//   SHARDS: the G per-GPU lists brought together by the NCCL all-gather (K4) -> the final result,
+//           ties resolved by (shard, position) == global insertion order, so any G gives the
+//           same answer as G = 1.
+// One CTA per query; each warp folds a slice of the lists into a register WarpTopK using the
+// threshold gate, warps are merged through shared memory, warp 0 writes the result and turns
+// packed keys into (distance, int64 key).  Latency-bound; traffic is P*k*8 bytes per query.
+#include "fr_common.cuh"
+#include "fr_kernels.h"
+
+namespace fr {
+
+template <int KPL, bool SHARDS>
+__global__ void __launch_bounds__(128)
+merge_topk_kernel(const uint64_t *__restrict__ packed, int P, int64_t shard_stride, int B, int k,
+                  const int64_t *__restrict__ row_keys, const int64_t *__restrict__ shard_keys, bool l2,
+                  float *__restrict__ out_dist, uint64_t *__restrict__ out_packed,
+                  int64_t *__restrict__ out_keys) {
+    __shared__ uint64_t lists[4 * 32 * KPL];
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+
+    WarpTopK<KPL> tk[1];
+    tk[0].clear();
+    uint64_t thr = 0ull;
+    for (int p = warp; p < P; p += nwarps) {
+        const uint64_t *src = packed + static_cast<int64_t>(p) * shard_stride + static_cast<int64_t>(b) * k;
+        for (int i0 = 0; i0 < k; i0 += 32) {
+            const int i = i0 + lane;
+            uint64_t key = (i < k) ? src[i] : 0ull;
+            if (SHARDS && key != 0ull)
+                key = (key & 0xffffffff00000000ull) | static_cast<uint64_t>(0xffffffffu - static_cast<uint32_t>(p * k + i));
+            unsigned m = __ballot_sync(FULL_MASK, key != 0ull && key > thr);
+            if (m == 0u) break;  // list is sorted: nothing further in it can enter
+            while (m) {
+                const int srcl = __ffs(m) - 1;
+                m &= m - 1;
+                const uint64_t kk = __shfl_sync(FULL_MASK, key, srcl);
+                tk[0].insert(kk, k, lane);
+            }
+            thr = tk[0].kth(k);
+        }
+    }
+    cta_merge_lists<KPL, 1>(tk, lists, nwarps, warp, lane, k);
+    if (warp != 0) return;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+        const int i = j * 32 + lane;
+        if (i >= k) continue;
+        const uint64_t key = tk[0].e[j];
+        const int64_t o = static_cast<int64_t>(b) * k + i;
+        if (key == 0ull) {
+            if (out_dist) out_dist[o] = INFINITY;
+            if (out_packed) out_packed[o] = 0ull;
+            out_keys[o] = -1;
+            continue;
+        }
+        const uint32_t idx = key_row(key);
+        const float s = key_score(key);
+        if (out_dist) out_dist[o] = l2 ? -s : 1.0f - s;
+        if (out_packed) out_packed[o] = key;
+        if (SHARDS) {
+            const int g = idx / k, jj = idx - g * k;
+            out_keys[o] = shard_keys[static_cast<int64_t>(g) * shard_stride + static_cast<int64_t>(b) * k + jj];
+        } else {
+            out_keys[o] = row_keys[idx];
+        }
+    }
+}
+
+cudaError_t launch_merge_topk(const MergeArgs &a) {
+    if (a.B <= 0) return cudaSuccess;
+    const dim3 grid(a.B), block(128);
+#define FR_MERGE(KPL, SH)                                                                          \
+    merge_topk_kernel<KPL, SH><<<grid, block, 0, a.stream>>>(a.packed, a.P, a.shard_stride, a.B, a.k, \
+                                                             a.row_keys, a.shard_keys, a.l2, a.out_dist, \
+                                                             a.out_packed, a.out_keys)
+    if (a.k <= 32) {
+        if (a.shards) FR_MERGE(1, true); else FR_MERGE(1, false);
+    } else {
+        if (a.shards) FR_MERGE(4, true); else FR_MERGE(4, false);
+    }
+#undef FR_MERGE
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace fr

@@ -1,0 +1,229 @@
+"""ShardIndex -- Python handle on one fr_index (one collection shard resident on one B200).
+
+Thin host code over the C ABI (include/fr_index.h); all arithmetic happens in the CUDA kernels.
+numpy arrays are used for the host entry points, torch tensors only as owners of device memory
+for the ``*_device`` entry points.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import FR_BF16, FR_COSINE, FR_F32, FR_IP, FR_L2, FR_MAX_K, check
+
+_METRICS = {"cosine": FR_COSINE, "l2": FR_L2, "ip": FR_IP}
+_DTYPES = {"bf16": FR_BF16, "f32": FR_F32}
+_PATHS = {"auto": 0, "stream": 1, "mma": 2}
+
+
+def canonical_space(space: Optional[str]) -> str:
+    """Metric vocabulary of the reference (parent_child/pgvector_child_store.py:7-26);
+    unknown names fall back to cosine exactly as ``_get_distance_ops`` does."""
+    d = (space or "cosine").lower()
+    if d in ("cos", "cosine"):
+        return "cosine"
+    if d in ("l2", "euclidean"):
+        return "l2"
+    if d in ("ip", "inner", "inner_product"):
+        return "ip"
+    return "cosine"
+
+
+def _stream_ptr(stream) -> ctypes.c_void_p:
+    if stream is None:
+        import torch
+
+        stream = torch.cuda.current_stream()
+    return ctypes.c_void_p(int(getattr(stream, "cuda_stream", stream)))
+
+
+class ShardIndex:
+    def __init__(self, dim: int = 384, space: str = "cosine", dtype: str = "bf16", device: int = 0,
+                 reserve_rows: int = 0):
+        self._lib = _lib.load()
+        self.dim = int(dim)
+        self.space = canonical_space(space)
+        if dtype not in _DTYPES:
+            raise ValueError(f"dtype must be 'bf16' or 'f32', got {dtype!r}")
+        self.dtype = dtype
+        self.device = int(device)
+        h = ctypes.c_void_p()
+        check(self._lib.fr_index_create(self.dim, _METRICS[self.space], _DTYPES[dtype], self.device,
+                                        int(reserve_rows), ctypes.byref(h)))
+        self._h = h
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    def close(self) -> None:
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.fr_index_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _handle(self):
+        if not self._h:
+            raise RuntimeError("ShardIndex is closed")
+        return self._h
+
+    def reserve(self, rows: int) -> None:
+        check(self._lib.fr_index_reserve(self._handle(), int(rows)))
+
+    def set_path(self, path: str) -> None:
+        """Pin the kernel regime: 'auto' | 'stream' (K1) | 'mma' (K2).  Tests and bench use it."""
+        check(self._lib.fr_index_set_option(self._handle(), b"path", _PATHS[path]))
+
+    def set_profile(self, on: bool) -> None:
+        """Bracket every scan launch with CUDA events (bench.py's roofline line)."""
+        check(self._lib.fr_index_set_option(self._handle(), b"profile", 1 if on else 0))
+
+    def profile_read(self):
+        """(summed scan-kernel ms, scan launches, searches) since the last read; resets."""
+        ms, nl, ns = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+        check(self._lib.fr_index_profile_read(self._handle(), ctypes.byref(ms), ctypes.byref(nl), ctypes.byref(ns)))
+        return float(ms.value), int(nl.value), int(ns.value)
+
+    def count(self) -> int:
+        out = ctypes.c_int64()
+        check(self._lib.fr_index_count(self._handle(), ctypes.byref(out)))
+        return int(out.value)
+
+    def rows(self) -> int:
+        out = ctypes.c_int64()
+        check(self._lib.fr_index_rows(self._handle(), ctypes.byref(out)))
+        return int(out.value)
+
+    # -- host entry points -----------------------------------------------------------------
+    def upsert(self, vectors, keys) -> None:
+        v = np.ascontiguousarray(vectors, dtype=np.float32)
+        if v.ndim == 1:
+            v = v[None, :]
+        k = np.ascontiguousarray(keys, dtype=np.int64).reshape(-1)
+        if v.ndim != 2 or v.shape[1] != self.dim:
+            raise ValueError(f"expected vectors of shape (n, {self.dim}), got {v.shape}")
+        if k.shape[0] != v.shape[0]:
+            raise ValueError("one key per vector required")
+        check(self._lib.fr_index_upsert(self._handle(), v.ctypes.data, k.ctypes.data, v.shape[0]))
+
+    def delete(self, keys) -> int:
+        k = np.ascontiguousarray(keys, dtype=np.int64).reshape(-1)
+        out = ctypes.c_int64()
+        check(self._lib.fr_index_delete(self._handle(), k.ctypes.data, k.shape[0], ctypes.byref(out)))
+        return int(out.value)
+
+    def search(self, queries, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Host buffers in, host buffers out (H2D/D2H inside): (dist [B,k] fp32, keys [B,k] int64)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"expected queries of shape (B, {self.dim}), got {q.shape}")
+        b = q.shape[0]
+        dist = np.empty((b, k), dtype=np.float32)
+        keys = np.empty((b, k), dtype=np.int64)
+        check(self._lib.fr_index_search(self._handle(), q.ctypes.data, b, int(k), dist.ctypes.data,
+                                        keys.ctypes.data))
+        return dist, keys
+
+    def search_raw(self, q_ptr: int, b: int, k: int, dist_ptr: int, keys_ptr: int) -> None:
+        """Same call on caller-owned host buffers (e.g. pinned torch tensors) -- no allocation."""
+        check(self._lib.fr_index_search(self._handle(), q_ptr, int(b), int(k), dist_ptr, keys_ptr))
+
+    def get_rows(self, first_row: int, n: int) -> Tuple[np.ndarray, np.ndarray]:
+        vecs = np.empty((n, self.dim), dtype=np.float32)
+        keys = np.empty((n,), dtype=np.int64)
+        check(self._lib.fr_index_get_rows(self._handle(), int(first_row), int(n), vecs.ctypes.data,
+                                          keys.ctypes.data))
+        return vecs, keys
+
+    # -- device entry points (torch tensors own the memory) --------------------------------------
+    def _check_dev(self, t, dtype, what):
+        import torch
+
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.device.index == self.device):
+            raise ValueError(f"{what} must be a CUDA tensor on device {self.device}")
+        if t.dtype != dtype or not t.is_contiguous():
+            raise ValueError(f"{what} must be contiguous {dtype}")
+
+    def append_device(self, vectors, keys=None, first_key: int = 0, stream=None) -> None:
+        import torch
+
+        self._check_dev(vectors, torch.float32, "vectors")
+        if vectors.ndim != 2 or vectors.shape[1] != self.dim:
+            raise ValueError(f"expected vectors of shape (n, {self.dim})")
+        kp = None
+        if keys is not None:
+            self._check_dev(keys, torch.int64, "keys")
+            kp = keys.data_ptr()
+        check(self._lib.fr_index_append_device(self._handle(), vectors.data_ptr(), kp, int(first_key),
+                                               vectors.shape[0], _stream_ptr(stream)))
+
+    def search_device(self, queries, k: int, out_dist=None, out_keys=None, stream=None):
+        import torch
+
+        self._check_dev(queries, torch.float32, "queries")
+        b = queries.shape[0]
+        if out_dist is None:
+            out_dist = torch.empty((b, k), dtype=torch.float32, device=queries.device)
+        if out_keys is None:
+            out_keys = torch.empty((b, k), dtype=torch.int64, device=queries.device)
+        check(self._lib.fr_index_search_device(self._handle(), queries.data_ptr(), b, int(k),
+                                               out_dist.data_ptr(), out_keys.data_ptr(), _stream_ptr(stream)))
+        return out_dist, out_keys
+
+    def search_partial_device(self, queries, k: int, out_packed, out_keys, stream=None) -> None:
+        """Local top-k in mergeable form (step 1 of the row-sharded search).
+        out_packed / out_keys: int64 tensors of B*k elements (packed keys are raw uint64 bits)."""
+        import torch
+
+        self._check_dev(queries, torch.float32, "queries")
+        check(self._lib.fr_index_search_partial_device(self._handle(), queries.data_ptr(), queries.shape[0],
+                                                       int(k), out_packed.data_ptr(), out_keys.data_ptr(),
+                                                       _stream_ptr(stream)))
+
+
+def merge_shards_device(device: int, space: str, packed, keys, shard_stride: int, g: int, b: int, k: int,
+                        out_dist, out_keys, stream=None) -> None:
+    """Step 2 of the row-sharded search: merge G gathered lists (K3 in SHARDS mode)."""
+    lib = _lib.load()
+    check(lib.fr_merge_shards_device(int(device), _METRICS[canonical_space(space)], packed.data_ptr(),
+                                     keys.data_ptr(), int(shard_stride), int(g), int(b), int(k),
+                                     out_dist.data_ptr(), out_keys.data_ptr(), _stream_ptr(stream)))
+
+
+def rrf_fuse_host(keys: np.ndarray, k_rrf: int = 60, k_out: int = 10, device: int = 0):
+    """keys: [L, B, kp] int64 (-1 = empty).  Returns (score [B,k_out] fp64, keys [B,k_out])."""
+    lib = _lib.load()
+    a = np.ascontiguousarray(keys, dtype=np.int64)
+    if a.ndim != 3:
+        raise ValueError("keys must be [L, B, kp]")
+    l, b, kp = a.shape
+    sc = np.zeros((b, k_out), dtype=np.float64)
+    ok = np.full((b, k_out), -1, dtype=np.int64)
+    check(lib.fr_rrf_fuse(int(device), a.ctypes.data, l, b, kp, int(k_rrf), int(k_out), sc.ctypes.data,
+                          ok.ctypes.data))
+    return sc, ok
+
+
+def rrf_fuse_device(keys, k_rrf: int = 60, k_out: int = 10, stream=None):
+    """keys: CUDA int64 tensor [L, B, kp].  Returns CUDA tensors (score fp64 [B,k_out], keys)."""
+    import torch
+
+    lib = _lib.load()
+    if not (keys.is_cuda and keys.dtype == torch.int64 and keys.is_contiguous() and keys.ndim == 3):
+        raise ValueError("keys must be a contiguous CUDA int64 tensor [L, B, kp]")
+    l, b, kp = keys.shape
+    sc = torch.empty((b, k_out), dtype=torch.float64, device=keys.device)
+    ok = torch.empty((b, k_out), dtype=torch.int64, device=keys.device)
+    check(lib.fr_rrf_fuse_device(keys.device.index, keys.data_ptr(), l, b, kp, int(k_rrf), int(k_out),
+                                 sc.data_ptr(), ok.data_ptr(), _stream_ptr(stream)))
+    return sc, ok
+
+
+__all__ = ["ShardIndex", "canonical_space", "merge_shards_device", "rrf_fuse_host", "rrf_fuse_device", "FR_MAX_K"]

@@ -1,0 +1,144 @@
+/*
+ * fr_index.h -- C ABI of the B200-native exact vector-search backend (libfrb200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of hawkai10/Financial-RAG: the child-chunk
+ * similarity scan + top-k + cross-collection fusion that the reference runs inside the
+ * third-party chromadb wheel.  Every entry point below names the reference call it replaces
+ * (paths relative to the reference tree).  The reference is pure Python, so its binding is the
+ * ctypes stub in INTEGRATION.md / financial_rag_b200/_lib.py.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - every function returns 0 on success, a negative FR_E* code otherwise; fr_last_error()
+ *     returns a thread-local, NUL-terminated description of the last failure on this thread.
+ *   - "host" entry points take host pointers and include the host<->device copies;
+ *     "_device" entry points take device pointers on the index's device and enqueue on `stream`
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream) without synchronising.
+ *   - keys are int64 (the reference's Snowflake child ids, parent_child/snowflake_id.py:27-49,
+ *     are int64-representable decimal strings); FR_KEY_NONE (-1) pads short result lists.
+ *   - distances follow chromadb/hnswlib: cosine d = 1 - <a/|a|, b/|b|>, ip d = 1 - <a,b>,
+ *     l2 d = sum (a-b)^2.  Results are sorted by ascending distance, ties by insertion order.
+ *   - all entry points are thread-safe; calls on one index are serialised internally.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef FR_INDEX_H
+#define FR_INDEX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FR_ABI_VERSION 1
+
+typedef struct fr_index fr_index; /* opaque */
+
+/* metric vocabulary: parent_child/pgvector_child_store.py:7-26, chroma_child_store.py:34 */
+enum { FR_COSINE = 0, FR_L2 = 1, FR_IP = 2 };
+/* storage type of the corpus matrix in HBM */
+enum { FR_BF16 = 0, FR_F32 = 1 };
+/* kernel selection for fr_index_set_option("path", v): tests and bench pin a regime with it */
+enum { FR_PATH_AUTO = 0, FR_PATH_STREAM = 1, FR_PATH_MMA = 2 };
+
+enum {
+    FR_OK = 0,
+    FR_EINVAL = -1,  /* bad argument */
+    FR_ECUDA = -2,   /* CUDA runtime / driver error (message holds cudaGetErrorString) */
+    FR_ENOMEM = -3,  /* host or device allocation failed */
+    FR_ENODEV = -4,  /* no CUDA device / wrong architecture (needs sm_100) */
+    FR_EUNSUP = -5   /* valid request this build does not implement (e.g. k > FR_MAX_K) */
+};
+
+#define FR_KEY_NONE ((int64_t)-1)
+#define FR_MAX_K 128
+#define FR_MAX_DIM 4096
+
+int fr_abi_version(void);
+const char *fr_last_error(void);
+
+/* Number of kernels this library has launched in this process (all indices); bench.py reports
+ * the delta over its timed region as "gpu_launches". */
+int64_t fr_launch_count(void);
+
+/* ---- collection lifecycle ---------------------------------------------------------------
+ * Replaces chromadb.PersistentClient(...).get_or_create_collection(name,
+ * metadata={"hnsw:space": "cosine"})            parent_child/chroma_child_store.py:32-34
+ * dim: vector width (384 for bge-small / gte-small); metric: FR_COSINE|FR_L2|FR_IP;
+ * dtype: FR_BF16|FR_F32; device: CUDA ordinal; reserve_rows: rows to pre-allocate (0 = grow). */
+int fr_index_create(int dim, int metric, int dtype, int device, int64_t reserve_rows,
+                    fr_index **out);
+int fr_index_destroy(fr_index *idx);
+int fr_index_reserve(fr_index *idx, int64_t rows);
+int fr_index_set_option(fr_index *idx, const char *name, int64_t value);
+
+/* Replaces Collection.count()                     parent_child/chroma_child_store.py:76-80
+ * count = live rows; rows = physical rows including deleted ones. */
+int fr_index_count(fr_index *idx, int64_t *out_count);
+int fr_index_rows(fr_index *idx, int64_t *out_rows);
+
+/* Replaces Collection.upsert(ids, embeddings, metadatas)   chroma_child_store.py:54-59
+ * vecs: n x dim row-major fp32 (host), keys: n int64 (host).  An existing key is overwritten in
+ * place (keeps its insertion position); a new key is appended.  Duplicates inside one call:
+ * last one wins.  Cosine collections normalise rows on the device (x * 1/(|x| + 1e-30)). */
+int fr_index_upsert(fr_index *idx, const float *vecs, const int64_t *keys, int64_t n);
+
+/* Replaces Collection.delete(ids)                 chroma_child_store.py:58, multivector_store.py:138 */
+int fr_index_delete(fr_index *idx, const int64_t *keys, int64_t n, int64_t *out_deleted);
+
+/* Bulk load from device memory (bench / sharded ingest): appends n rows without key lookup;
+ * the caller guarantees the keys are new.  d_keys may be NULL: keys = first_key + i. */
+int fr_index_append_device(fr_index *idx, const float *d_vecs, const int64_t *d_keys,
+                           int64_t first_key, int64_t n, void *stream);
+
+/* Read back what the index stores (tests: parity of the ingest kernel, storage-exact oracle).
+ * out_vecs: n x dim fp32 (bf16 rows are widened), out_keys: n (INT64_MIN marks a deleted row). */
+int fr_index_get_rows(fr_index *idx, int64_t first_row, int64_t n, float *out_vecs,
+                      int64_t *out_keys);
+
+/* ---- the hot path -------------------------------------------------------------------------
+ * Replaces Collection.query(query_embeddings=[...], n_results=k,
+ *                           include=["metadatas","distances"])
+ *                                  parent_child/chroma_child_store.py:63, multivector_store.py:151
+ * queries: B x dim fp32; out_dist: B x k fp32 ascending; out_keys: B x k (FR_KEY_NONE padded,
+ * matching pad distances are +inf).  1 <= k <= FR_MAX_K, B >= 0. */
+int fr_index_search(fr_index *idx, const float *queries, int B, int k, float *out_dist,
+                    int64_t *out_keys);
+int fr_index_search_device(fr_index *idx, const float *d_queries, int B, int k,
+                           float *d_out_dist, int64_t *d_out_keys, void *stream);
+
+/* Row-sharded search, step 1 (per GPU): local top-k in mergeable form.  d_out_packed: B x k
+ * uint64 = (order-preserving score bits << 32) | ~local_row, descending, 0 = empty slot;
+ * d_out_keys: B x k int64.  Step 2 (after an all-gather of both arrays over NCCL):
+ * fr_merge_shards_device merges G shards' lists, ties -> lower shard, then lower local row, so
+ * the result is identical to a single-GPU search for any G.
+ * d_packed: [G][B][k] uint64 with `shard_stride_bytes` between shards; same for d_keys. */
+int fr_index_search_partial_device(fr_index *idx, const float *d_queries, int B, int k,
+                                   uint64_t *d_out_packed, int64_t *d_out_keys, void *stream);
+int fr_merge_shards_device(int device, int metric, const uint64_t *d_packed,
+                           const int64_t *d_keys, int64_t shard_stride_elems, int G, int B, int k,
+                           float *d_out_dist, int64_t *d_out_keys, void *stream);
+
+/* Scan-kernel timing for the roofline line of bench.py.  After fr_index_set_option("profile", 1)
+ * every search brackets its scan launches (K1 or K2, not the query normalisation or the merge)
+ * with CUDA events on the stream they run on.  fr_index_profile_read waits for those events,
+ * returns the summed device time, the number of scan kernel launches and of searches they
+ * belong to, and resets the counters. */
+int fr_index_profile_read(fr_index *idx, double *out_scan_ms, int64_t *out_scan_launches,
+                          int64_t *out_searches);
+
+/* ---- cross-collection fusion ----------------------------------------------------------------
+ * Replaces the RRF loops of parent_child/retriever.py:94-107 and rag_backend.py:720-731:
+ * score[key] = sum over lists, in list order, of 1.0/(k_rrf + rank) (rank from 1, fp64);
+ * output sorted by score descending, ties in first-seen order, cut to k_out.
+ * keys: [L][B][kp] int64 (FR_KEY_NONE entries are skipped); out_*: [B][k_out]
+ * (FR_KEY_NONE / 0.0 padded). */
+int fr_rrf_fuse(int device, const int64_t *keys, int L, int B, int kp, int k_rrf, int k_out,
+                double *out_score, int64_t *out_keys);
+int fr_rrf_fuse_device(int device, const int64_t *d_keys, int L, int B, int kp, int k_rrf,
+                       int k_out, double *d_out_score, int64_t *d_out_keys, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FR_INDEX_H */
