@@ -1,0 +1,441 @@
+#!/usr/bin/env python3
+"""bench.py -- QPS of exact top-10 over a synthetic 100M x 384 bf16 corpus (BASELINE.json cfg4).
+
+    python bench.py --gpus 1 --steps 50 --warmup 5                    # this repo's CUDA path
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                              # CPU arm (see below)
+
+A "step" is one search of one query batch over the whole corpus.  The corpus (fixed total size,
+row-sharded over the N ranks => "strong" scaling) is generated on the device, chunk by chunk, from
+fixed seeds, so every N sees the same 100M rows; it is far larger than L2 (>= 9.6 GB per GPU), so
+no flush is needed between timed iterations.
+
+  value     whole-job QPS with the query block already resident in HBM (CUDA events, max over ranks)
+  e2e       the same through the host-buffer C-ABI call (fr_index_search; for N>1 rank 0's pinned
+            query block -> H2D -> NCCL broadcast -> scan -> all-gather -> merge -> D2H to rank 0)
+  roofline  the scan kernel alone: algorithmic bytes (rows_per_gpu * 768) / its mean launch time,
+            bracketed by CUDA events inside the library on the launching stream
+  cpu_baseline / --impl reference
+            The reference's own path is chromadb's HNSW (a third-party wheel that is not in this
+            image), so the CPU arm is the oracle port of the exact scan the north star
+            names as the reference: numpy fp32 ``Q @ C.T`` + top-k with all BLAS threads, and the
+            OpenMP C restatement; the faster of the two is reported.  It is timed on a bounded
+            row sample and scaled linearly to the full corpus (an exact scan is linear in rows).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DIM = 384
+CHUNK_ROWS = 500_000          # global generation chunk; seed = 1234 + chunk index
+DEFAULT_ROWS = 100_000_000    # BASELINE.json: "exact top-10 over 100M x 384"
+DEFAULT_BATCH = 4             # largest batch the streaming kernel serves in one corpus pass
+METRIC = "QPS exact top-10 over 100Mx384 bf16 (cosine), row-sharded"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=DEFAULT_ROWS)
+    ap.add_argument("--batch", type=int, default=DEFAULT_BATCH)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--path", default="auto", choices=["auto", "stream", "mma"])
+    ap.add_argument("--sweep", default="1", help="extra batch sizes measured briefly (comma list, '' = none)")
+    ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+def workload_name(args):
+    return (f"cfg4: synthetic unit-norm {args.rows}x{DIM} {args.dtype} corpus, cosine top-{args.k}, "
+            f"query batch {args.batch}")
+
+
+def gen_chunk(torch, device, c, rows):
+    g = torch.Generator(device=device).manual_seed(1234 + c)
+    return torch.randn((rows, DIM), generator=g, device=device, dtype=torch.float32)
+
+
+def planted_rows(n_rows, batch):
+    import numpy as np
+
+    return np.random.default_rng(99).integers(0, n_rows, size=batch)
+
+
+def make_queries(torch, device, n_rows, batch):
+    """seed 4321 Gaussian queries; every even one is a noisy copy of a corpus row."""
+    g = torch.Generator(device=device).manual_seed(4321)
+    q = torch.randn((batch, DIM), generator=g, device=device, dtype=torch.float32)
+    noise = torch.randn((batch, DIM), generator=g, device=device, dtype=torch.float32)
+    rows = planted_rows(n_rows, batch)
+    by_chunk = {}
+    for i in range(0, batch, 2):
+        by_chunk.setdefault(int(rows[i]) // CHUNK_ROWS, []).append(i)
+    for c, idxs in by_chunk.items():
+        lo = c * CHUNK_ROWS
+        chunk = gen_chunk(torch, device, c, min(CHUNK_ROWS, n_rows - lo))
+        for i in idxs:
+            q[i] = chunk[int(rows[i]) - lo] + 0.1 * noise[i]
+        del chunk
+    return q, rows
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.samples = []
+        self.proc = None
+        self.dev = device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.dev)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) >= 7:
+                self.samples.append(p)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        mhz, mx, reasons = [], None, set()
+        for p in self.samples:
+            try:
+                mhz.append(float(p[0]))
+                mx = float(p[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(mhz) if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(mhz)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained") or d["bf16_tflops"]), "measured"
+    except Exception:
+        return 6650.0, 1590.0, "fallback"
+
+
+def ncu_traffic(path_kind):
+    """dram bytes per scan launch from the committed ncu summary (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get(path_kind)
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_scan_qps(n_rows_full, batch, k, sample_rows, steps, warmup, torch=None, device=None):
+    """Exact fp32 scan on the host cores over a bounded row sample; QPS scaled to the full corpus."""
+    import numpy as np
+
+    from oracle import cscan
+    from oracle import exact_scan as ox
+
+    sample_rows = int(min(sample_rows, n_rows_full))
+    rng_rows = sample_rows
+    # the same synthetic rows as the GPU arm where a device is available, else numpy Gaussians
+    if torch is not None and device is not None:
+        parts = []
+        for c in range((rng_rows + CHUNK_ROWS - 1) // CHUNK_ROWS):
+            parts.append(gen_chunk(torch, device, c, min(CHUNK_ROWS, rng_rows - c * CHUNK_ROWS)).cpu().numpy())
+        corpus = np.concatenate(parts)
+        q = make_queries(torch, device, sample_rows, batch)[0].cpu().numpy()
+    else:
+        rng = np.random.default_rng(1234)
+        corpus = rng.standard_normal((rng_rows, DIM), dtype=np.float32)
+        q = rng.standard_normal((batch, DIM), dtype=np.float32)
+    corpus = ox.prepare_corpus(corpus, "cosine", "f32")
+    q = ox.prepare_queries(q, "cosine")
+    cores = os.cpu_count() or 1
+
+    def run_numpy():
+        return ox.exact_topk(q, corpus, k, "cosine", "f32", prepared=True)
+
+    def run_c():
+        return cscan.exact_topk_prepared(corpus, q, k, "cosine")
+
+    results = {}
+    for name, fn in (("numpy_sgemm", run_numpy), ("c_openmp", run_c)):
+        try:
+            for _ in range(max(1, min(warmup, 2))):
+                fn()
+            ts = []
+            for _ in range(max(1, steps)):
+                t0 = time.perf_counter()
+                fn()
+                ts.append(time.perf_counter() - t0)
+            results[name] = statistics.median(ts)
+        except Exception as e:  # the C port needs gcc/OpenMP on the box
+            results[name] = None
+            sys.stderr.write(f"[bench] cpu arm {name} unavailable: {e}\n")
+    best = min((t, n) for n, t in results.items() if t)
+    t_full = best[0] * (n_rows_full / sample_rows)
+    return {
+        "value": batch / t_full,
+        "unit": "queries/s",
+        "cores": cores,
+        "kind": "port",
+        "sample": (f"exact fp32 scan of {sample_rows} of {n_rows_full} rows x {batch} queries, "
+                   f"{best[1]} ({', '.join(f'{n}={t * 1e3:.0f}ms' for n, t in results.items() if t)}), "
+                   f"time scaled linearly to the full corpus"),
+        "ms_per_step_sample": best[0] * 1e3,
+    }
+
+
+def run_reference(args):
+    """--impl reference: the CPU exact scan (oracle port; chromadb is not installable offline)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch = device = None
+    try:
+        import torch as _t
+
+        if _t.cuda.is_available():
+            torch, device = _t, _t.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    except Exception:
+        pass
+    # bounded: ~1 s per step on 8 cores at the default sample
+    steps = max(1, min(args.steps, 20))
+    r = cpu_scan_qps(args.rows, args.batch, args.k, args.cpu_sample_rows, steps, args.warmup, torch, device)
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": r["value"], "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step_sample"] * (args.rows / min(args.cpu_sample_rows, args.rows)),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "rows": args.rows, "batch": args.batch, "k": args.k,
+                   "note": "reference arm = CPU exact scan (oracle port); Chroma HNSW is not runnable offline"},
+        "cpu_baseline": {k_: r[k_] for k_ in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 backend has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    import financial_rag_b200 as frb
+    from financial_rag_b200 import _lib
+    from financial_rag_b200.sharded import ShardedSearcher, shard_bounds
+
+    n, b, k = args.rows, args.batch, args.k
+    lo, hi = shard_bounds(n, world, rank, align=CHUNK_ROWS)
+    ix = frb.ShardIndex(dim=DIM, space="cosine", dtype=args.dtype, device=local_rank, reserve_rows=hi - lo)
+    ix.set_path(args.path)
+    t0 = time.time()
+    for c in range(lo // CHUNK_ROWS, (hi + CHUNK_ROWS - 1) // CHUNK_ROWS):
+        r0 = c * CHUNK_ROWS
+        chunk = gen_chunk(torch, device, c, min(CHUNK_ROWS, n - r0))
+        ix.append_device(chunk, None, first_key=r0)
+        del chunk
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
+    assert ix.count() == hi - lo
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def measure(batch, steps, warmup, profile=False):
+        q, planted = make_queries(torch, device, n, batch)
+        s = ShardedSearcher(ix, k, batch, space="cosine", device=device)
+        for _ in range(warmup):
+            s.search_device(q)
+        barrier()
+        if profile:
+            ix.profile_read()
+            ix.set_profile(True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        ev0.record()
+        for _ in range(steps):
+            d, kk = s.search_device(q)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=device)
+        launches = _lib.launch_count() - l0
+        scan = None
+        if profile:
+            ix.set_profile(False)
+            scan = ix.profile_read()
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item()), launches, scan, (q, planted, d.clone(), kk.clone(), s)
+
+    # ---- headline: device-resident queries ----------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches, scan, (q, planted, d, kk, searcher) = measure(b, args.steps, max(args.warmup, 3), profile=True)
+    clocks = sampler.stop() if rank == 0 else None
+    value = b * args.steps / (ms / 1e3)
+
+    # ---- sanity of what was timed (outside the timed region) -----------------------------------
+    kk_h, d_h = kk.cpu().numpy(), d.cpu().numpy()
+    verified = bool((np.diff(d_h, axis=1) >= 0).all())
+    for i in range(0, b, 2):  # planted neighbours must come back first, with a high score
+        verified &= int(kk_h[i, 0]) == int(planted[i]) and (1.0 - float(d_h[i, 0])) > 0.9
+    for i in range(1, b, 2):
+        verified &= (1.0 - float(d_h[i, 0])) < 0.6
+
+    # ---- e2e: host buffers through the public call -----------------------------------------------
+    q_pin = torch.empty((b, DIM), dtype=torch.float32).pin_memory()
+    q_pin.copy_(q.cpu())
+    od_pin = torch.empty((b, k), dtype=torch.float32).pin_memory()
+    ok_pin = torch.empty((b, k), dtype=torch.int64).pin_memory()
+    q_dev = torch.empty_like(q)
+    e2e_steps = args.steps
+
+    def e2e_once():
+        if world == 1:
+            ix.search_raw(q_pin.data_ptr(), b, k, od_pin.data_ptr(), ok_pin.data_ptr())
+        else:
+            searcher.search_host(q_pin, q_dev, od_pin, ok_pin)
+
+    for _ in range(3):
+        e2e_once()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(e2e_steps):
+        e2e_once()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms_e2e = torch.tensor([ev0.elapsed_time(ev1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    barrier()
+    e2e_value = b * e2e_steps / (float(ms_e2e.item()) / 1e3)
+    if rank == 0:
+        verified &= bool((ok_pin.numpy() == kk_h).all())
+
+    # ---- roofline of the scan kernel ---------------------------------------------------------------
+    hbm_peak, tf_peak, peak_kind = measured_peaks()
+    rows_local = hi - lo
+    elem = 2 if args.dtype == "bf16" else 4
+    scan_ms, scan_launches, _ = scan
+    avg_launch_s = (scan_ms / max(scan_launches, 1)) / 1e3
+    achieved = rows_local * DIM * elem / avg_launch_s / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+        "traffic": ncu_traffic("stream"), "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+        "kernel": "scan_stream_kernel", "bytes_per_launch": rows_local * DIM * elem,
+        "avg_launch_ms": avg_launch_s * 1e3, "launches_timed": scan_launches,
+        "scan_share_of_step": scan_ms / ms,
+    }
+
+    # ---- brief sweep over other batch sizes ---------------------------------------------------------
+    sweep = []
+    for sb in [int(x) for x in args.sweep.split(",") if x.strip()]:
+        if sb == b:
+            continue
+        sms, _, sscan, _ = measure(sb, max(3, min(10, args.steps)), 3, profile=True)
+        st = max(3, min(10, args.steps))
+        s_avg = (sscan[0] / max(sscan[1], 1)) / 1e3
+        sweep.append({"batch": sb, "qps": sb * st / (sms / 1e3), "ms_per_step": sms / st,
+                      "scan_gbs": rows_local * DIM * elem / s_avg / 1e9,
+                      "scan_frac_of_hbm_peak": rows_local * DIM * elem / s_avg / 1e9 / hbm_peak})
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_scan_qps(n, b, k, args.cpu_sample_rows, 5, 1, torch, device)
+        cpu = {k_: r[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(args), "rows": n, "rows_per_gpu": rows_local, "dim": DIM,
+                       "batch": b, "k": k, "space": "cosine", "parallelism": f"row-shard x{world}",
+                       "path": args.path, "l2_policy": "inputs larger than L2 (>= 9.6 GB per GPU), no flush",
+                       "build_s": round(t_build, 2)},
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": b * DIM * 4,
+                    "d2h_bytes_per_step": b * k * 12, "ms_per_step": float(ms_e2e.item()) / e2e_steps},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "verified": verified,
+            "sweep": sweep,
+        }
+        print(json.dumps(line))
+    ix.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -99,7 +99,20 @@ struct PinBuf {
     }
 };
 
+// cudaGetDeviceProperties costs milliseconds; the answer never changes, so ask once per device.
+struct DevInfo {
+    int state = 0;  // 0 unknown, 1 ok, -1 not sm_100
+    int sm_count = 0, major = 0, minor = 0;
+};
+std::mutex g_dev_mu;
+DevInfo g_dev[64];
+
 int check_device(int device, int *sm_count) {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (device >= 0 && device < 64 && g_dev[device].state == 1) {
+        if (sm_count) *sm_count = g_dev[device].sm_count;
+        return FR_OK;
+    }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
@@ -107,14 +120,23 @@ int check_device(int device, int *sm_count) {
         return fail(FR_ENODEV, "no CUDA device available (%s); this backend has no CPU fallback",
                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     }
-    if (device < 0 || device >= n) return fail(FR_EINVAL, "device %d out of range (0..%d)", device, n - 1);
-    cudaDeviceProp prop;
-    e = cudaGetDeviceProperties(&prop, device);
-    if (e != cudaSuccess) return fail(FR_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
-    if (prop.major != 10)
-        return fail(FR_ENODEV, "device %d is sm_%d%d; libfrb200 is built for sm_100a (B200) only", device,
-                    prop.major, prop.minor);
-    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (device < 0 || device >= n || device >= 64) return fail(FR_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    DevInfo &d = g_dev[device];
+    if (d.state == 0) {
+        int major = 0, minor = 0, sms = 0;
+        e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (e != cudaSuccess) return fail(FR_ECUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+        d.major = major;
+        d.minor = minor;
+        d.sm_count = sms;
+        d.state = (major == 10) ? 1 : -1;
+    }
+    if (d.state != 1)
+        return fail(FR_ENODEV, "device %d is sm_%d%d; libfrb200 is built for sm_100a (B200) only", device, d.major,
+                    d.minor);
+    if (sm_count) *sm_count = d.sm_count;
     return FR_OK;
 }
 

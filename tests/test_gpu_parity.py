@@ -193,7 +193,7 @@ def test_ingest_kernel_matches_oracle_preparation(frb, dtype):
         assert np.isfinite(got).all()
         if space == "ip" or dtype == "f32":
             # ip: stored verbatim (bf16: RNE rounding must match bit for bit)
-            tol = 0.0 if space == "ip" else 3e-7
+            tol = 0.0 if space == "ip" else 6e-7
             np.testing.assert_allclose(got, want, rtol=tol, atol=0.0 if space == "ip" else 1e-9)
         else:
             # cosine + bf16: the fp32 norm may differ in the last ulp from numpy's summation order,
@@ -217,7 +217,7 @@ def test_upsert_delete_semantics(frb):
     model = corpus[:501].copy()
     model[7] = corpus[511]
     model[500] = corpus[512]
-    np.testing.assert_allclose(got, ox.prepare_corpus(model, "cosine"), rtol=3e-7, atol=1e-9)
+    np.testing.assert_allclose(got, ox.prepare_corpus(model, "cosine"), rtol=6e-7, atol=1e-9)
     assert gk[7] == keys[7] and gk[500] == keys[501]
     q = make_queries(4, model, seed=5)
     q[0] = model[7]
