@@ -157,11 +157,12 @@ def measured_peaks():
         return 6650.0, 1590.0, "fallback"
 
 
-def ncu_traffic(path_kind):
-    """dram bytes per scan launch from the committed ncu summary (profiles/), or None."""
+def ncu_traffic(path_kind, rows_local):
+    """DRAM bytes per scan launch (dram__bytes_read.sum + dram__bytes_write.sum from the committed
+    ``ncu --set full`` capture under profiles/, measured per row), scaled to this launch; or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get(path_kind)
+            return float(json.load(f)[path_kind]["bytes_per_row"]) * rows_local
     except Exception:
         return None
 
@@ -381,7 +382,7 @@ def run_ours(args):
     achieved = rows_local * DIM * elem / avg_launch_s / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-        "traffic": ncu_traffic("stream"), "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+        "traffic": ncu_traffic("stream", rows_local), "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
         "kernel": "scan_stream_kernel", "bytes_per_launch": rows_local * DIM * elem,
         "avg_launch_ms": avg_launch_s * 1e3, "launches_timed": scan_launches,
         "scan_share_of_step": scan_ms / ms,
