@@ -159,6 +159,8 @@ struct fr_index {
     cudaStream_t stream = nullptr;   // host-path stream
     cudaEvent_t last_use = nullptr;  // orders scratch reuse across caller streams
     DevBuf q_raw, q_prep, q_keys, partials, out_dist, out_keys, stage_vecs, stage_keys, stage_rows;
+    DevBuf q_bf16, err_bound, sel, sel_keys, flags, fail, fb_partials;  // K2 path
+    int mma_min_batch = 3;  // FR_PATH_AUTO: batches at least this large go to the tensor-core scan
     PinBuf pin;
     std::mutex mu;
     bool profile = false;
@@ -243,12 +245,195 @@ int rebuild_keymap(fr_index *ix) {
     return FR_OK;
 }
 
+// profiling brackets around the scan launches (bench.py's roofline line)
+struct ProfScope {
+    fr_index *ix;
+    cudaStream_t s;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches_before = 0;
+    int begin() {
+        if (!ix->profile) return FR_OK;
+        for (cudaEvent_t *ev : {&ev0, &ev1}) {
+            if (!ix->prof_pool.empty()) {
+                *ev = ix->prof_pool.back();
+                ix->prof_pool.pop_back();
+            } else {
+                FR_CUDA(cudaEventCreate(ev));
+            }
+        }
+        FR_CUDA(cudaEventRecord(ev0, s));
+        launches_before = fr_launch_count();
+        return FR_OK;
+    }
+    int end() {
+        if (!ix->profile) return FR_OK;
+        FR_CUDA(cudaEventRecord(ev1, s));
+        ix->prof_events.emplace_back(ev0, ev1);
+        ix->prof_launches += fr_launch_count() - launches_before;
+        return FR_OK;
+    }
+};
+
+bool mma_eligible(const fr_index *ix, int k) {
+    return ix->dtype == FR_BF16 && ix->dim == 384 && ix->metric == FR_COSINE && fr::scan_mma_ksel(k) != 0 &&
+           ix->rows > 0;
+}
+
+// K1 path: CUDA-core streaming scan, ceil(B/4) corpus passes.
+int search_stream(fr_index *ix, const float *q, int B, int k, float *d_out_dist, uint64_t *d_out_packed,
+                  int64_t *d_out_keys, cudaStream_t s) {
+    fr::ScanArgs sa{};
+    sa.corpus = ix->corpus;
+    sa.keys_or_null = ix->n_deleted > 0 ? ix->keys : nullptr;
+    sa.queries = q;
+    sa.n_rows = ix->rows;
+    sa.dim = ix->dim;
+    sa.bf16 = ix->dtype == FR_BF16;
+    sa.l2 = ix->metric == FR_L2;
+    sa.k = k;
+    sa.nq_total = B;
+    sa.stream = s;
+    sa.grid = fr::scan_stream_plan_grid(sa, ix->sm_count);
+    FR_CUDA(ix->partials.need(static_cast<size_t>(sa.grid) * B * k * sizeof(uint64_t)));
+    sa.partials = static_cast<uint64_t *>(ix->partials.p);
+    ProfScope prof{ix, s};
+    int rc = prof.begin();
+    if (rc != FR_OK) return rc;
+    FR_CUDA(fr::launch_scan_stream(sa));
+    rc = prof.end();
+    if (rc != FR_OK) return rc;
+
+    fr::MergeArgs ma{};
+    ma.packed = sa.partials;
+    ma.P = sa.grid;
+    ma.shard_stride = static_cast<int64_t>(B) * k;
+    ma.B = B;
+    ma.k = k;
+    ma.shards = false;
+    ma.row_keys = ix->keys;
+    ma.l2 = sa.l2;
+    ma.out_dist = d_out_dist;
+    ma.out_packed = d_out_packed;
+    ma.out_keys = d_out_keys;
+    ma.stream = s;
+    FR_CUDA(fr::launch_merge_topk(ma));
+    return FR_OK;
+}
+
+// K2 path: tensor-core selection of k' candidates per query, exact fp32-query rescoring with
+// certification, and a device-side re-scan of whatever could not be certified.
+int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, uint64_t *d_out_packed,
+               int64_t *d_out_keys, cudaStream_t s) {
+    const int ksel = fr::scan_mma_ksel(k);
+    const int nq_pad = ((B + 127) / 128) * 128;
+    const int grid = fr::scan_mma_plan_grid(ix->sm_count, ix->rows);
+    FR_CUDA(ix->q_bf16.need(static_cast<size_t>(nq_pad) * ix->dim * 2));
+    FR_CUDA(ix->err_bound.need(static_cast<size_t>(B) * sizeof(float)));
+    FR_CUDA(ix->partials.need(static_cast<size_t>(grid) * B * ksel * sizeof(uint64_t)));
+    FR_CUDA(ix->sel.need(static_cast<size_t>(B) * ksel * sizeof(uint64_t)));
+    FR_CUDA(ix->sel_keys.need(static_cast<size_t>(B) * ksel * sizeof(int64_t)));
+    FR_CUDA(ix->flags.need(static_cast<size_t>(B)));
+    FR_CUDA(ix->fail.need(static_cast<size_t>(B + 1) * sizeof(int)));
+    int *fail_count = static_cast<int *>(ix->fail.p);
+    int *fail_list = fail_count + 1;
+    FR_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), s));
+    FR_CUDA(fr::launch_prep_queries(q, B, nq_pad, ix->q_bf16.p, static_cast<float *>(ix->err_bound.p), s));
+
+    fr::MmaScanArgs ms{};
+    ms.corpus = ix->corpus;
+    ms.keys_or_null = ix->n_deleted > 0 ? ix->keys : nullptr;
+    ms.queries_bf16 = ix->q_bf16.p;
+    ms.nq_pad = nq_pad;
+    ms.n_rows = ix->rows;
+    ms.nq_total = B;
+    ms.ksel = ksel;
+    ms.partials = static_cast<uint64_t *>(ix->partials.p);
+    ms.grid = grid;
+    ms.stream = s;
+    ProfScope prof{ix, s};
+    int rc = prof.begin();
+    if (rc != FR_OK) return rc;
+    FR_CUDA(fr::launch_scan_mma(ms));
+    rc = prof.end();
+    if (rc != FR_OK) return rc;
+
+    fr::MergeArgs ma{};
+    ma.packed = ms.partials;
+    ma.P = grid;
+    ma.shard_stride = static_cast<int64_t>(B) * ksel;
+    ma.B = B;
+    ma.k = ksel;
+    ma.shards = false;
+    ma.row_keys = ix->keys;
+    ma.l2 = false;
+    ma.out_packed = static_cast<uint64_t *>(ix->sel.p);
+    ma.out_keys = static_cast<int64_t *>(ix->sel_keys.p);
+    ma.stream = s;
+    FR_CUDA(fr::launch_merge_topk(ma));
+
+    fr::RescoreArgs ra{};
+    ra.sel = static_cast<const uint64_t *>(ix->sel.p);
+    ra.ksel = ksel;
+    ra.queries = q;
+    ra.corpus = ix->corpus;
+    ra.row_keys = ix->keys;
+    ra.err_bound = static_cast<const float *>(ix->err_bound.p);
+    ra.B = B;
+    ra.k = k;
+    ra.out_dist = d_out_dist;
+    ra.out_packed = d_out_packed;
+    ra.out_keys = d_out_keys;
+    ra.flags = static_cast<uint8_t *>(ix->flags.p);
+    ra.fail_count = fail_count;
+    ra.fail_list = fail_list;
+    ra.stream = s;
+    FR_CUDA(fr::launch_rescore(ra));
+
+    // safety net: both launches return immediately when every query was certified
+    fr::ScanArgs sa{};
+    sa.corpus = ix->corpus;
+    sa.keys_or_null = ms.keys_or_null;
+    sa.queries = q;
+    sa.n_rows = ix->rows;
+    sa.dim = ix->dim;
+    sa.bf16 = true;
+    sa.l2 = false;
+    sa.k = k;
+    sa.nq_total = B;
+    sa.stream = s;
+    sa.grid = fr::scan_stream_fallback_grid(sa, ix->sm_count);
+    FR_CUDA(ix->fb_partials.need(static_cast<size_t>(sa.grid) * B * k * sizeof(uint64_t)));
+    sa.partials = static_cast<uint64_t *>(ix->fb_partials.p);
+    FR_CUDA(fr::launch_scan_stream_fallback(sa, fail_count, fail_list));
+    fr::MergeArgs mf{};
+    mf.packed = sa.partials;
+    mf.P = sa.grid;
+    mf.shard_stride = static_cast<int64_t>(B) * k;
+    mf.B = B;
+    mf.k = k;
+    mf.shards = false;
+    mf.row_keys = ix->keys;
+    mf.l2 = false;
+    mf.out_dist = d_out_dist;
+    mf.out_packed = d_out_packed;
+    mf.out_keys = d_out_keys;
+    mf.only_flagged = static_cast<const uint8_t *>(ix->flags.p);
+    mf.stream = s;
+    FR_CUDA(fr::launch_merge_topk(mf));
+    return FR_OK;
+}
+
 // Core of every search entry point: device queries in, merged lists out, all on stream `s`.
 int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *d_out_dist,
                      uint64_t *d_out_packed, int64_t *d_out_keys, cudaStream_t s) {
     if (B == 0) return FR_OK;
-    if (ix->path == FR_PATH_MMA)
-        return fail(FR_EUNSUP, "FR_PATH_MMA (tcgen05 scan) is not built into this library yet");
+    const bool eligible = mma_eligible(ix, k);
+    if (ix->path == FR_PATH_MMA && !eligible)
+        return fail(FR_EUNSUP,
+                    "FR_PATH_MMA serves bf16 x 384 cosine collections with k <= 32 and at least one row "
+                    "(this one: dtype %d, dim %d, metric %d, k %d, rows %lld)",
+                    ix->dtype, ix->dim, ix->metric, k, (long long)ix->rows);
+    const bool use_mma = eligible && (ix->path == FR_PATH_MMA || (ix->path == FR_PATH_AUTO && B >= ix->mma_min_batch));
     const size_t qbytes = static_cast<size_t>(B) * ix->dim * sizeof(float);
     const float *q = d_queries;
     if (ix->metric == FR_COSINE) {
@@ -266,55 +451,8 @@ int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *
         FR_CUDA(fr::launch_ingest(ia));
         q = static_cast<const float *>(ix->q_prep.p);
     }
-    fr::ScanArgs sa{};
-    sa.corpus = ix->corpus;
-    sa.keys_or_null = ix->n_deleted > 0 ? ix->keys : nullptr;
-    sa.queries = q;
-    sa.n_rows = ix->rows;
-    sa.dim = ix->dim;
-    sa.bf16 = ix->dtype == FR_BF16;
-    sa.l2 = ix->metric == FR_L2;
-    sa.k = k;
-    sa.nq_total = B;
-    sa.stream = s;
-    sa.grid = fr::scan_stream_plan_grid(sa, ix->sm_count);
-    FR_CUDA(ix->partials.need(static_cast<size_t>(sa.grid) * B * k * sizeof(uint64_t)));
-    sa.partials = static_cast<uint64_t *>(ix->partials.p);
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (ix->profile) {
-        for (cudaEvent_t *ev : {&ev0, &ev1}) {
-            if (!ix->prof_pool.empty()) {
-                *ev = ix->prof_pool.back();
-                ix->prof_pool.pop_back();
-            } else {
-                FR_CUDA(cudaEventCreate(ev));
-            }
-        }
-        FR_CUDA(cudaEventRecord(ev0, s));
-    }
-    const int64_t launches_before = fr_launch_count();
-    FR_CUDA(fr::launch_scan_stream(sa));
-    if (ix->profile) {
-        FR_CUDA(cudaEventRecord(ev1, s));
-        ix->prof_events.emplace_back(ev0, ev1);
-        ix->prof_launches += fr_launch_count() - launches_before;
-    }
-
-    fr::MergeArgs ma{};
-    ma.packed = sa.partials;
-    ma.P = sa.grid;
-    ma.shard_stride = static_cast<int64_t>(B) * k;
-    ma.B = B;
-    ma.k = k;
-    ma.shards = false;
-    ma.row_keys = ix->keys;
-    ma.l2 = sa.l2;
-    ma.out_dist = d_out_dist;
-    ma.out_packed = d_out_packed;
-    ma.out_keys = d_out_keys;
-    ma.stream = s;
-    FR_CUDA(fr::launch_merge_topk(ma));
-    return FR_OK;
+    return use_mma ? search_mma(ix, q, B, k, d_out_dist, d_out_packed, d_out_keys, s)
+                   : search_stream(ix, q, B, k, d_out_dist, d_out_packed, d_out_keys, s);
 }
 
 int check_search_args(fr_index *ix, const void *q, int B, int k, const void *o1, const void *o2) {
@@ -378,7 +516,9 @@ int fr_index_destroy(fr_index *ix) {
         if (ix->corpus) cudaFree(ix->corpus);
         if (ix->keys) cudaFree(ix->keys);
         DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist,
-                          &ix->out_keys, &ix->stage_vecs, &ix->stage_keys, &ix->stage_rows};
+                          &ix->out_keys, &ix->stage_vecs, &ix->stage_keys, &ix->stage_rows,
+                          &ix->q_bf16, &ix->err_bound, &ix->sel, &ix->sel_keys, &ix->flags, &ix->fail,
+                          &ix->fb_partials};
         for (DevBuf *b : bufs) b->release();
         ix->pin.release();
         for (auto &pr : ix->prof_events) {
@@ -403,6 +543,11 @@ int fr_index_reserve(fr_index *ix, int64_t rows) {
 int fr_index_set_option(fr_index *ix, const char *name, int64_t value) {
     if (!ix || !name) return fail(FR_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(ix->mu);
+    if (std::strcmp(name, "mma_min_batch") == 0) {
+        if (value < 1) return fail(FR_EINVAL, "mma_min_batch must be >= 1");
+        ix->mma_min_batch = static_cast<int>(value);
+        return FR_OK;
+    }
     if (std::strcmp(name, "profile") == 0) {
         ix->profile = value != 0;
         return FR_OK;

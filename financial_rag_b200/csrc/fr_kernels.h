@@ -27,6 +27,47 @@ struct ScanArgs {
 // capped by the amount of work.  The same value is the number of partial lists per query.
 int scan_stream_plan_grid(const ScanArgs &a, int sm_count);
 cudaError_t launch_scan_stream(const ScanArgs &a);
+// Re-scan of the queries K2 could not certify: one launch, loops over fail_list[0..*fail_count),
+// exits at once when the count is zero.  partials: [grid][nq_total][k], grid from
+// scan_stream_fallback_grid.
+int scan_stream_fallback_grid(const ScanArgs &a, int sm_count);
+cudaError_t launch_scan_stream_fallback(const ScanArgs &a, const int *fail_count, const int *fail_list);
+
+// ---- K2 scan_topk_mma (tcgen05) ---------------------------------------------------------------
+struct MmaScanArgs {
+    const void *corpus;         // [rows][384] bf16
+    const int64_t *keys_or_null;
+    const void *queries_bf16;   // [nq_pad][384] bf16, nq_pad multiple of 128, zero padded
+    int nq_pad;
+    int64_t n_rows;
+    int nq_total;
+    int ksel;                   // candidates kept per query (32 or 64), >= 2k
+    uint64_t *partials;         // [grid][nq_total][ksel]
+    int grid;
+    cudaStream_t stream;
+};
+int scan_mma_ksel(int k);  // 0 = k not served by the tensor-core path
+int scan_mma_plan_grid(int sm_count, int64_t n_rows);
+cudaError_t launch_prep_queries(const float *q, int nq, int nq_pad, void *qb, float *err_bound, cudaStream_t s);
+cudaError_t launch_scan_mma(const MmaScanArgs &a);
+
+struct RescoreArgs {
+    const uint64_t *sel;  // [B][ksel] selection lists (K3 output, packed)
+    int ksel;
+    const float *queries;  // [B][384] fp32 prepared queries
+    const uint8_t *corpus;
+    const int64_t *row_keys;
+    const float *err_bound;  // [B] |q - bf16(q)|_2
+    int B, k;
+    float *out_dist;       // [B][k] or null
+    uint64_t *out_packed;  // [B][k] or null
+    int64_t *out_keys;     // [B][k]
+    uint8_t *flags;        // [B] 1 = not certified
+    int *fail_count;
+    int *fail_list;        // [B]
+    cudaStream_t stream;
+};
+cudaError_t launch_rescore(const RescoreArgs &a);
 
 // ---- K3 merge_topk --------------------------------------------------------------------------
 struct MergeArgs {
@@ -46,6 +87,7 @@ struct MergeArgs {
     float *out_dist;            // [B][k] or null
     uint64_t *out_packed;       // [B][k] or null (mergeable form for the all-gather)
     int64_t *out_keys;          // [B][k]
+    const uint8_t *only_flagged;  // optional [B]: CTAs of unflagged queries exit at once (K2 fallback)
     cudaStream_t stream;
 };
 cudaError_t launch_merge_topk(const MergeArgs &a);

@@ -73,11 +73,11 @@ __device__ __forceinline__ float bfly(float lo, float hi, int lane, int stride) 
 // Fast kernel.  RU = rows per 1536-byte unit (2: bf16 x 384, 1: fp32 x 384 / bf16 x 768).
 // BT = queries per pass (1, 2, 4), KPL = top-k slots per lane (k <= 32*KPL).
 template <bool BF16, int RU, int BT, int KPL, bool L2>
-__global__ void __launch_bounds__(256)
-scan_stream_kernel(const uint8_t *__restrict__ corpus, const int64_t *__restrict__ keys_or_null,
-                   const float *__restrict__ queries, int64_t n_rows, int k, int nq,
-                   uint64_t *__restrict__ partials /* [gridDim.x][nq_total][k] */, int nq_total,
-                   int q_offset) {
+__device__ __forceinline__ void
+scan_stream_body(const uint8_t *__restrict__ corpus, const int64_t *__restrict__ keys_or_null,
+                 const float *__restrict__ queries, int64_t n_rows, int k, int nq,
+                 uint64_t *__restrict__ partials /* [gridDim.x][nq_total][k] */, int nq_total,
+                 int q_offset) {
     constexpr int UNIT_BYTES = 1536;
     constexpr int ROW_BYTES = UNIT_BYTES / RU;
     constexpr int CPR = ROW_BYTES / 16;          // 16-byte chunks per row
@@ -235,6 +235,30 @@ scan_stream_kernel(const uint8_t *__restrict__ corpus, const int64_t *__restrict
                 }
             }
         }
+    }
+}
+
+template <bool BF16, int RU, int BT, int KPL, bool L2>
+__global__ void __launch_bounds__(256)
+scan_stream_kernel(const uint8_t *__restrict__ corpus, const int64_t *__restrict__ keys_or_null,
+                   const float *__restrict__ queries, int64_t n_rows, int k, int nq,
+                   uint64_t *__restrict__ partials, int nq_total, int q_offset) {
+    scan_stream_body<BF16, RU, BT, KPL, L2>(corpus, keys_or_null, queries, n_rows, k, nq, partials, nq_total, q_offset);
+}
+
+// K2's safety net: re-scan, one query per corpus pass, the queries whose tensor-core selection could
+// not be certified (scan_mma.cu).  Launched unconditionally; returns at once when nothing failed.
+template <bool BF16, int RU, int KPL, bool L2>
+__global__ void __launch_bounds__(256)
+scan_stream_fallback_kernel(const uint8_t *__restrict__ corpus, const int64_t *__restrict__ keys_or_null,
+                            const float *__restrict__ queries, int64_t n_rows, int k,
+                            uint64_t *__restrict__ partials, int nq_total, const int *__restrict__ fail_count,
+                            const int *__restrict__ fail_list) {
+    const int nf = *fail_count;
+    for (int f = 0; f < nf; ++f) {
+        scan_stream_body<BF16, RU, 1, KPL, L2>(corpus, keys_or_null, queries, n_rows, k, 1, partials, nq_total,
+                                               fail_list[f]);
+        __syncthreads();
     }
 }
 
@@ -426,5 +450,35 @@ int scan_stream_plan_grid(const ScanArgs &a, int sm_count) {
 }
 
 cudaError_t launch_scan_stream(const ScanArgs &a) { return dispatch(a, nullptr); }
+
+// fallback: bf16 x 384 rows, dot metrics only (the only layout K2 serves)
+namespace {
+template <int KPL>
+cudaError_t fallback_impl(const ScanArgs &a, const int *fail_count, const int *fail_list, int *occ_out) {
+    const size_t smem = static_cast<size_t>(THREADS / 32) * 32 * KPL * sizeof(uint64_t);
+    auto kern = scan_stream_fallback_kernel<true, 2, KPL, false>;
+    cudaError_t e = prepare_kernel(kern, smem, occ_out);
+    if (e != cudaSuccess || occ_out) return e;
+    kern<<<a.grid, THREADS, smem, a.stream>>>(a.corpus, a.keys_or_null, a.queries, a.n_rows, a.k, a.partials,
+                                              a.nq_total, fail_count, fail_list);
+    count_launch();
+    return cudaGetLastError();
+}
+}  // namespace
+
+int scan_stream_fallback_grid(const ScanArgs &a, int sm_count) {
+    int occ = 1 << 20;
+    cudaError_t e = a.k <= 32 ? fallback_impl<1>(a, nullptr, nullptr, &occ) : fallback_impl<4>(a, nullptr, nullptr, &occ);
+    if (e != cudaSuccess || occ == (1 << 20)) occ = 1;
+    int64_t want = ((a.n_rows + 31) / 32 + (THREADS / 32) - 1) / (THREADS / 32);
+    if (want < 1) want = 1;
+    const int64_t cap = static_cast<int64_t>(sm_count) * occ;
+    return static_cast<int>(want < cap ? want : cap);
+}
+
+cudaError_t launch_scan_stream_fallback(const ScanArgs &a, const int *fail_count, const int *fail_list) {
+    return a.k <= 32 ? fallback_impl<1>(a, fail_count, fail_list, nullptr)
+                     : fallback_impl<4>(a, fail_count, fail_list, nullptr);
+}
 
 }  // namespace fr

@@ -394,3 +394,109 @@ def test_million_rows_strict_gate(frb):
     s = scores_from_dist(d, "cosine")
     assert (s[0::2, 0] > 0.4).all() and (s[1::2, 0] < 0.4).all()
     ix.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# K2: tensor-core selection + exact rescoring + certified fallback
+MMA_CASES = [
+    # n, B, k
+    (1, 1, 1),
+    (100, 3, 10),
+    (128, 5, 10),
+    (129, 64, 16),
+    (5000, 128, 10),
+    (5000, 129, 17),
+    (70001, 200, 32),
+    (300000, 7, 10),
+]
+
+
+@pytest.mark.parametrize("n,B,k", MMA_CASES)
+def test_mma_path_matches_oracle_and_stream(frb, n, B, k):
+    dups = [(5, n - 3)] if n > 40 else []
+    corpus = make_corpus(n, 384, seed=1000 + n, dup_pairs=dups)
+    queries = make_queries(B, corpus, seed=B + k)
+    if dups:
+        queries[0] = corpus[5]
+    ix = build_index(frb, corpus, "cosine", "bf16")
+    ix.set_path("stream")
+    d_s, k_s = ix.search(queries, k)
+    ix.set_path("mma")
+    d_m, k_m = ix.search(queries, k)
+    rows = keys_to_rows(k_m, KEY_BASE)
+    assert_matches_oracle(d_m, rows, queries, corpus, k, "cosine", "bf16", stored=stored_rows(ix),
+                          label=f"mma n={n} B={B} k={k}")
+    # the two kernels implement the same definition (fp32 queries on the stored bf16 rows): same ids
+    # except fp32-summation-order ties, same scores to accumulation noise
+    np.testing.assert_allclose(d_m, d_s, rtol=0, atol=2e-6)
+    mism = k_m != k_s
+    if mism.any():
+        assert np.abs(d_m[mism] - d_s[mism]).max() <= 2e-6
+    if dups and k >= 2:
+        assert rows[0, 0] == 5 and rows[0, 1] == n - 3
+    ix.close()
+
+
+def test_mma_certification_fallback_on_mass_ties(frb):
+    """More exact duplicates than the k' = 32 selection slots: the tensor-core selection cannot be
+    certified, so the query must be re-scanned by the stream kernel and still return the LOWEST
+    rows first (insertion order), exactly like the stream path."""
+    n, k = 20000, 10
+    corpus = make_corpus(n, 384, seed=77)
+    dup_rows = np.arange(100, 20000, 150)  # 133 copies of row 100
+    corpus[dup_rows] = corpus[100]
+    queries = make_queries(6, corpus, seed=78)
+    queries[1] = corpus[100]
+    queries[4] = corpus[100] + 1e-4 * make_corpus(1, 384, seed=79)[0]
+    ix = build_index(frb, corpus, "cosine", "bf16")
+    ix.set_path("stream")
+    d_s, k_s = ix.search(queries, k)
+    ix.set_path("mma")
+    d_m, k_m = ix.search(queries, k)
+    np.testing.assert_array_equal(keys_to_rows(k_m[1], KEY_BASE), dup_rows[:k])
+    np.testing.assert_array_equal(k_m[1], k_s[1])
+    np.testing.assert_array_equal(k_m[4], k_s[4])
+    np.testing.assert_allclose(d_m, d_s, rtol=0, atol=2e-6)
+    assert_matches_oracle(d_m, keys_to_rows(k_m, KEY_BASE), queries, corpus, k, "cosine", "bf16",
+                          stored=stored_rows(ix), label="mma mass ties")
+    ix.close()
+
+
+def test_mma_path_with_deletes_and_eligibility(frb):
+    from financial_rag_b200._lib import FrError
+
+    n, B, k = 30000, 40, 10
+    corpus = make_corpus(n, 384, seed=91)
+    queries = make_queries(B, corpus, seed=92)
+    ix = build_index(frb, corpus, "cosine", "bf16", key_base=0)
+    ix.set_path("mma")
+    d0, k0 = ix.search(queries, k)
+    victims = np.unique(k0[:, 0])  # delete every current top-1
+    assert ix.delete(victims) == len(victims)
+    live = np.ones(n, bool)
+    live[victims] = False
+    d1, k1 = ix.search(queries, k)
+    assert not np.isin(k1, victims).any()
+    assert_matches_oracle(d1, k1, queries, corpus, k, "cosine", "bf16", stored=stored_rows(ix), live=live,
+                          label="mma after delete")
+    # auto picks the tensor-core path for this batch and gives the same answer
+    ix.set_path("auto")
+    d2, k2 = ix.search(queries, k)
+    np.testing.assert_array_equal(k2, k1)
+    d3, k3 = ix.search(queries, 33)  # k' would not fit 2k: auto serves it with the stream kernel
+    np.testing.assert_array_equal(k3[:, :k], k1)
+    ix.set_path("mma")
+    with pytest.raises(FrError):
+        ix.search(queries, 33)
+    ix.close()
+    for kw in ({"dtype": "f32"}, {"space": "l2"}, {"dim": 768}):
+        args = {"dim": 384, "space": "cosine", "dtype": "bf16"}
+        args.update(kw)
+        jx = frb.ShardIndex(**args)
+        jx.upsert(make_corpus(10, args["dim"], seed=1), np.arange(10))
+        jx.set_path("mma")
+        with pytest.raises(FrError):
+            jx.search(make_corpus(1, args["dim"], seed=2), 5)
+        jx.set_path("auto")  # auto silently uses the kernel that serves the configuration
+        jx.search(make_corpus(8, args["dim"], seed=2), 5)
+        jx.close()
