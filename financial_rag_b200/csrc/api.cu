@@ -159,7 +159,7 @@ struct fr_index {
     cudaStream_t stream = nullptr;   // host-path stream
     cudaEvent_t last_use = nullptr;  // orders scratch reuse across caller streams
     DevBuf q_raw, q_prep, q_keys, partials, out_dist, out_keys, stage_vecs, stage_keys, stage_rows;
-    DevBuf q_bf16, err_bound, sel, sel_keys, flags, fail, fb_partials;  // K2 path
+    DevBuf q_bf16, err_bound, sel, sel_keys, flags, fail, fb_partials, tau;  // K2 path
     int mma_min_batch = 3;  // FR_PATH_AUTO: batches at least this large go to the tensor-core scan
     PinBuf pin;
     std::mutex mu;
@@ -325,8 +325,9 @@ int search_stream(fr_index *ix, const float *q, int B, int k, float *d_out_dist,
 int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, uint64_t *d_out_packed,
                int64_t *d_out_keys, cudaStream_t s) {
     const int ksel = fr::scan_mma_ksel(k);
-    const int nq_pad = ((B + 127) / 128) * 128;
-    const int grid = fr::scan_mma_plan_grid(ix->sm_count, ix->rows);
+    const int group = fr::scan_mma_group(B);
+    const int nq_pad = ((B + group - 1) / group) * group;
+    const int grid = fr::scan_mma_plan_lists(ix->sm_count, ix->rows, B);  // partial lists per query
     FR_CUDA(ix->q_bf16.need(static_cast<size_t>(nq_pad) * ix->dim * 2));
     FR_CUDA(ix->err_bound.need(static_cast<size_t>(B) * sizeof(float)));
     FR_CUDA(ix->partials.need(static_cast<size_t>(grid) * B * ksel * sizeof(uint64_t)));
@@ -334,6 +335,8 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     FR_CUDA(ix->sel_keys.need(static_cast<size_t>(B) * ksel * sizeof(int64_t)));
     FR_CUDA(ix->flags.need(static_cast<size_t>(B)));
     FR_CUDA(ix->fail.need(static_cast<size_t>(B + 1) * sizeof(int)));
+    FR_CUDA(ix->tau.need(static_cast<size_t>(B) * ksel * sizeof(uint32_t)));
+    FR_CUDA(cudaMemsetAsync(ix->tau.p, 0, static_cast<size_t>(B) * ksel * sizeof(uint32_t), s));
     int *fail_count = static_cast<int *>(ix->fail.p);
     int *fail_list = fail_count + 1;
     FR_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), s));
@@ -348,7 +351,8 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     ms.nq_total = B;
     ms.ksel = ksel;
     ms.partials = static_cast<uint64_t *>(ix->partials.p);
-    ms.grid = grid;
+    ms.lists = grid;
+    ms.tau_g = static_cast<uint32_t *>(ix->tau.p);
     ms.stream = s;
     ProfScope prof{ix, s};
     int rc = prof.begin();
@@ -518,7 +522,7 @@ int fr_index_destroy(fr_index *ix) {
         DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist,
                           &ix->out_keys, &ix->stage_vecs, &ix->stage_keys, &ix->stage_rows,
                           &ix->q_bf16, &ix->err_bound, &ix->sel, &ix->sel_keys, &ix->flags, &ix->fail,
-                          &ix->fb_partials};
+                          &ix->fb_partials, &ix->tau};
         for (DevBuf *b : bufs) b->release();
         ix->pin.release();
         for (auto &pr : ix->prof_events) {

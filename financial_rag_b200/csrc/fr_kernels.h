@@ -37,17 +37,19 @@ cudaError_t launch_scan_stream_fallback(const ScanArgs &a, const int *fail_count
 struct MmaScanArgs {
     const void *corpus;         // [rows][384] bf16
     const int64_t *keys_or_null;
-    const void *queries_bf16;   // [nq_pad][384] bf16, nq_pad multiple of 128, zero padded
+    const void *queries_bf16;   // [nq_pad][384] bf16, nq_pad multiple of scan_mma_group(), zero padded
     int nq_pad;
     int64_t n_rows;
     int nq_total;
     int ksel;                   // candidates kept per query (32 or 64), >= 2k
-    uint64_t *partials;         // [grid][nq_total][ksel]
-    int grid;
+    uint64_t *partials;         // [lists][nq_total][ksel]
+    int lists;                  // from scan_mma_plan_lists: CTAs (<= 128 queries) or CTA pairs
+    uint32_t *tau_g;            // [ksel][nq_total] shared threshold slots (order_bits of a score), zeroed before the launches
     cudaStream_t stream;
 };
 int scan_mma_ksel(int k);  // 0 = k not served by the tensor-core path
-int scan_mma_plan_grid(int sm_count, int64_t n_rows);
+int scan_mma_group(int nq_total);  // queries per corpus pass: 128 (one CTA per SM) or 256 (CTA pairs)
+int scan_mma_plan_lists(int sm_count, int64_t n_rows, int nq_total);
 cudaError_t launch_prep_queries(const float *q, int nq, int nq_pad, void *qb, float *err_bound, cudaStream_t s);
 cudaError_t launch_scan_mma(const MmaScanArgs &a);
 

@@ -5,20 +5,35 @@
 // kernel (K1 is FFMA-bound above ~2 queries per pass).
 //
 // The scan of a query block against the corpus IS a dense contraction, so it runs on the 5th-gen
-// tensor cores:   D[128 queries x 128 rows] += A[128 x 16] * B[128 x 16]^T   (bf16 in, fp32 in TMEM)
-//   * A = the query block (bf16 copy of the normalised queries, zero-padded to 128 rows), loaded once
-//     by TMA into shared memory as six K-chunks of [128 rows x 64 elements], SWIZZLE_128B, K-major;
-//   * B = corpus tiles of 128 rows, streamed by TMA ([64 x 128] boxes of the row-major bf16 corpus
-//     -- its natural layout is already the K-major operand) through a 5-stage mbarrier ring;
-//   * one elected thread issues 24 tcgen05.mma (K = 16 each) per corpus tile into one of four
-//     128-column TMEM accumulators; tcgen05.commit frees the smem stage / publishes the accumulator;
+// tensor cores.  Two instances of one kernel template:
+//   CG = 1 (<= 128 queries per pass):  D[128 queries x 128 rows] += A[128 x 16] * B[128 x 16]^T
+//   CG = 2 (<= 256 queries per pass):  a CTA pair (cluster of 2, tcgen05 cta_group::2) computes
+//          D[256 queries x 256 rows]; each CTA keeps ITS 128 queries and loads ITS half of the
+//          corpus tile, so one byte of corpus fetched from HBM feeds twice the math -- at 256
+//          queries per pass the kernel sits on the tensor roofline instead of the HBM one.
+//   * A = the query block (bf16 copy of the normalised queries, zero-padded), loaded once by TMA
+//     into shared memory as six K-chunks of [128 rows x 64 elements], SWIZZLE_128B, K-major;
+//   * B = corpus tiles, streamed by TMA ([64 x 128] boxes of the row-major bf16 corpus -- its
+//     natural layout is already the K-major operand) through an mbarrier ring;
+//   * one elected thread (of the leader CTA when CG = 2) issues 24 tcgen05.mma (K = 16 each) per
+//     corpus tile into a TMEM accumulator (4 x 128 columns, or 2 x 256); tcgen05.commit frees the
+//     smem stage / publishes the accumulator (multicast to both CTAs of a pair);
 //   * one TMEM lane = one query: each of the 128 epilogue threads reads ITS query's scores with
-//     tcgen05.ld (32 columns at a time) and keeps a running maximum; only when some lane's maximum
+//     tcgen05.ld (64 columns at a time) and keeps a running maximum; only when some lane's maximum
 //     beats its current threshold does the warp enter the insert path (transpose 16 columns through
 //     shared memory, warp-cooperative sorted insert into that query's list in shared memory).
 //     No score ever goes to HBM.
+//   * thresholds are shared between CTAs.  A CTA alone only knows the k'-th best of ITS rows, which
+//     rises 148x slower than the k'-th best of everything scanned so far.  So the CTAs are dealt
+//     into k' groups; slot[group][query] (global, atomicMax of the order-preserving score bits)
+//     holds the best score any CTA of the group has INSERTED for the query.  The minimum over the
+//     k' slots is a score that k' distinct live rows reach, i.e. a lower bound on the final k'-th
+//     selection score, and every CTA gates on max(own k'-th, that minimum).  A row is therefore
+//     only dropped when its selection score is <= a value that is itself <= the final k'-th
+//     selection score -- all the certification below needs.
 // Roofline: at <= 128 queries per pass the MMA work per tile (24 x 64 cycles) is far below the HBM
-// time of the tile (128 rows x 768 B), so this kernel is HBM-bound like K1, but for 128 queries at once.
+// time of the tile (128 rows x 768 B): HBM-bound like K1, but for 128 queries at once.  At 256
+// queries per pass (CG = 2) MMA time per 256-row tile (24 x 128 cycles per pair) matches its HBM time.
 //
 // Exactness.  The tensor cores need bf16 queries; the reference semantics (and K1) use fp32 queries.
 // So K2 only SELECTS: it keeps k' = 32*KPL >= 2k candidates per query, ranked by the bf16-query
@@ -36,16 +51,16 @@ namespace fr {
 namespace mma {
 
 constexpr int DIM = 384;
-constexpr int M_TILE = 128;                    // queries per pass (TMEM lanes)
-constexpr int N_TILE = 128;                    // corpus rows per accumulator
+constexpr int M_TILE = 128;                    // queries per CTA (TMEM lanes)
+constexpr int N_TILE = 128;                    // corpus rows loaded per CTA per tile
 constexpr int K_CHUNK = 64;                    // bf16 elements per 128-byte swizzle row
 constexpr int K_CHUNKS = DIM / K_CHUNK;        // 6
 constexpr int UMMA_K = 16;
 constexpr int CHUNK_BYTES = N_TILE * K_CHUNK * 2;  // 16 KB: one [128 x 64] bf16 box (A chunk or B stage)
-constexpr int TMEM_BUFS = 4;
-constexpr int TMEM_COLS = TMEM_BUFS * N_TILE;  // 512
+constexpr int TMEM_COLS = 512;                 // the whole tensor memory: 4 x 128 or 2 x 256 columns
 constexpr int THREADS = 192;                   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
-constexpr int TR_STRIDE = 17;                  // transpose scratch row stride (floats), conflict-free
+
+constexpr int PEND = 16;                       // unsorted pending candidates per query between compactions
 
 template <int KPL>
 struct SmemPlan {
@@ -53,16 +68,32 @@ struct SmemPlan {
     static constexpr int CAP = 32 * KPL;
     static constexpr size_t A_OFF = 0;
     static constexpr size_t B_OFF = A_OFF + size_t(K_CHUNKS) * CHUNK_BYTES;
-    static constexpr size_t LIST_OFF = B_OFF + size_t(STAGES) * CHUNK_BYTES;
-    static constexpr size_t TR_OFF = LIST_OFF + size_t(M_TILE) * CAP * 8;
-    static constexpr size_t BAR_OFF = TR_OFF + size_t(4) * 32 * TR_STRIDE * 4;
+    static constexpr size_t LIST_OFF = B_OFF + size_t(STAGES) * CHUNK_BYTES;   // [128 queries][CAP] sorted
+    static constexpr size_t PEND_OFF = LIST_OFF + size_t(M_TILE) * CAP * 8;    // [4 warps][PEND][32] swizzled
+    static constexpr size_t BAR_OFF = PEND_OFF + size_t(M_TILE) * PEND * 8;
     static constexpr size_t TOTAL = BAR_OFF + 256;
     static constexpr size_t ALLOC = TOTAL + 1024;  // slack to align the base to 1024 B
 };
+static_assert(SmemPlan<1>::ALLOC <= 232448 && SmemPlan<2>::ALLOC <= 232448, "exceeds 227 KB of shared memory");
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -72,6 +103,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on a barrier that may live in the other CTA of the pair (shared::cluster address)
+// (default .release.cta semantics: the accumulator reads are ordered by tcgen05.fence::before_thread_sync;
+//  a cluster-scope release would cost a MEMBAR.GPU per tile)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -86,41 +123,87 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// TMA tile load; `bar` is a shared::cluster address (for CG = 2 the leader CTA's barrier)
+template <int CG>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
+    if constexpr (CG == 1) {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+            "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+            : "memory");
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+            "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+            : "memory");
+    }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// all MMAs issued so far -> one arrival on `bar` (same smem offset in both CTAs when CG = 2)
+template <int CG>
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    } else {
+        const uint16_t mask = 3;
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+            "h"(mask)
+            : "memory");
+    }
 }
+template <int CG>
 __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
+    if constexpr (CG == 1) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+            : "memory");
+    }
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// 64 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+    uint32_t r[64];
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+          "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+          "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// one fp32 column of this thread's TMEM lane (warp-uniform column address)
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return __uint_as_float(r);
 }
 
 // Shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows 128 B apart, 8-row groups 1024 B apart
@@ -142,32 +225,105 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
            (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-// ---------------------------------------------------------------------------------------------
+// ---- warp-wide bitonic networks on packed keys (one key per lane) -------------------------------
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t x, int m) {
+    const uint32_t lo = __shfl_xor_sync(FULL_MASK, static_cast<uint32_t>(x), m);
+    const uint32_t hi = __shfl_xor_sync(FULL_MASK, static_cast<uint32_t>(x >> 32), m);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint64_t umax64(uint64_t a, uint64_t b) { return a > b ? a : b; }
+__device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+// 32 keys in bitonic order -> descending (lane 0 holds the largest)
+__device__ __forceinline__ uint64_t bitonic_merge32_desc(uint64_t x, int lane) {
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const uint64_t y = shfl_xor_u64(x, j);
+        x = ((lane & j) == 0) ? umax64(x, y) : umin64(x, y);
+    }
+    return x;
+}
+// any 32 keys -> descending
+__device__ __forceinline__ uint64_t bitonic_sort32_desc(uint64_t x, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint64_t y = shfl_xor_u64(x, j);
+            const bool desc = (lane & k) == 0;  // k = 32: every lane sorts descending
+            const bool keep_max = ((lane & j) == 0) == desc;
+            x = keep_max ? umax64(x, y) : umin64(x, y);
+        }
+    }
+    return x;
+}
+__device__ __forceinline__ uint64_t reverse32(uint64_t x, int lane) {
+    const uint32_t lo = __shfl_sync(FULL_MASK, static_cast<uint32_t>(x), 31 - lane);
+    const uint32_t hi = __shfl_sync(FULL_MASK, static_cast<uint32_t>(x >> 32), 31 - lane);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// Fold the pending candidates of one query into its sorted list (all 32 lanes cooperate).
+//   list: [32*KPL] sorted descending (0 = empty), pend_w: this warp's pending block, n = pending count.
+// Returns the new k'-th key (0 while the list is not full).
 template <int KPL>
+__device__ __forceinline__ uint64_t compact_query(uint64_t *list, const uint64_t *pend_w, int tq, int n, int lane) {
+    uint64_t p = (lane < n) ? pend_w[lane * 32 + ((tq + lane) & 31)] : 0ull;
+    p = bitonic_sort32_desc(p, lane);
+    uint64_t L[KPL];
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) L[j] = list[j * 32 + lane];
+    // top-32 of (last 32 of the list  U  pending): elementwise max against the reversed pending block
+    // is a bitonic sequence; everything ahead of it in the list stays in the top 32*KPL.
+    uint64_t m = bitonic_merge32_desc(umax64(L[KPL - 1], reverse32(p, lane)), lane);
+    if constexpr (KPL == 1) {
+        L[0] = m;
+    } else {
+        static_assert(KPL == 2, "lists hold 32 or 64 candidates");
+        const uint64_t r = reverse32(m, lane);
+        L[1] = bitonic_merge32_desc(umin64(L[0], r), lane);
+        L[0] = bitonic_merge32_desc(umax64(L[0], r), lane);
+    }
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) list[j * 32 + lane] = L[j];
+    const uint32_t lo = __shfl_sync(FULL_MASK, static_cast<uint32_t>(L[KPL - 1]), 31);
+    const uint32_t hi = __shfl_sync(FULL_MASK, static_cast<uint32_t>(L[KPL - 1] >> 32), 31);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid = P * CG CTAs (P = partial lists per query); CTA pair p = blockIdx.x / CG takes corpus tiles
+// p, p + P, ... of 128*CG rows.  partials: [P][nq_total][ksel].
+template <int KPL, int CG>
 __global__ void __launch_bounds__(THREADS, 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                 const int64_t *__restrict__ keys_or_null, int64_t n_rows, int nq, int q_row0, int ksel,
-                uint64_t *__restrict__ partials /* [gridDim.x][nq_total][ksel] */, int nq_total, int q_offset) {
+                uint64_t *__restrict__ partials, int nq_total, int q_offset, uint32_t *__restrict__ tau_g) {
     using Plan = SmemPlan<KPL>;
     constexpr int STAGES = Plan::STAGES;
     constexpr int CAP = Plan::CAP;
+    constexpr int ACC_COLS = N_TILE * CG;            // accumulator width = corpus rows per tile
+    constexpr int TMEM_BUFS = TMEM_COLS / ACC_COLS;  // 4 or 2
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_a = smem + Plan::A_OFF;
     uint8_t *smem_b = smem + Plan::B_OFF;
     uint64_t *lists = reinterpret_cast<uint64_t *>(smem + Plan::LIST_OFF);
-    float *tr_all = reinterpret_cast<float *>(smem + Plan::TR_OFF);
+    uint64_t *pend_all = reinterpret_cast<uint64_t *>(smem + Plan::PEND_OFF);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Plan::BAR_OFF);
     // barrier slots: full[STAGES] | empty[STAGES] | tmem_full[4] | tmem_empty[4] | a_full | tmem_ptr
+    // (identical offsets in both CTAs of a pair; full / tmem_empty / a_full are used in the leader only)
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = smem_u32(bars + STAGES);
     const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES);
-    const uint32_t bar_tempty = smem_u32(bars + 2 * STAGES + TMEM_BUFS);
-    const uint32_t bar_afull = smem_u32(bars + 2 * STAGES + 2 * TMEM_BUFS);
-    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2 * TMEM_BUFS + 1);
+    const uint32_t bar_tempty = smem_u32(bars + 2 * STAGES + 4);
+    const uint32_t bar_afull = smem_u32(bars + 2 * STAGES + 8);
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 9);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // position inside the CTA pair
+    const int pair = blockIdx.x / CG;
+    const int npairs = gridDim.x / CG;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -176,16 +332,23 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         for (int b = 0; b < TMEM_BUFS; ++b) {
             mbar_init(bar_tfull + 8 * b, 1);
-            mbar_init(bar_tempty + 8 * b, 4);  // one arrival per epilogue warp
+            mbar_init(bar_tempty + 8 * b, 4 * CG);  // one arrival per epilogue warp of the pair
         }
         mbar_init(bar_afull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                     "r"(TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                         "r"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                         "r"(TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     // epilogue warps clear their queries' lists while the allocation happens
     if (warp >= 2) {
@@ -193,27 +356,34 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int64_t num_tiles = (n_rows + N_TILE - 1) / N_TILE;
+    constexpr int TILE_ROWS = N_TILE * CG;
+    const int64_t num_tiles = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
+    const int nq_local = max(0, min(M_TILE, nq - static_cast<int>(rank) * M_TILE));  // this CTA's live queries
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (both CTAs of a pair) =====================
         if (lane == 0) {
-            mbar_expect_tx(bar_afull, K_CHUNKS * CHUNK_BYTES);
+            // barriers the MMA issuer waits on live in the leader CTA
+            const uint32_t l_afull = (CG == 2) ? map_to_cta(bar_afull, 0) : bar_afull;
+            const uint32_t l_full = (CG == 2) ? map_to_cta(bar_full, 0) : bar_full;
+            if (rank == 0) mbar_expect_tx(bar_afull, K_CHUNKS * CHUNK_BYTES * CG);
 #pragma unroll
             for (int kc = 0; kc < K_CHUNKS; ++kc)
-                tma_load_2d(smem_u32(smem_a + kc * CHUNK_BYTES), &tmap_q, bar_afull, kc * K_CHUNK, q_row0);
+                tma_load_2d<CG>(smem_u32(smem_a + kc * CHUNK_BYTES), &tmap_q, l_afull, kc * K_CHUNK,
+                                q_row0 + static_cast<int>(rank) * M_TILE);
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int row0 = static_cast<int>(t * N_TILE);
+            for (int64_t t = pair; t < num_tiles; t += npairs) {
+                const int row0 = static_cast<int>(t * TILE_ROWS) + static_cast<int>(rank) * N_TILE;
 #pragma unroll 1
                 for (int kc = 0; kc < K_CHUNKS; ++kc) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    mbar_expect_tx(bar_full + 8 * stage, CHUNK_BYTES);
-                    tma_load_2d(smem_u32(smem_b + stage * CHUNK_BYTES), &tmap_c, bar_full + 8 * stage, kc * K_CHUNK, row0);
+                    if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, CHUNK_BYTES * CG);
+                    tma_load_2d<CG>(smem_u32(smem_b + stage * CHUNK_BYTES), &tmap_c, l_full + 8 * stage, kc * K_CHUNK, row0);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -222,20 +392,20 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(M_TILE, N_TILE);
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(M_TILE * CG, ACC_COLS);
             mbar_wait(bar_afull, 0);
             tc_fence_after();
             int stage = 0;
             uint32_t phase = 0;
             uint32_t it = 0;
-            for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            for (int64_t t = pair; t < num_tiles; t += npairs, ++it) {
                 const uint32_t buf = it % TMEM_BUFS;
                 const uint32_t bphase = (it / TMEM_BUFS) & 1;
-                mbar_wait(bar_tempty + 8 * buf, bphase ^ 1);  // epilogue has drained this accumulator
+                mbar_wait(bar_tempty + 8 * buf, bphase ^ 1);  // both epilogues have drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * N_TILE;
+                const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
 #pragma unroll 1
                 for (int kc = 0; kc < K_CHUNKS; ++kc) {
                     mbar_wait(bar_full + 8 * stage, phase);
@@ -246,97 +416,157 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     for (int k4 = 0; k4 < K_CHUNK / UMMA_K; ++k4) {
                         const uint64_t adesc = make_kmajor_sw128_desc(a_addr + k4 * UMMA_K * 2);
                         const uint64_t bdesc = make_kmajor_sw128_desc(b_addr + k4 * UMMA_K * 2);
-                        tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kc | k4) != 0 ? 1u : 0u);
+                        tc_mma_bf16<CG>(d_tmem, adesc, bdesc, idesc, (kc | k4) != 0 ? 1u : 0u);
                     }
-                    tc_commit(bar_empty + 8 * stage);  // smem stage reusable once these MMAs have read it
+                    tc_commit<CG>(bar_empty + 8 * stage);  // smem stage reusable once these MMAs have read it
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                tc_commit(bar_tfull + 8 * buf);  // accumulator complete
+                tc_commit<CG>(bar_tfull + 8 * buf);  // accumulator complete
             }
         }
     } else {
         // ===================== epilogue: one TMEM lane = one query =====================
         const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-        const int my_q = quarter * 32 + lane;      // query index inside the block
-        float *tr = tr_all + (warp - 2) * 32 * TR_STRIDE;
+        const int my_q = quarter * 32 + lane;      // query index inside this CTA's block of 128
         uint64_t *my_lists = lists + static_cast<size_t>(quarter) * 32 * CAP;
-        float tau = (my_q < nq) ? -INFINITY : INFINITY;  // padded query rows never pass the gate
+        uint64_t *pend_w = pend_all + static_cast<size_t>(warp - 2) * PEND * 32;  // entry j of lane q: [j][(q + j) & 31]
+        const bool live = my_q < nq_local;
+        float tau = live ? -INFINITY : INFINITY;   // padded query rows never pass the gate
+        int cnt = 0;                               // this query's pending (unsorted) candidates
+        // shared thresholds: slot[group][query]; this CTA (pair) publishes into group pair % ksel
+        const uint32_t *slots_q = tau_g + q_offset + static_cast<int>(rank) * M_TILE + (live ? my_q : 0);
+        uint32_t *my_slot = tau_g + static_cast<size_t>(pair % ksel) * nq_total + q_offset +
+                            static_cast<int>(rank) * M_TILE + (live ? my_q : 0);
+        uint32_t best = 0, published = 0;          // order bits of the best score appended / published
+        const uint32_t l_tempty = (CG == 2) ? map_to_cta(bar_tempty, 0) : bar_tempty;
         uint32_t it = 0;
-        for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        for (int64_t t = pair; t < num_tiles; t += npairs, ++it) {
             const uint32_t buf = it % TMEM_BUFS;
             const uint32_t bphase = (it / TMEM_BUFS) & 1;
+            // min over the k' group slots = a score k' distinct rows reach (monotone hints: relaxed loads)
+            uint32_t g = 0;
+            if (live && (it < 8u || (it & 7u) == 0u)) {
+                g = 0xffffffffu;
+#pragma unroll 8
+                for (int j = 0; j < ksel; ++j) {
+                    uint32_t x;
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(x) : "l"(slots_q + static_cast<size_t>(j) * nq_total));
+                    g = min(g, x);
+                }
+            }
             mbar_wait(bar_tfull + 8 * buf, bphase);
             tc_fence_after();
-            const uint32_t row0 = static_cast<uint32_t>(t * N_TILE);
+            if (g != 0u) tau = fmaxf(tau, unorder_bits(g));
+            const uint32_t row0 = static_cast<uint32_t>(t * TILE_ROWS);
+            const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * ACC_COLS;
 #pragma unroll 1
-            for (int c = 0; c < N_TILE / 32; ++c) {
-                float v[32];
-                tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * N_TILE + c * 32, v);
+            for (int c = 0; c < ACC_COLS / 64; ++c) {
+                float v[64];
+                tmem_ld64(tcol + c * 64, v);
                 float mx = v[0];
 #pragma unroll
-                for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
-                if (__ballot_sync(FULL_MASK, mx > tau) == 0u) continue;  // the common case
-                // ---- insert path: 16 columns at a time through the transpose scratch ----
+                for (int i = 1; i < 64; ++i) mx = fmaxf(mx, v[i]);
+                if (!__any_sync(FULL_MASK, mx > tau)) continue;  // the common case
+                // ---- candidate path.  Every lane appends its own query's passing scores to its pending
+                //      block; a lane whose block fills up gets it folded into its sorted list (warp-wide
+                //      bitonic network) and resumes where it stopped, with the raised threshold.
+                //      The walk is warp-uniform: OR of the lanes' pass masks, one iteration per column
+                //      that holds a candidate, the column re-read from TMEM (registers cannot be
+                //      indexed by a run-time column number). ----
+                const uint32_t rbase = row0 + c * 64;
+                int resume = 0;
+                while (true) {
+                    uint32_t mlo = 0, mhi = 0;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float hmx = v[h * 16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        tr[lane * TR_STRIDE + i] = v[h * 16 + i];
-                        hmx = fmaxf(hmx, v[h * 16 + i]);
+                    for (int i = 0; i < 32; ++i) {
+                        mlo |= (v[i] > tau) ? (1u << i) : 0u;
+                        mhi |= (v[32 + i] > tau) ? (1u << i) : 0u;
                     }
-                    __syncwarp();
-                    unsigned m = __ballot_sync(FULL_MASK, hmx > tau);
-                    while (m) {
-                        const int tq = __ffs(m) - 1;  // the lane (query) that has candidates
-                        m &= m - 1;
-                        const float tau_t = __shfl_sync(FULL_MASK, tau, tq);
-                        const float val = (lane < 16) ? tr[tq * TR_STRIDE + lane] : -INFINITY;
-                        const uint32_t row = row0 + c * 32 + h * 16 + lane;
-                        unsigned cm = __ballot_sync(FULL_MASK, lane < 16 && val > tau_t && row < n_rows);
-                        if (cm == 0u) continue;
-                        WarpTopK<KPL> lst;
-                        uint64_t *lp = my_lists + static_cast<size_t>(tq) * CAP;
-#pragma unroll
-                        for (int j = 0; j < KPL; ++j) lst.e[j] = lp[j * 32 + lane];
-                        while (cm) {
-                            const int src = __ffs(cm) - 1;
-                            cm &= cm - 1;
-                            const float sv = __shfl_sync(FULL_MASK, val, src);
-                            const uint32_t rv = row0 + c * 32 + h * 16 + src;
-                            if (keys_or_null != nullptr && keys_or_null[rv] == KEY_TOMBSTONE) continue;
-                            lst.insert(pack_key(sv, rv), ksel, lane);
+                    uint64_t m = (static_cast<uint64_t>(mhi) << 32) | mlo;
+                    m = resume < 64 ? (m & (~0ull << resume)) : 0ull;
+                    uint32_t alo = __reduce_or_sync(FULL_MASK, static_cast<uint32_t>(m));
+                    uint32_t ahi = __reduce_or_sync(FULL_MASK, static_cast<uint32_t>(m >> 32));
+                    bool full = false;
+                    int stop = 64;
+                    while ((alo | ahi) != 0u) {
+                        int i;
+                        if (alo != 0u) {
+                            i = __ffs(alo) - 1;
+                            alo &= alo - 1;
+                        } else {
+                            i = 32 + __ffs(ahi) - 1;
+                            ahi &= ahi - 1;
                         }
-                        lst.store(lp, lane);
-                        const float new_tau = key_threshold(lst.kth(ksel));
-                        if (lane == tq) tau = new_tau;
+                        const float x = tmem_ld1(tcol + c * 64 + i);
+                        if (((m >> i) & 1ull) != 0ull && !full) {
+                            const uint32_t row = rbase + i;
+                            bool ok = row < n_rows;
+                            if (ok && keys_or_null != nullptr) ok = keys_or_null[row] != KEY_TOMBSTONE;
+                            if (ok) {
+                                if (cnt == PEND) {
+                                    full = true;
+                                    stop = i;
+                                } else {
+                                    pend_w[cnt * 32 + ((lane + cnt) & 31)] = pack_key(x, row);
+                                    ++cnt;
+                                    best = max(best, order_bits(x));
+                                }
+                            }
+                        }
+                    }
+                    resume = stop;
+                    unsigned fm = __ballot_sync(FULL_MASK, full);
+                    if (fm == 0u) break;
+                    __syncwarp();
+                    while (fm) {
+                        const int tq = __ffs(fm) - 1;
+                        fm &= fm - 1;
+                        const uint64_t kth = compact_query<KPL>(my_lists + static_cast<size_t>(tq) * CAP, pend_w, tq, PEND, lane);
+                        if (lane == tq) {
+                            cnt = 0;
+                            tau = fmaxf(tau, key_threshold(kth));
+                        }
                     }
                     __syncwarp();
+                }
+                if (best > published) {  // best live row this CTA holds for the query: other CTAs gate on it
+                    published = best;
+                    atomicMax(my_slot, best);
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+            if (lane == 0) {
+                if constexpr (CG == 2) mbar_arrive_cluster(l_tempty + 8 * buf);
+                else mbar_arrive(bar_tempty + 8 * buf);
+            }
         }
-        // ---- this CTA's list for each of its queries ----
+        // ---- fold what is still pending, then this CTA's list for each of its queries ----
         __syncwarp();
         for (int q = 0; q < 32; ++q) {
             const int qq = quarter * 32 + q;
-            if (qq >= nq) break;
-            uint64_t *dst = partials + (static_cast<size_t>(blockIdx.x) * nq_total + q_offset + qq) * ksel;
-            const uint64_t *lp = my_lists + static_cast<size_t>(q) * CAP;
+            if (qq >= nq_local) break;
+            const int n = __shfl_sync(FULL_MASK, cnt, q);
+            uint64_t *lp = my_lists + static_cast<size_t>(q) * CAP;
+            if (n > 0) compact_query<KPL>(lp, pend_w, q, n, lane);
+            __syncwarp();
+            uint64_t *dst = partials + (static_cast<size_t>(pair) * nq_total + q_offset + static_cast<int>(rank) * M_TILE + qq) * ksel;
             for (int i = lane; i < ksel; i += 32) dst[i] = lp[i];
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // no CTA leaves while its pair may still signal or read it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        if constexpr (CG == 1)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -475,47 +705,66 @@ static bool make_row_major_map(CUtensorMap *map, const void *base, int64_t rows)
 // ---- host launchers ---------------------------------------------------------------------------
 int scan_mma_ksel(int k) { return k <= 16 ? 32 : (k <= 32 ? 64 : 0); }
 
+// queries served by one corpus pass: a single CTA per SM up to 128, CTA pairs (cta_group::2) above
+int scan_mma_group(int nq_total) { return nq_total <= mma::M_TILE ? mma::M_TILE : 2 * mma::M_TILE; }
+
 cudaError_t launch_prep_queries(const float *q, int nq, int nq_pad, void *qb, float *err_bound, cudaStream_t s) {
     mma::prep_queries_kernel<<<nq_pad, 32, 0, s>>>(q, nq, nq_pad, static_cast<__nv_bfloat16 *>(qb), err_bound);
     count_launch();
     return cudaGetLastError();
 }
 
+namespace {
+template <int KPL, int CG>
+cudaError_t launch_one(const MmaScanArgs &a, const CUtensorMap &tq, const CUtensorMap &tc, int nq, int q0) {
+    auto kern = mma::scan_mma_kernel<KPL, CG>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(mma::SmemPlan<KPL>::ALLOC));
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(a.lists * CG));
+    cfg.blockDim = dim3(mma::THREADS);
+    cfg.dynamicSmemBytes = mma::SmemPlan<KPL>::ALLOC;
+    cfg.stream = a.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, tq, tc, a.keys_or_null, a.n_rows, nq, q0, a.ksel, a.partials, a.nq_total, q0,
+                           a.tau_g);
+    count_launch();
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+}  // namespace
+
 cudaError_t launch_scan_mma(const MmaScanArgs &a) {
     CUtensorMap tq, tc;
     if (!mma::make_row_major_map(&tq, a.queries_bf16, a.nq_pad) || !mma::make_row_major_map(&tc, a.corpus, a.n_rows))
         return cudaErrorNotSupported;
-    const int ksel = a.ksel;
-    for (int g = 0; g * mma::M_TILE < a.nq_total; ++g) {
-        const int q0 = g * mma::M_TILE;
-        const int nq = (a.nq_total - q0 < mma::M_TILE) ? (a.nq_total - q0) : mma::M_TILE;
+    const int group = scan_mma_group(a.nq_total);
+    for (int q0 = 0; q0 < a.nq_total; q0 += group) {
+        const int nq = (a.nq_total - q0 < group) ? (a.nq_total - q0) : group;
         cudaError_t e;
-        if (ksel <= 32) {
-            auto kern = mma::scan_mma_kernel<1>;
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(mma::SmemPlan<1>::ALLOC));
-            if (e != cudaSuccess) return e;
-            kern<<<a.grid, mma::THREADS, mma::SmemPlan<1>::ALLOC, a.stream>>>(tq, tc, a.keys_or_null, a.n_rows, nq, q0,
-                                                                              ksel, a.partials, a.nq_total, q0);
-        } else {
-            auto kern = mma::scan_mma_kernel<2>;
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(mma::SmemPlan<2>::ALLOC));
-            if (e != cudaSuccess) return e;
-            kern<<<a.grid, mma::THREADS, mma::SmemPlan<2>::ALLOC, a.stream>>>(tq, tc, a.keys_or_null, a.n_rows, nq, q0,
-                                                                              ksel, a.partials, a.nq_total, q0);
-        }
-        count_launch();
-        e = cudaGetLastError();
+        if (group == mma::M_TILE)
+            e = a.ksel <= 32 ? launch_one<1, 1>(a, tq, tc, nq, q0) : launch_one<2, 1>(a, tq, tc, nq, q0);
+        else
+            e = a.ksel <= 32 ? launch_one<1, 2>(a, tq, tc, nq, q0) : launch_one<2, 2>(a, tq, tc, nq, q0);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
 }
 
-int scan_mma_plan_grid(int sm_count, int64_t n_rows) {
-    const int64_t tiles = (n_rows + mma::N_TILE - 1) / mma::N_TILE;
+// number of partial lists per query (= CTAs, or CTA pairs above 128 queries)
+int scan_mma_plan_lists(int sm_count, int64_t n_rows, int nq_total) {
+    const int cg = scan_mma_group(nq_total) / mma::M_TILE;
+    const int64_t tile_rows = static_cast<int64_t>(mma::N_TILE) * cg;
+    const int64_t tiles = (n_rows + tile_rows - 1) / tile_rows;
+    const int64_t units = sm_count / cg;
     if (tiles < 1) return 1;
-    return static_cast<int>(tiles < sm_count ? tiles : sm_count);
+    return static_cast<int>(tiles < units ? tiles : units);
 }
 
 cudaError_t launch_rescore(const RescoreArgs &a) {

@@ -408,6 +408,12 @@ MMA_CASES = [
     (5000, 129, 17),
     (70001, 200, 32),
     (300000, 7, 10),
+    # above 128 queries: CTA pairs (cta_group::2), 256 queries per corpus pass
+    (255, 256, 10),
+    (257, 130, 3),
+    (100000, 300, 10),   # second pass holds 44 queries: the pair's second CTA has none
+    (40000, 513, 5),
+    (1, 256, 1),
 ]
 
 
