@@ -40,7 +40,10 @@ if ROOT not in sys.path:
 DIM = 384
 CHUNK_ROWS = 500_000          # global generation chunk; seed = 1234 + chunk index
 DEFAULT_ROWS = 100_000_000    # BASELINE.json: "exact top-10 over 100M x 384"
-DEFAULT_BATCH = 4             # largest batch the streaming kernel serves in one corpus pass
+DEFAULT_BATCH = 1024          # cfg4 spans batch 1-4096; QPS is quoted in the batched (tensor-core) regime,
+                              # the HBM-streaming regime (batch 1 ... 128) is in "sweep" of the same line
+DEFAULT_SWEEP = "1,8,64,128,256,4096"
+MMA_GROUP = 256               # queries per K2 corpus pass above 128 (CTA pairs); K1 serves batch 1
 METRIC = "QPS exact top-10 over 100Mx384 bf16 (cosine), row-sharded"
 
 
@@ -55,8 +58,8 @@ def parse_args():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--path", default="auto", choices=["auto", "stream", "mma"])
-    ap.add_argument("--sweep", default="1", help="extra batch sizes measured briefly (comma list, '' = none)")
-    ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000)
+    ap.add_argument("--sweep", default=DEFAULT_SWEEP, help="extra batch sizes measured briefly (comma list, '' = none)")
+    ap.add_argument("--cpu-sample-rows", type=int, default=0, help="0 = sized for a few seconds of CPU work per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -152,9 +155,10 @@ def measured_peaks():
     try:
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained") or d["bf16_tflops"]), "measured"
+        return (float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained") or d["bf16_tflops"]),
+                float(d["bf16_tflops"]), "measured")
     except Exception:
-        return 6650.0, 1590.0, "fallback"
+        return 6650.0, 1400.0, 1590.0, "fallback"
 
 
 def ncu_traffic(path_kind, rows_local):
@@ -167,6 +171,55 @@ def ncu_traffic(path_kind, rows_local):
         return None
 
 
+def scan_kernel_of(batch, path, k):
+    """Which scan kernel a batch runs on (mirrors search_on_stream in csrc/api.cu) and the queries
+    one launch of it serves."""
+    mma_ok = k <= 32
+    use_mma = mma_ok and (path == "mma" or (path == "auto" and batch >= 2))
+    if not use_mma:
+        return "scan_stream_kernel", "stream", min(batch, 4)
+    if batch <= 128:
+        return "scan_mma_kernel<1,1> (tcgen05, one CTA per SM)", "mma_cg1", batch
+    return "scan_mma_kernel<1,2> (tcgen05 cta_group::2, CTA pairs)", "mma_cg2", None  # per launch: from the count
+
+
+def roofline_of(batch, path, k, rows_local, elem, scan_ms, scan_launches, searches, step_ms_total):
+    """Roofline of the dominant (scan) kernel from its CUDA-event time inside the library.
+    Algorithmic work per launch (DESIGN.md 4): bytes = rows_per_gpu * 384 * sizeof(elem) -- the corpus is
+    read once per launch whatever the number of queries; flops = 2 * rows_per_gpu * 384 * queries the
+    launch serves.  The bound is whichever of bytes/hbm_peak and flops/tensor_peak is the longer."""
+    hbm_peak, tf_sustained, tf_burst, peak_kind = measured_peaks()
+    kernel, kind, _ = scan_kernel_of(batch, path, k)
+    avg_launch_s = (scan_ms / max(scan_launches, 1)) / 1e3
+    q_per_launch = batch * max(searches, 1) / max(scan_launches, 1)
+    bytes_per_launch = rows_local * DIM * elem
+    flops_per_launch = 2.0 * rows_local * DIM * q_per_launch
+    gbs = bytes_per_launch / avg_launch_s / 1e9
+    tfs = flops_per_launch / avg_launch_s / 1e12
+    t_hbm, t_tensor = bytes_per_launch / (hbm_peak * 1e9), flops_per_launch / (tf_sustained * 1e12)
+    tensor_bound = kind != "stream" and t_tensor > t_hbm
+    r = {
+        "bound": "tensor" if tensor_bound else "hbm",
+        "achieved": tfs if tensor_bound else gbs,
+        "peak": tf_sustained if tensor_bound else hbm_peak,
+        "unit": "TFLOP/s" if tensor_bound else "GB/s",
+        "frac": (tfs / tf_sustained) if tensor_bound else (gbs / hbm_peak),
+        "traffic": ncu_traffic(kind, rows_local),
+        "peak_kind": (f"{peak_kind} (MEASURED_PEAKS.json bf16_tflops_sustained: the kernel runs inside a long step; "
+                      f"burst {tf_burst})" if tensor_bound else f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)"),
+        "kernel": kernel,
+        "queries_per_launch": q_per_launch,
+        "bytes_per_launch": bytes_per_launch,
+        "flops_per_launch": flops_per_launch,
+        "avg_launch_ms": avg_launch_s * 1e3,
+        "launches_timed": scan_launches,
+        "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak,
+        "tensor_tflops": tfs, "tensor_frac_sustained": tfs / tf_sustained, "tensor_frac_burst": tfs / tf_burst,
+        "scan_share_of_step": scan_ms / step_ms_total if step_ms_total else None,
+    }
+    return r
+
+
 # ---------------------------------------------------------------------------------------------
 def cpu_scan_qps(n_rows_full, batch, k, sample_rows, steps, warmup, torch=None, device=None):
     """Exact fp32 scan on the host cores over a bounded row sample; QPS scaled to the full corpus."""
@@ -175,6 +228,10 @@ def cpu_scan_qps(n_rows_full, batch, k, sample_rows, steps, warmup, torch=None, 
     from oracle import cscan
     from oracle import exact_scan as ox
 
+    if not sample_rows:
+        # ~1.5e12 flop (sgemm regime) or 2M rows (bandwidth regime) per step: a few seconds on a host CPU
+        sample_rows = int(max(250_000, min(2_000_000, 1.5e12 / (2.0 * DIM * batch))))
+        sample_rows = (sample_rows // 250_000) * 250_000
     sample_rows = int(min(sample_rows, n_rows_full))
     rng_rows = sample_rows
     # the same synthetic rows as the GPU arm where a device is available, else numpy Gaussians
@@ -193,13 +250,16 @@ def cpu_scan_qps(n_rows_full, batch, k, sample_rows, steps, warmup, torch=None, 
     cores = os.cpu_count() or 1
 
     def run_numpy():
-        return ox.exact_topk(q, corpus, k, "cosine", "f32", prepared=True)
+        return ox.exact_topk_thresholded(q, corpus, k, "cosine", chunk_rows=max(16384, min(1 << 20, (1 << 26) // batch)))
 
     def run_c():
         return cscan.exact_topk_prepared(corpus, q, k, "cosine")
 
     results = {}
-    for name, fn in (("numpy_sgemm", run_numpy), ("c_openmp", run_c)):
+    arms = [("numpy_sgemm", run_numpy)]
+    if batch <= 16:  # the C port scans row by row for each query: the bandwidth regime's algorithm
+        arms.append(("c_openmp", run_c))
+    for name, fn in arms:
         try:
             for _ in range(max(1, min(warmup, 2))):
                 fn()
@@ -223,6 +283,7 @@ def cpu_scan_qps(n_rows_full, batch, k, sample_rows, steps, warmup, torch=None, 
                    f"{best[1]} ({', '.join(f'{n}={t * 1e3:.0f}ms' for n, t in results.items() if t)}), "
                    f"time scaled linearly to the full corpus"),
         "ms_per_step_sample": best[0] * 1e3,
+        "sample_rows": sample_rows,
     }
 
 
@@ -239,14 +300,14 @@ def run_reference(args):
             torch, device = _t, _t.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     except Exception:
         pass
-    # bounded: ~1 s per step on 8 cores at the default sample
-    steps = max(1, min(args.steps, 20))
+    # bounded: a few seconds per step at the default sample
+    steps = max(1, min(args.steps, 8))
     r = cpu_scan_qps(args.rows, args.batch, args.k, args.cpu_sample_rows, steps, args.warmup, torch, device)
     line = {
         "impl": "reference",
         "metric": METRIC, "value": r["value"], "unit": "queries/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup,
-        "ms_per_step": r["ms_per_step_sample"] * (args.rows / min(args.cpu_sample_rows, args.rows)),
+        "ms_per_step": r["ms_per_step_sample"] * (args.rows / r["sample_rows"]),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "rows": args.rows, "batch": args.batch, "k": args.k,
                    "note": "reference arm = CPU exact scan (oracle port); Chroma HNSW is not runnable offline"},
@@ -374,31 +435,24 @@ def run_ours(args):
         verified &= bool((ok_pin.numpy() == kk_h).all())
 
     # ---- roofline of the scan kernel ---------------------------------------------------------------
-    hbm_peak, tf_peak, peak_kind = measured_peaks()
     rows_local = hi - lo
     elem = 2 if args.dtype == "bf16" else 4
-    scan_ms, scan_launches, _ = scan
-    avg_launch_s = (scan_ms / max(scan_launches, 1)) / 1e3
-    achieved = rows_local * DIM * elem / avg_launch_s / 1e9
-    roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-        "traffic": ncu_traffic("stream", rows_local), "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-        "kernel": "scan_stream_kernel", "bytes_per_launch": rows_local * DIM * elem,
-        "avg_launch_ms": avg_launch_s * 1e3, "launches_timed": scan_launches,
-        "scan_share_of_step": scan_ms / ms,
-    }
+    scan_ms, scan_launches, scan_searches = scan
+    roofline = roofline_of(b, args.path, k, rows_local, elem, scan_ms, scan_launches, scan_searches, ms)
+    uncertified = ix.stat("mma_uncertified_queries")
 
-    # ---- brief sweep over other batch sizes ---------------------------------------------------------
+    # ---- brief sweep over the other batch sizes of cfg4 (each with its own roofline) ------------------
     sweep = []
     for sb in [int(x) for x in args.sweep.split(",") if x.strip()]:
         if sb == b:
             continue
-        sms, _, sscan, _ = measure(sb, max(3, min(10, args.steps)), 3, profile=True)
         st = max(3, min(10, args.steps))
-        s_avg = (sscan[0] / max(sscan[1], 1)) / 1e3
+        sms, _, sscan, _ = measure(sb, st, 3, profile=True)
+        r = roofline_of(sb, args.path, k, rows_local, elem, sscan[0], sscan[1], sscan[2], sms)
         sweep.append({"batch": sb, "qps": sb * st / (sms / 1e3), "ms_per_step": sms / st,
-                      "scan_gbs": rows_local * DIM * elem / s_avg / 1e9,
-                      "scan_frac_of_hbm_peak": rows_local * DIM * elem / s_avg / 1e9 / hbm_peak})
+                      "kernel": r["kernel"], "bound": r["bound"], "frac": r["frac"], "achieved": r["achieved"],
+                      "unit": r["unit"], "hbm_gbs": r["hbm_gbs"], "hbm_frac": r["hbm_frac"],
+                      "tensor_tflops": r["tensor_tflops"], "tensor_frac_sustained": r["tensor_frac_sustained"]})
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------------
     cpu = None
@@ -422,6 +476,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
             "verified": verified,
+            "mma_uncertified_queries": uncertified,
             "sweep": sweep,
         }
         print(json.dumps(line))

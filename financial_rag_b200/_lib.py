@@ -35,6 +35,10 @@ SYMBOLS = {
     "fr_index_delete": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int64)]),
     "fr_index_append_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "fr_index_get_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "fr_index_export_raw": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "fr_index_import_raw": (c_int, [c_void_p, c_void_p, c_void_p, c_int64]),
+    "fr_index_lookup_rows": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "fr_index_get_stat": (c_int, [c_void_p, c_char_p, POINTER(c_int64)]),
     "fr_index_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64), POINTER(c_int64)]),
     "fr_index_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "fr_index_search_device": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -44,6 +48,9 @@ SYMBOLS = {
     "fr_rrf_fuse": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "fr_rrf_fuse_device": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p]),
+    "fr_maxsim_aggregate": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "fr_maxsim_aggregate_device": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                           c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -160,7 +160,11 @@ struct fr_index {
     cudaEvent_t last_use = nullptr;  // orders scratch reuse across caller streams
     DevBuf q_raw, q_prep, q_keys, partials, out_dist, out_keys, stage_vecs, stage_keys, stage_rows;
     DevBuf q_bf16, err_bound, sel, sel_keys, flags, fail, fb_partials, tau;  // K2 path
-    int mma_min_batch = 3;  // FR_PATH_AUTO: batches at least this large go to the tensor-core scan
+    int mma_min_batch = 2;  // FR_PATH_AUTO: batches at least this large go to the tensor-core scan
+    int mma_debug = 0;      // diagnostics (scripts/ablate_mma.py): results are wrong when non-zero
+    int mma_co_groups = 2;  // K2: query groups of 256 that share one corpus stream through L2
+    DevBuf stats;           // [0] queries K2 could not certify (re-scanned by the stream kernel), cumulative
+    int64_t n_searches = 0, n_queries = 0, n_mma_queries = 0;
     PinBuf pin;
     std::mutex mu;
     bool profile = false;
@@ -327,7 +331,8 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     const int ksel = fr::scan_mma_ksel(k);
     const int group = fr::scan_mma_group(B);
     const int nq_pad = ((B + group - 1) / group) * group;
-    const int grid = fr::scan_mma_plan_lists(ix->sm_count, ix->rows, B);  // partial lists per query
+    const fr::MmaPlan plan = fr::scan_mma_plan(ix->sm_count, ix->rows, B, ix->mma_co_groups);
+    const int grid = plan.lists_max;  // partial lists per query (at most)
     FR_CUDA(ix->q_bf16.need(static_cast<size_t>(nq_pad) * ix->dim * 2));
     FR_CUDA(ix->err_bound.need(static_cast<size_t>(B) * sizeof(float)));
     FR_CUDA(ix->partials.need(static_cast<size_t>(grid) * B * ksel * sizeof(uint64_t)));
@@ -336,6 +341,11 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     FR_CUDA(ix->flags.need(static_cast<size_t>(B)));
     FR_CUDA(ix->fail.need(static_cast<size_t>(B + 1) * sizeof(int)));
     FR_CUDA(ix->tau.need(static_cast<size_t>(B) * ksel * sizeof(uint32_t)));
+    if (!ix->stats.p) {
+        FR_CUDA(ix->stats.need(64));
+        FR_CUDA(cudaMemsetAsync(ix->stats.p, 0, 64, s));
+    }
+    ix->n_mma_queries += B;
     FR_CUDA(cudaMemsetAsync(ix->tau.p, 0, static_cast<size_t>(B) * ksel * sizeof(uint32_t), s));
     int *fail_count = static_cast<int *>(ix->fail.p);
     int *fail_list = fail_count + 1;
@@ -351,7 +361,8 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     ms.nq_total = B;
     ms.ksel = ksel;
     ms.partials = static_cast<uint64_t *>(ix->partials.p);
-    ms.lists = grid;
+    ms.plan = plan;
+    ms.dbg = ix->mma_debug;
     ms.tau_g = static_cast<uint32_t *>(ix->tau.p);
     ms.stream = s;
     ProfScope prof{ix, s};
@@ -361,19 +372,25 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     rc = prof.end();
     if (rc != FR_OK) return rc;
 
-    fr::MergeArgs ma{};
-    ma.packed = ms.partials;
-    ma.P = grid;
-    ma.shard_stride = static_cast<int64_t>(B) * ksel;
-    ma.B = B;
-    ma.k = ksel;
-    ma.shards = false;
-    ma.row_keys = ix->keys;
-    ma.l2 = false;
-    ma.out_packed = static_cast<uint64_t *>(ix->sel.p);
-    ma.out_keys = static_cast<int64_t *>(ix->sel_keys.p);
-    ma.stream = s;
-    FR_CUDA(fr::launch_merge_topk(ma));
+    // queries of the full launches hold plan.lists partial lists each, those of the tail launch plan.lists_tail
+    for (int part = 0; part < 2; ++part) {
+        const int q0 = part == 0 ? 0 : plan.tail_q0;
+        const int nq = part == 0 ? plan.tail_q0 : B - plan.tail_q0;
+        if (nq <= 0) continue;
+        fr::MergeArgs ma{};
+        ma.packed = ms.partials + static_cast<size_t>(q0) * ksel;
+        ma.P = part == 0 ? plan.lists : plan.lists_tail;
+        ma.shard_stride = static_cast<int64_t>(B) * ksel;
+        ma.B = nq;
+        ma.k = ksel;
+        ma.shards = false;
+        ma.row_keys = ix->keys;
+        ma.l2 = false;
+        ma.out_packed = static_cast<uint64_t *>(ix->sel.p) + static_cast<size_t>(q0) * ksel;
+        ma.out_keys = static_cast<int64_t *>(ix->sel_keys.p) + static_cast<size_t>(q0) * ksel;
+        ma.stream = s;
+        FR_CUDA(fr::launch_merge_topk(ma));
+    }
 
     fr::RescoreArgs ra{};
     ra.sel = static_cast<const uint64_t *>(ix->sel.p);
@@ -390,6 +407,7 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     ra.flags = static_cast<uint8_t *>(ix->flags.p);
     ra.fail_count = fail_count;
     ra.fail_list = fail_list;
+    ra.fail_total = static_cast<unsigned long long *>(ix->stats.p);
     ra.stream = s;
     FR_CUDA(fr::launch_rescore(ra));
 
@@ -431,10 +449,12 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
 int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *d_out_dist,
                      uint64_t *d_out_packed, int64_t *d_out_keys, cudaStream_t s) {
     if (B == 0) return FR_OK;
+    ix->n_searches += 1;
+    ix->n_queries += B;
     const bool eligible = mma_eligible(ix, k);
     if (ix->path == FR_PATH_MMA && !eligible)
         return fail(FR_EUNSUP,
-                    "FR_PATH_MMA serves bf16 x 384 cosine collections with k <= 32 and at least one row "
+                    "FR_PATH_MMA serves bf16 x 384 cosine collections with k <= 100 and at least one row "
                     "(this one: dtype %d, dim %d, metric %d, k %d, rows %lld)",
                     ix->dtype, ix->dim, ix->metric, k, (long long)ix->rows);
     const bool use_mma = eligible && (ix->path == FR_PATH_MMA || (ix->path == FR_PATH_AUTO && B >= ix->mma_min_batch));
@@ -522,7 +542,7 @@ int fr_index_destroy(fr_index *ix) {
         DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist,
                           &ix->out_keys, &ix->stage_vecs, &ix->stage_keys, &ix->stage_rows,
                           &ix->q_bf16, &ix->err_bound, &ix->sel, &ix->sel_keys, &ix->flags, &ix->fail,
-                          &ix->fb_partials, &ix->tau};
+                          &ix->fb_partials, &ix->tau, &ix->stats};
         for (DevBuf *b : bufs) b->release();
         ix->pin.release();
         for (auto &pr : ix->prof_events) {
@@ -550,6 +570,15 @@ int fr_index_set_option(fr_index *ix, const char *name, int64_t value) {
     if (std::strcmp(name, "mma_min_batch") == 0) {
         if (value < 1) return fail(FR_EINVAL, "mma_min_batch must be >= 1");
         ix->mma_min_batch = static_cast<int>(value);
+        return FR_OK;
+    }
+    if (std::strcmp(name, "mma_co_groups") == 0) {
+        if (value < 1 || value > 8) return fail(FR_EINVAL, "mma_co_groups must be in [1, 8]");
+        ix->mma_co_groups = static_cast<int>(value);
+        return FR_OK;
+    }
+    if (std::strcmp(name, "mma_debug") == 0) {
+        ix->mma_debug = static_cast<int>(value);
         return FR_OK;
     }
     if (std::strcmp(name, "profile") == 0) {
@@ -583,6 +612,34 @@ int fr_index_profile_read(fr_index *ix, double *out_scan_ms, int64_t *out_scan_l
     ix->prof_events.clear();
     ix->prof_launches = 0;
     return FR_OK;
+}
+
+int fr_index_get_stat(fr_index *ix, const char *name, int64_t *out) {
+    if (!ix || !name || !out) return fail(FR_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (std::strcmp(name, "searches") == 0) {
+        *out = ix->n_searches;
+        return FR_OK;
+    }
+    if (std::strcmp(name, "queries") == 0) {
+        *out = ix->n_queries;
+        return FR_OK;
+    }
+    if (std::strcmp(name, "mma_queries") == 0) {
+        *out = ix->n_mma_queries;
+        return FR_OK;
+    }
+    if (std::strcmp(name, "mma_uncertified_queries") == 0) {
+        *out = 0;
+        if (!ix->stats.p) return FR_OK;
+        DeviceGuard g(ix->device);
+        FR_CUDA(cudaDeviceSynchronize());
+        unsigned long long v = 0;
+        FR_CUDA(cudaMemcpy(&v, ix->stats.p, sizeof(v), cudaMemcpyDeviceToHost));
+        *out = static_cast<int64_t>(v);
+        return FR_OK;
+    }
+    return fail(FR_EINVAL, "unknown stat '%s'", name);
 }
 
 int fr_index_count(fr_index *ix, int64_t *out) {
@@ -766,6 +823,73 @@ int fr_index_get_rows(fr_index *ix, int64_t first_row, int64_t n, float *out_vec
     return FR_OK;
 }
 
+int fr_index_export_raw(fr_index *ix, int64_t first_row, int64_t n, void *out_rows, int64_t *out_keys) {
+    if (!ix) return fail(FR_EINVAL, "index is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (first_row < 0 || n < 0 || first_row + n > ix->rows)
+        return fail(FR_EINVAL, "rows [%lld, %lld) out of range (index holds %lld)", (long long)first_row,
+                    (long long)(first_row + n), (long long)ix->rows);
+    if (n == 0) return FR_OK;
+    DeviceGuard g(ix->device);
+    FR_CUDA(cudaDeviceSynchronize());
+    const size_t rb = ix->row_bytes();
+    if (out_rows)
+        FR_CUDA(cudaMemcpy(out_rows, ix->corpus + first_row * rb, static_cast<size_t>(n) * rb, cudaMemcpyDeviceToHost));
+    if (out_keys)
+        FR_CUDA(cudaMemcpy(out_keys, ix->keys + first_row, static_cast<size_t>(n) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return FR_OK;
+}
+
+int fr_index_import_raw(fr_index *ix, const void *rows, const int64_t *keys, int64_t n) {
+    if (!ix) return fail(FR_EINVAL, "index is NULL");
+    if (n < 0) return fail(FR_EINVAL, "n is negative");
+    if (n == 0) return FR_OK;
+    if (!rows || !keys) return fail(FR_EINVAL, "NULL buffer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (ix->rows + n > 0xfffffff0ll) return fail(FR_EUNSUP, "a shard holds at most 2^32-16 rows");
+    int rc = grow(ix, ix->rows + n, true);
+    if (rc != FR_OK) return rc;
+    cudaStream_t s = ix->stream;
+    rc = begin_use(ix, s);
+    if (rc != FR_OK) return rc;
+    const size_t rb = ix->row_bytes();
+    // the source is typically a memory-mapped shard file: copy in bounded pieces so the driver's
+    // staging of pageable memory stays small
+    const int64_t CH = static_cast<int64_t>((size_t(64) << 20) / rb);
+    for (int64_t lo = 0; lo < n; lo += CH) {
+        const int64_t m = (n - lo < CH) ? (n - lo) : CH;
+        FR_CUDA(cudaMemcpyAsync(ix->corpus + static_cast<size_t>(ix->rows + lo) * rb,
+                                static_cast<const uint8_t *>(rows) + static_cast<size_t>(lo) * rb,
+                                static_cast<size_t>(m) * rb, cudaMemcpyHostToDevice, s));
+        FR_CUDA(cudaStreamSynchronize(s));
+    }
+    FR_CUDA(cudaMemcpyAsync(ix->keys + ix->rows, keys, static_cast<size_t>(n) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    FR_CUDA(cudaStreamSynchronize(s));
+    for (int64_t i = 0; i < n; ++i)
+        if (keys[i] == fr::KEY_TOMBSTONE) ix->n_deleted += 1;
+    ix->rows += n;
+    ix->keymap_valid = false;
+    ix->keymap.clear();
+    return end_use(ix, s);
+}
+
+int fr_index_lookup_rows(fr_index *ix, const int64_t *keys, int64_t n, int64_t *out_rows) {
+    if (!ix) return fail(FR_EINVAL, "index is NULL");
+    if (n < 0) return fail(FR_EINVAL, "n is negative");
+    if (n == 0) return FR_OK;
+    if (!keys || !out_rows) return fail(FR_EINVAL, "NULL buffer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    int rc = rebuild_keymap(ix);
+    if (rc != FR_OK) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        auto it = ix->keymap.find(keys[i]);
+        out_rows[i] = it == ix->keymap.end() ? -1 : it->second;
+    }
+    return FR_OK;
+}
+
 int fr_index_search(fr_index *ix, const float *queries, int B, int k, float *out_dist, int64_t *out_keys) {
     int rc = check_search_args(ix, queries, B, k, out_dist, out_keys);
     if (rc != FR_OK || B == 0) return rc;
@@ -903,6 +1027,62 @@ int fr_rrf_fuse(int device, const int64_t *keys, int L, int B, int kp, int k_rrf
         if (e == cudaSuccess) e = cudaMemcpyAsync(out_keys, d_k, ob, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) rc = fail(FR_ECUDA, "rrf copy-back failed: %s", cudaGetErrorString(e));
+    }
+    cleanup();
+    return rc;
+}
+
+int fr_maxsim_aggregate_device(int device, const float *d_dist, const int64_t *d_keys, int B, int T, int kp,
+                               int group_shift, int k_out, double *d_out_score, int64_t *d_out_group, void *stream) {
+    if (B < 0 || T < 1 || kp < 1 || k_out < 1 || group_shift < 0 || group_shift > 62)
+        return fail(FR_EINVAL, "bad B/T/kp/group_shift/k_out");
+    if (static_cast<int64_t>(T) * kp > 1024) return fail(FR_EUNSUP, "T*kp = %d exceeds 1024 candidates per query", T * kp);
+    if (B == 0) return FR_OK;
+    if (!d_dist || !d_keys || !d_out_score || !d_out_group) return fail(FR_EINVAL, "NULL buffer");
+    int rc = check_device(device, nullptr);
+    if (rc != FR_OK) return rc;
+    DeviceGuard g(device);
+    fr::MaxSimArgs ma{d_dist, d_keys, B, T, kp, group_shift, k_out, d_out_score, d_out_group,
+                      static_cast<cudaStream_t>(stream)};
+    FR_CUDA(fr::launch_maxsim(ma));
+    return FR_OK;
+}
+
+int fr_maxsim_aggregate(int device, const float *dist, const int64_t *keys, int B, int T, int kp, int group_shift,
+                        int k_out, double *out_score, int64_t *out_group) {
+    if (B < 0 || T < 1 || kp < 1 || k_out < 1) return fail(FR_EINVAL, "bad B/T/kp/k_out");
+    if (B == 0) return FR_OK;
+    if (!dist || !keys || !out_score || !out_group) return fail(FR_EINVAL, "NULL buffer");
+    int rc = check_device(device, nullptr);
+    if (rc != FR_OK) return rc;
+    DeviceGuard g(device);
+    const size_t ne = static_cast<size_t>(B) * T * kp;
+    const size_t ob = static_cast<size_t>(B) * k_out * 8;
+    void *d_d = nullptr, *d_k = nullptr, *d_sc = nullptr, *d_g = nullptr;
+    cudaStream_t s = nullptr;
+    auto cleanup = [&]() {
+        for (void *p : {d_d, d_k, d_sc, d_g})
+            if (p) cudaFree(p);
+        if (s) cudaStreamDestroy(s);
+    };
+    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&d_d, ne * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_k, ne * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_sc, ob);
+    if (e == cudaSuccess) e = cudaMalloc(&d_g, ob);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dist, ne * sizeof(float), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_k, keys, ne * sizeof(int64_t), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(FR_ECUDA, "maxsim staging failed: %s", cudaGetErrorString(e));
+    }
+    rc = fr_maxsim_aggregate_device(device, static_cast<const float *>(d_d), static_cast<const int64_t *>(d_k), B, T, kp,
+                                    group_shift, k_out, static_cast<double *>(d_sc), static_cast<int64_t *>(d_g), s);
+    if (rc == FR_OK) {
+        e = cudaMemcpyAsync(out_score, d_sc, ob, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_group, d_g, ob, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = fail(FR_ECUDA, "maxsim copy-back failed: %s", cudaGetErrorString(e));
     }
     cleanup();
     return rc;

@@ -34,6 +34,17 @@ int scan_stream_fallback_grid(const ScanArgs &a, int sm_count);
 cudaError_t launch_scan_stream_fallback(const ScanArgs &a, const int *fail_count, const int *fail_list);
 
 // ---- K2 scan_topk_mma (tcgen05) ---------------------------------------------------------------
+struct MmaPlan {
+    int group;       // queries per group: 128 (one CTA per SM) or 256 (CTA pairs, cta_group::2)
+    int co;          // groups co-resident in a full launch (they share each corpus tile through L2)
+    int lists;       // corpus streams of a full launch = partial lists per query it writes
+    int tail_q0;     // first query served by the tail launch (== nq_total when there is none)
+    int co_tail;     // groups in the tail launch (0 = none)
+    int lists_tail;  // corpus streams of the tail launch
+    int lists_max;   // partials holds [lists_max][nq_total][ksel]
+};
+MmaPlan scan_mma_plan(int sm_count, int64_t n_rows, int nq_total, int co_max);
+
 struct MmaScanArgs {
     const void *corpus;         // [rows][384] bf16
     const int64_t *keys_or_null;
@@ -42,14 +53,15 @@ struct MmaScanArgs {
     int64_t n_rows;
     int nq_total;
     int ksel;                   // candidates kept per query (32 or 64), >= 2k
-    uint64_t *partials;         // [lists][nq_total][ksel]
-    int lists;                  // from scan_mma_plan_lists: CTAs (<= 128 queries) or CTA pairs
+    uint64_t *partials;         // [plan.lists_max][nq_total][ksel]; queries < plan.tail_q0 get plan.lists lists,
+                                // the others plan.lists_tail
+    MmaPlan plan;
+    int dbg;                    // diagnostics only (option "mma_debug"): 1 = no corpus loads, 2 = no accumulator reads
     uint32_t *tau_g;            // [ksel][nq_total] shared threshold slots (order_bits of a score), zeroed before the launches
     cudaStream_t stream;
 };
 int scan_mma_ksel(int k);  // 0 = k not served by the tensor-core path
 int scan_mma_group(int nq_total);  // queries per corpus pass: 128 (one CTA per SM) or 256 (CTA pairs)
-int scan_mma_plan_lists(int sm_count, int64_t n_rows, int nq_total);
 cudaError_t launch_prep_queries(const float *q, int nq, int nq_pad, void *qb, float *err_bound, cudaStream_t s);
 cudaError_t launch_scan_mma(const MmaScanArgs &a);
 
@@ -67,6 +79,7 @@ struct RescoreArgs {
     uint8_t *flags;        // [B] 1 = not certified
     int *fail_count;
     int *fail_list;        // [B]
+    unsigned long long *fail_total;  // cumulative count of uncertified queries (fr_index_get_stat)
     cudaStream_t stream;
 };
 cudaError_t launch_rescore(const RescoreArgs &a);
@@ -121,5 +134,16 @@ struct RrfArgs {
     cudaStream_t stream;
 };
 cudaError_t launch_rrf_fuse(const RrfArgs &a);
+
+// ---- K6 maxsim_aggregate -------------------------------------------------------------------------
+struct MaxSimArgs {
+    const float *dist;    // [B][T][kp] distances of the per-token hit lists
+    const int64_t *keys;  // [B][T][kp] row keys (-1 = empty); child group = key >> group_shift
+    int B, T, kp, group_shift, k_out;
+    double *out_score;    // [B][k_out]
+    int64_t *out_group;   // [B][k_out] (-1 padded)
+    cudaStream_t stream;
+};
+cudaError_t launch_maxsim(const MaxSimArgs &a);
 
 }  // namespace fr

@@ -62,19 +62,25 @@ constexpr int THREADS = 192;                   // warp 0 TMA, warp 1 MMA + TMEM 
 
 constexpr int PEND = 16;                       // unsorted pending candidates per query between compactions
 
+// Per-query candidate lists hold CAP = 32*KPL = k' entries.  For k' <= 64 they live in shared memory;
+// for k' = 128 (k up to 100) 128 queries x 1 KB would not fit beside the 96 KB query block, so the CTA
+// works directly in ITS slice of the `partials` array in global memory (L2-resident, touched only on
+// the rare compactions, and each lane only ever touches the entries congruent to its lane id).
 template <int KPL>
 struct SmemPlan {
-    static constexpr int STAGES = (KPL == 1) ? 5 : 3;
+    static constexpr bool LISTS_IN_SMEM = KPL <= 2;
+    static constexpr int STAGES = (KPL == 1) ? 5 : (KPL == 2 ? 3 : 6);
     static constexpr int CAP = 32 * KPL;
     static constexpr size_t A_OFF = 0;
     static constexpr size_t B_OFF = A_OFF + size_t(K_CHUNKS) * CHUNK_BYTES;
     static constexpr size_t LIST_OFF = B_OFF + size_t(STAGES) * CHUNK_BYTES;   // [128 queries][CAP] sorted
-    static constexpr size_t PEND_OFF = LIST_OFF + size_t(M_TILE) * CAP * 8;    // [4 warps][PEND][32] swizzled
+    static constexpr size_t PEND_OFF = LIST_OFF + (LISTS_IN_SMEM ? size_t(M_TILE) * CAP * 8 : 0);  // [4 warps][PEND][32] swizzled
     static constexpr size_t BAR_OFF = PEND_OFF + size_t(M_TILE) * PEND * 8;
     static constexpr size_t TOTAL = BAR_OFF + 256;
     static constexpr size_t ALLOC = TOTAL + 1024;  // slack to align the base to 1024 B
 };
-static_assert(SmemPlan<1>::ALLOC <= 232448 && SmemPlan<2>::ALLOC <= 232448, "exceeds 227 KB of shared memory");
+static_assert(SmemPlan<1>::ALLOC <= 232448 && SmemPlan<2>::ALLOC <= 232448 && SmemPlan<4>::ALLOC <= 232448,
+              "exceeds 227 KB of shared memory");
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -272,16 +278,16 @@ __device__ __forceinline__ uint64_t compact_query(uint64_t *list, const uint64_t
     uint64_t L[KPL];
 #pragma unroll
     for (int j = 0; j < KPL; ++j) L[j] = list[j * 32 + lane];
-    // top-32 of (last 32 of the list  U  pending): elementwise max against the reversed pending block
-    // is a bitonic sequence; everything ahead of it in the list stays in the top 32*KPL.
-    uint64_t m = bitonic_merge32_desc(umax64(L[KPL - 1], reverse32(p, lane)), lane);
-    if constexpr (KPL == 1) {
-        L[0] = m;
-    } else {
-        static_assert(KPL == 2, "lists hold 32 or 64 candidates");
-        const uint64_t r = reverse32(m, lane);
-        L[1] = bitonic_merge32_desc(umin64(L[0], r), lane);
-        L[0] = bitonic_merge32_desc(umax64(L[0], r), lane);
+    // Push the sorted pending block down the list, 32 entries at a time: the elementwise max / min of a
+    // descending block and the reversed carry are bitonic sequences holding the top / bottom 32 of their
+    // union; the bottom half carries on to the next block and what falls off the end is dropped.
+    uint64_t carry = p;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+        const uint64_t r = reverse32(carry, lane);
+        const uint64_t hi = bitonic_merge32_desc(umax64(L[j], r), lane);
+        if (j + 1 < KPL) carry = bitonic_merge32_desc(umin64(L[j], r), lane);
+        L[j] = hi;
     }
 #pragma unroll
     for (int j = 0; j < KPL; ++j) list[j * 32 + lane] = L[j];
@@ -291,13 +297,18 @@ __device__ __forceinline__ uint64_t compact_query(uint64_t *list, const uint64_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// grid = P * CG CTAs (P = partial lists per query); CTA pair p = blockIdx.x / CG takes corpus tiles
-// p, p + P, ... of 128*CG rows.  partials: [P][nq_total][ksel].
+// grid = P * co * CG CTAs.  P = partial lists per query = corpus "streams": stream p takes corpus
+// tiles p, p + P, ... of 128*CG rows.  `co` query groups (of 128*CG queries each) are co-resident:
+// CTA unit u = blockIdx.x / CG serves group u % co on stream u / co, so the `co` units that walk the
+// same tile sequence sit on neighbouring SMs, run in lock step (same work per tile) and all but the
+// first of them find the corpus tile in L2 -- HBM traffic per query drops by `co` in the regime
+// where one pass over the corpus is not HBM-bound any more.  partials: [P][nq_total][ksel].
+//   nq_launch = queries served by this launch (all groups), q_row0 = first of them.
 template <int KPL, int CG>
 __global__ void __launch_bounds__(THREADS, 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
-                const int64_t *__restrict__ keys_or_null, int64_t n_rows, int nq, int q_row0, int ksel,
-                uint64_t *__restrict__ partials, int nq_total, int q_offset, uint32_t *__restrict__ tau_g) {
+                const int64_t *__restrict__ keys_or_null, int64_t n_rows, int nq_launch, int q_row0_launch, int ksel,
+                uint64_t *__restrict__ partials, int nq_total, int co, uint32_t *__restrict__ tau_g, int dbg) {
     using Plan = SmemPlan<KPL>;
     constexpr int STAGES = Plan::STAGES;
     constexpr int CAP = Plan::CAP;
@@ -307,7 +318,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_a = smem + Plan::A_OFF;
     uint8_t *smem_b = smem + Plan::B_OFF;
-    uint64_t *lists = reinterpret_cast<uint64_t *>(smem + Plan::LIST_OFF);
+    uint64_t *lists_smem = reinterpret_cast<uint64_t *>(smem + Plan::LIST_OFF);
     uint64_t *pend_all = reinterpret_cast<uint64_t *>(smem + Plan::PEND_OFF);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Plan::BAR_OFF);
     // barrier slots: full[STAGES] | empty[STAGES] | tmem_full[4] | tmem_empty[4] | a_full | tmem_ptr
@@ -322,8 +333,13 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // position inside the CTA pair
-    const int pair = blockIdx.x / CG;
-    const int npairs = gridDim.x / CG;
+    const int unit = blockIdx.x / CG;
+    const int grp = unit % co;                       // query group of this CTA (pair)
+    const int pair = unit / co;                      // corpus stream
+    const int npairs = gridDim.x / (CG * co);
+    const int q_row0 = q_row0_launch + grp * (M_TILE * CG);  // first query row of the group
+    const int q_offset = q_row0;
+    const int nq = min(M_TILE * CG, nq_launch - grp * (M_TILE * CG));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -350,9 +366,14 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         }
     }
+    // this CTA's 128 candidate lists: shared memory, or (k' = 128) its own slice of `partials`
+    uint64_t *lists = Plan::LISTS_IN_SMEM
+                          ? lists_smem
+                          : partials + (static_cast<size_t>(pair) * nq_total + q_offset + static_cast<int>(rank) * M_TILE) * CAP;
     // epilogue warps clear their queries' lists while the allocation happens
     if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < M_TILE * CAP; i += 128) lists[i] = 0ull;
+        const int n_clear = Plan::LISTS_IN_SMEM ? M_TILE * CAP : max(0, min(M_TILE, nq - static_cast<int>(rank) * M_TILE)) * CAP;
+        for (int i = threadIdx.x - 64; i < n_clear; i += 128) lists[i] = 0ull;
     }
     tc_fence_before();
     __syncthreads();
@@ -382,8 +403,12 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll 1
                 for (int kc = 0; kc < K_CHUNKS; ++kc) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, CHUNK_BYTES * CG);
-                    tma_load_2d<CG>(smem_u32(smem_b + stage * CHUNK_BYTES), &tmap_c, l_full + 8 * stage, kc * K_CHUNK, row0);
+                    if (dbg & 1) {  // diagnostics: no corpus traffic at all, the MMAs re-read stale smem
+                        if (rank == 0) mbar_arrive(bar_full + 8 * stage);
+                    } else {
+                        if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, CHUNK_BYTES * CG);
+                        tma_load_2d<CG>(smem_u32(smem_b + stage * CHUNK_BYTES), &tmap_c, l_full + 8 * stage, kc * K_CHUNK, row0);
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -436,10 +461,16 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const bool live = my_q < nq_local;
         float tau = live ? -INFINITY : INFINITY;   // padded query rows never pass the gate
         int cnt = 0;                               // this query's pending (unsorted) candidates
-        // shared thresholds: slot[group][query]; this CTA (pair) publishes into group pair % ksel
-        const uint32_t *slots_q = tau_g + q_offset + static_cast<int>(rank) * M_TILE + (live ? my_q : 0);
-        uint32_t *my_slot = tau_g + static_cast<size_t>(pair % ksel) * nq_total + q_offset +
-                            static_cast<int>(rank) * M_TILE + (live ? my_q : 0);
+        // shared thresholds: slot[j][query], j < k'.  With at least k' streams, stream s raises slot s % k'
+        // to the best score it holds.  With fewer streams, stream s owns the slots s, s + S, s + 2S, ... and
+        // raises slot s + r*S to the score of the r-th best row it holds (read off its sorted list after a
+        // compaction; r = 0 also eagerly).  Either way every slot is backed by a row of its own, so the
+        // minimum over the k' slots is a score that k' distinct live rows reach.
+        const int q_cta0 = q_offset + static_cast<int>(rank) * M_TILE;  // first query of this CTA
+        const uint32_t *slots_q = tau_g + q_cta0 + (live ? my_q : 0);
+        uint32_t *my_slot = tau_g + static_cast<size_t>(pair % ksel) * nq_total + q_cta0 + (live ? my_q : 0);
+        // slots this stream owns (tiny corpora with fewer than k'/32 streams leave some slots empty: no sharing)
+        const int my_ranks = npairs >= ksel ? 1 : min(32, (ksel - pair + npairs - 1) / npairs);
         uint32_t best = 0, published = 0;          // order bits of the best score appended / published
         const uint32_t l_tempty = (CG == 2) ? map_to_cta(bar_tempty, 0) : bar_tempty;
         uint32_t it = 0;
@@ -464,6 +495,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * ACC_COLS;
 #pragma unroll 1
             for (int c = 0; c < ACC_COLS / 64; ++c) {
+                if (dbg & 2) break;  // diagnostics: accumulators are never read
                 float v[64];
                 tmem_ld64(tcol + c * 64, v);
                 float mx = v[0];
@@ -524,10 +556,17 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     while (fm) {
                         const int tq = __ffs(fm) - 1;
                         fm &= fm - 1;
-                        const uint64_t kth = compact_query<KPL>(my_lists + static_cast<size_t>(tq) * CAP, pend_w, tq, PEND, lane);
+                        uint64_t *lp = my_lists + static_cast<size_t>(tq) * CAP;
+                        const uint64_t kth = compact_query<KPL>(lp, pend_w, tq, PEND, lane);
                         if (lane == tq) {
                             cnt = 0;
                             tau = fmaxf(tau, key_threshold(kth));
+                        }
+                        if (my_ranks > 1 && lane < my_ranks) {  // lane r: entry r of the sorted list (its own store)
+                            const uint64_t e = lp[lane];
+                            if (e != 0ull)
+                                atomicMax(tau_g + static_cast<size_t>(pair + lane * npairs) * nq_total + q_cta0 + quarter * 32 + tq,
+                                          static_cast<uint32_t>(e >> 32));
                         }
                     }
                     __syncwarp();
@@ -553,8 +592,10 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             uint64_t *lp = my_lists + static_cast<size_t>(q) * CAP;
             if (n > 0) compact_query<KPL>(lp, pend_w, q, n, lane);
             __syncwarp();
-            uint64_t *dst = partials + (static_cast<size_t>(pair) * nq_total + q_offset + static_cast<int>(rank) * M_TILE + qq) * ksel;
-            for (int i = lane; i < ksel; i += 32) dst[i] = lp[i];
+            if constexpr (Plan::LISTS_IN_SMEM) {
+                uint64_t *dst = partials + (static_cast<size_t>(pair) * nq_total + q_cta0 + qq) * ksel;
+                for (int i = lane; i < ksel; i += 32) dst[i] = lp[i];
+            }
         }
     }
 
@@ -600,7 +641,7 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
                const uint8_t *__restrict__ corpus, const int64_t *__restrict__ row_keys,
                const float *__restrict__ err_bound, int k, float *__restrict__ out_dist,
                uint64_t *__restrict__ out_packed, int64_t *__restrict__ out_keys, uint8_t *__restrict__ flags,
-               int *__restrict__ fail_count, int *__restrict__ fail_list) {
+               int *__restrict__ fail_count, int *__restrict__ fail_list, unsigned long long *__restrict__ fail_total) {
     __shared__ float sq[DIM];
     __shared__ uint64_t exact[32 * KPL];
     const int b = blockIdx.x;
@@ -666,7 +707,10 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
     }
     if (lane == 0) {
         flags[b] = certified ? 0 : 1;
-        if (!certified) fail_list[atomicAdd(fail_count, 1)] = b;
+        if (!certified) {
+            fail_list[atomicAdd(fail_count, 1)] = b;
+            if (fail_total) atomicAdd(fail_total, 1ull);
+        }
     }
 }
 
@@ -703,7 +747,8 @@ static bool make_row_major_map(CUtensorMap *map, const void *base, int64_t rows)
 }  // namespace mma
 
 // ---- host launchers ---------------------------------------------------------------------------
-int scan_mma_ksel(int k) { return k <= 16 ? 32 : (k <= 32 ? 64 : 0); }
+// candidates kept per query: k' > k leaves the certification a margin (k' - k rows may overtake)
+int scan_mma_ksel(int k) { return k <= 16 ? 32 : (k <= 32 ? 64 : (k <= 100 ? 128 : 0)); }
 
 // queries served by one corpus pass: a single CTA per SM up to 128, CTA pairs (cta_group::2) above
 int scan_mma_group(int nq_total) { return nq_total <= mma::M_TILE ? mma::M_TILE : 2 * mma::M_TILE; }
@@ -716,13 +761,14 @@ cudaError_t launch_prep_queries(const float *q, int nq, int nq_pad, void *qb, fl
 
 namespace {
 template <int KPL, int CG>
-cudaError_t launch_one(const MmaScanArgs &a, const CUtensorMap &tq, const CUtensorMap &tc, int nq, int q0) {
+cudaError_t launch_one(const MmaScanArgs &a, const CUtensorMap &tq, const CUtensorMap &tc, int nq, int q0, int co,
+                       int lists) {
     auto kern = mma::scan_mma_kernel<KPL, CG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(mma::SmemPlan<KPL>::ALLOC));
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(static_cast<unsigned>(a.lists * CG));
+    cfg.gridDim = dim3(static_cast<unsigned>(lists * co * CG));
     cfg.blockDim = dim3(mma::THREADS);
     cfg.dynamicSmemBytes = mma::SmemPlan<KPL>::ALLOC;
     cfg.stream = a.stream;
@@ -733,50 +779,74 @@ cudaError_t launch_one(const MmaScanArgs &a, const CUtensorMap &tq, const CUtens
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, tq, tc, a.keys_or_null, a.n_rows, nq, q0, a.ksel, a.partials, a.nq_total, q0,
-                           a.tau_g);
+    e = cudaLaunchKernelEx(&cfg, kern, tq, tc, a.keys_or_null, a.n_rows, nq, q0, a.ksel, a.partials, a.nq_total, co,
+                           a.tau_g, a.dbg);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 }  // namespace
 
+// How a call of nq_total queries is laid over the SMs: full launches of `co` co-resident groups on
+// `lists` corpus streams each, and (when the number of groups is not a multiple of co) one tail
+// launch whose `co_tail` groups spread over `lists_tail` streams, so that no SM idles.
+MmaPlan scan_mma_plan(int sm_count, int64_t n_rows, int nq_total, int co_max) {
+    MmaPlan p{};
+    p.group = scan_mma_group(nq_total);
+    const int cg = p.group / mma::M_TILE;
+    const int groups = (nq_total + p.group - 1) / p.group;
+    p.co = groups < co_max ? groups : co_max;
+    if (p.co < 1) p.co = 1;
+    const int64_t tile_rows = static_cast<int64_t>(mma::N_TILE) * cg;
+    int64_t tiles = (n_rows + tile_rows - 1) / tile_rows;
+    if (tiles < 1) tiles = 1;
+    auto streams = [&](int co) {
+        int64_t units = sm_count / (cg * co);
+        if (units < 1) units = 1;
+        return static_cast<int>(tiles < units ? tiles : units);
+    };
+    p.lists = streams(p.co);
+    p.co_tail = groups % p.co;
+    p.tail_q0 = p.co_tail ? (groups - p.co_tail) * p.group : nq_total;
+    p.lists_tail = p.co_tail ? streams(p.co_tail) : 0;
+    p.lists_max = p.lists > p.lists_tail ? p.lists : p.lists_tail;
+    return p;
+}
+
 cudaError_t launch_scan_mma(const MmaScanArgs &a) {
     CUtensorMap tq, tc;
     if (!mma::make_row_major_map(&tq, a.queries_bf16, a.nq_pad) || !mma::make_row_major_map(&tc, a.corpus, a.n_rows))
         return cudaErrorNotSupported;
-    const int group = scan_mma_group(a.nq_total);
-    for (int q0 = 0; q0 < a.nq_total; q0 += group) {
-        const int nq = (a.nq_total - q0 < group) ? (a.nq_total - q0) : group;
+    const MmaPlan &p = a.plan;
+    const int per_launch = p.group * p.co;  // queries served by one full launch
+    for (int q0 = 0; q0 < a.nq_total; q0 += per_launch) {
+        const bool tail = q0 >= p.tail_q0;
+        const int nq = (a.nq_total - q0 < per_launch) ? (a.nq_total - q0) : per_launch;
+        const int co = tail ? p.co_tail : p.co;
+        const int lists = tail ? p.lists_tail : p.lists;
         cudaError_t e;
-        if (group == mma::M_TILE)
-            e = a.ksel <= 32 ? launch_one<1, 1>(a, tq, tc, nq, q0) : launch_one<2, 1>(a, tq, tc, nq, q0);
+        if (p.group == mma::M_TILE)
+            e = a.ksel <= 32   ? launch_one<1, 1>(a, tq, tc, nq, q0, co, lists)
+                : a.ksel <= 64 ? launch_one<2, 1>(a, tq, tc, nq, q0, co, lists)
+                               : launch_one<4, 1>(a, tq, tc, nq, q0, co, lists);
         else
-            e = a.ksel <= 32 ? launch_one<1, 2>(a, tq, tc, nq, q0) : launch_one<2, 2>(a, tq, tc, nq, q0);
+            e = a.ksel <= 32   ? launch_one<1, 2>(a, tq, tc, nq, q0, co, lists)
+                : a.ksel <= 64 ? launch_one<2, 2>(a, tq, tc, nq, q0, co, lists)
+                               : launch_one<4, 2>(a, tq, tc, nq, q0, co, lists);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
 }
 
-// number of partial lists per query (= CTAs, or CTA pairs above 128 queries)
-int scan_mma_plan_lists(int sm_count, int64_t n_rows, int nq_total) {
-    const int cg = scan_mma_group(nq_total) / mma::M_TILE;
-    const int64_t tile_rows = static_cast<int64_t>(mma::N_TILE) * cg;
-    const int64_t tiles = (n_rows + tile_rows - 1) / tile_rows;
-    const int64_t units = sm_count / cg;
-    if (tiles < 1) return 1;
-    return static_cast<int>(tiles < units ? tiles : units);
-}
-
 cudaError_t launch_rescore(const RescoreArgs &a) {
     if (a.B <= 0) return cudaSuccess;
-    if (a.ksel <= 32)
-        mma::rescore_kernel<1><<<a.B, 128, 0, a.stream>>>(a.sel, a.ksel, a.queries, a.corpus, a.row_keys, a.err_bound,
-                                                         a.k, a.out_dist, a.out_packed, a.out_keys, a.flags,
-                                                         a.fail_count, a.fail_list);
-    else
-        mma::rescore_kernel<2><<<a.B, 128, 0, a.stream>>>(a.sel, a.ksel, a.queries, a.corpus, a.row_keys, a.err_bound,
-                                                         a.k, a.out_dist, a.out_packed, a.out_keys, a.flags,
-                                                         a.fail_count, a.fail_list);
+#define FR_RESCORE(KPL)                                                                                       \
+    mma::rescore_kernel<KPL><<<a.B, 128, 0, a.stream>>>(a.sel, a.ksel, a.queries, a.corpus, a.row_keys, a.err_bound, \
+                                                       a.k, a.out_dist, a.out_packed, a.out_keys, a.flags,       \
+                                                       a.fail_count, a.fail_list, a.fail_total)
+    if (a.ksel <= 32) FR_RESCORE(1);
+    else if (a.ksel <= 64) FR_RESCORE(2);
+    else FR_RESCORE(4);
+#undef FR_RESCORE
     count_launch();
     return cudaGetLastError();
 }

@@ -79,6 +79,16 @@ class ShardIndex:
         """Pin the kernel regime: 'auto' | 'stream' (K1) | 'mma' (K2).  Tests and bench use it."""
         check(self._lib.fr_index_set_option(self._handle(), b"path", _PATHS[path]))
 
+    def set_option(self, name: str, value: int) -> None:
+        """Tuning knobs of the C ABI: 'mma_min_batch', 'mma_co_groups', 'path', 'profile'."""
+        check(self._lib.fr_index_set_option(self._handle(), name.encode(), int(value)))
+
+    def stat(self, name: str) -> int:
+        """'searches' | 'queries' | 'mma_queries' | 'mma_uncertified_queries' since creation."""
+        out = ctypes.c_int64()
+        check(self._lib.fr_index_get_stat(self._handle(), name.encode(), ctypes.byref(out)))
+        return int(out.value)
+
     def set_profile(self, on: bool) -> None:
         """Bracket every scan launch with CUDA events (bench.py's roofline line)."""
         check(self._lib.fr_index_set_option(self._handle(), b"profile", 1 if on else 0))

@@ -72,6 +72,12 @@ int fr_index_destroy(fr_index *idx);
 int fr_index_reserve(fr_index *idx, int64_t rows);
 int fr_index_set_option(fr_index *idx, const char *name, int64_t value);
 
+/* Counters since creation (bench.py and tests report them): "searches", "queries", "mma_queries"
+ * (queries served by the tensor-core scan) and "mma_uncertified_queries" (of those, the ones whose
+ * bf16-query selection could not be certified against the fp32-query order and were re-scanned by
+ * the streaming kernel inside the same call). */
+int fr_index_get_stat(fr_index *idx, const char *name, int64_t *out);
+
 /* Replaces Collection.count()                     parent_child/chroma_child_store.py:76-80
  * count = live rows; rows = physical rows including deleted ones. */
 int fr_index_count(fr_index *idx, int64_t *out_count);
@@ -95,6 +101,17 @@ int fr_index_append_device(fr_index *idx, const float *d_vecs, const int64_t *d_
  * out_vecs: n x dim fp32 (bf16 rows are widened), out_keys: n (INT64_MIN marks a deleted row). */
 int fr_index_get_rows(fr_index *idx, int64_t first_row, int64_t n, float *out_vecs,
                       int64_t *out_keys);
+
+/* ---- persistence (replaces the .chroma_children/ sqlite WAL + HNSW bin files) ------
+ * The shard's rows exactly as they sit in HBM (bf16 or fp32, already normalised for cosine) and the
+ * key of every physical row (INT64_MIN = deleted).  export -> a flat shard file; import appends rows
+ * verbatim (no normalisation, no key lookup), so restart = mmap + H2D and a reloaded shard returns
+ * bit-identical results.  out_rows / rows: n x dim x sizeof(storage type) bytes, host memory.
+ * fr_index_lookup_rows: physical row of each key (-1 = absent), for incremental flushes. */
+int fr_index_export_raw(fr_index *idx, int64_t first_row, int64_t n, void *out_rows,
+                        int64_t *out_keys);
+int fr_index_import_raw(fr_index *idx, const void *rows, const int64_t *keys, int64_t n);
+int fr_index_lookup_rows(fr_index *idx, const int64_t *keys, int64_t n, int64_t *out_rows);
 
 /* ---- the hot path -------------------------------------------------------------------------
  * Replaces Collection.query(query_embeddings=[...], n_results=k,
@@ -137,6 +154,20 @@ int fr_rrf_fuse(int device, const int64_t *keys, int L, int B, int kp, int k_rrf
                 double *out_score, int64_t *out_keys);
 int fr_rrf_fuse_device(int device, const int64_t *d_keys, int L, int B, int kp, int k_rrf,
                        int k_out, double *d_out_score, int64_t *d_out_keys, void *stream);
+
+/* ---- multi-vector (late interaction) aggregation ---------------------------------
+ * Replaces the per-token loop of parent_child/multivector_store.py:150-176.  The T query-token vectors
+ * are searched as ONE batch (fr_index_search with B = T, k = kp); this call then folds the T hit lists:
+ * per token the best (1.0 - dist) of each child, summed over tokens in token order (fp64), sorted by
+ * score descending with ties in first-seen order, cut to k_out.  The child ("group") of a token row is
+ * key >> group_shift (the host maps "child:tok" ids to keys (child_ordinal << group_shift) | tok).
+ * dist/keys: [B][T][kp] (B independent queries of T tokens; key -1 = empty slot);
+ * out_score/out_group: [B][k_out], padded with 0.0 / -1. */
+int fr_maxsim_aggregate(int device, const float *dist, const int64_t *keys, int B, int T, int kp,
+                        int group_shift, int k_out, double *out_score, int64_t *out_group);
+int fr_maxsim_aggregate_device(int device, const float *d_dist, const int64_t *d_keys, int B, int T,
+                               int kp, int group_shift, int k_out, double *d_out_score,
+                               int64_t *d_out_group, void *stream);
 
 #ifdef __cplusplus
 }

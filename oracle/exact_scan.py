@@ -180,6 +180,41 @@ def exact_topk(
     return merge_topk(parts, k)
 
 
+def exact_topk_thresholded(
+    queries: np.ndarray, corpus: np.ndarray, k: int, space: str = "cosine", chunk_rows: int = 1 << 16
+) -> Tuple[np.ndarray, np.ndarray]:
+    """Same result as ``exact_topk(..., prepared=True)``, organised the way a CPU scan is fast at
+    large batches: one sgemm per corpus chunk, then a vectorised compare against each query's
+    running k-th distance so only the few rows that can still enter a list are touched.
+    Used by bench.py's CPU arm; checked against ``exact_topk`` in tests/test_oracle_golden.py."""
+    space = canonical_space(space)
+    q = np.ascontiguousarray(queries, dtype=np.float32)
+    b, n = q.shape[0], corpus.shape[0]
+    best_d = np.full((b, k), np.inf, dtype=np.float32)
+    best_r = np.full((b, k), -1, dtype=np.int64)
+    for lo in range(0, n, chunk_rows):
+        c = np.ascontiguousarray(corpus[lo : lo + chunk_rows], dtype=np.float32)
+        d = distances(q, c, space)
+        if lo == 0 or not np.isfinite(best_d[:, -1]).all():
+            pd, pr = _select_topk_rows(d, k, lo)
+            best_d, best_r = merge_topk([(best_d, best_r), (pd, pr)], k)
+            continue
+        qi, ri = np.nonzero(d <= best_d[:, -1][:, None])  # ties at the boundary stay candidates
+        if qi.size == 0:
+            continue
+        starts = np.flatnonzero(np.r_[True, qi[1:] != qi[:-1]])
+        ends = np.r_[starts[1:], qi.size]
+        for s0, e0 in zip(starts, ends):
+            i = int(qi[s0])
+            cd = np.concatenate([best_d[i], d[i, ri[s0:e0]]])
+            cr = np.concatenate([best_r[i], ri[s0:e0] + lo])
+            valid = np.nonzero(cr >= 0)[0]
+            order = valid[np.lexsort((cr[valid], cd[valid]))][:k]
+            best_d[i, : len(order)] = cd[order]
+            best_r[i, : len(order)] = cr[order]
+    return best_d, best_r
+
+
 def distances_for_rows(
     queries: np.ndarray, corpus: np.ndarray, rows: np.ndarray, space: str = "cosine", storage: str = "f32"
 ) -> np.ndarray:

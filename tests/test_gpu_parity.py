@@ -412,8 +412,16 @@ MMA_CASES = [
     (255, 256, 10),
     (257, 130, 3),
     (100000, 300, 10),   # second pass holds 44 queries: the pair's second CTA has none
-    (40000, 513, 5),
+    (40000, 513, 5),     # two co-resident groups + a tail launch with one query
     (1, 256, 1),
+    (60000, 768, 10),    # full launch of two groups, tail launch of one group on all CTA pairs
+    (30000, 1030, 8),    # two full launches + tail
+    # k' = 128 (k up to 100): candidate lists live in the CTA's slice of the partials array
+    (70001, 200, 50),
+    (20000, 300, 100),
+    (500, 4, 100),
+    (90, 2, 100),        # fewer rows than k
+    (150000, 20, 64),
 ]
 
 
@@ -443,6 +451,32 @@ def test_mma_path_matches_oracle_and_stream(frb, n, B, k):
     ix.close()
 
 
+@pytest.mark.gpu
+def test_mma_co_resident_groups_do_not_change_results(frb):
+    """Query groups that share corpus tiles through L2 (option mma_co_groups) are a scheduling
+    choice only: ids and distances are bit-identical for 1, 2 and 3 co-resident groups, and the
+    uncertified-query counter stays at zero on tie-free data."""
+    n, B, k = 50000, 700, 10
+    corpus = make_corpus(n, 384, seed=4242)
+    queries = make_queries(B, corpus, seed=4243)
+    ix = build_index(frb, corpus, "cosine", "bf16")
+    ix.set_path("mma")
+    ref = None
+    for co in (1, 2, 3):
+        ix.set_option("mma_co_groups", co)
+        d, kk = ix.search(queries, k)
+        if ref is None:
+            ref = (d, kk)
+            assert_matches_oracle(d, keys_to_rows(kk, KEY_BASE), queries, corpus, k, "cosine", "bf16",
+                                  stored=stored_rows(ix), label="mma co=1")
+        else:
+            np.testing.assert_array_equal(kk, ref[1])
+            np.testing.assert_array_equal(d, ref[0])
+    assert ix.stat("mma_queries") == 3 * B and ix.stat("queries") == 3 * B and ix.stat("searches") == 3
+    assert ix.stat("mma_uncertified_queries") == 0
+    ix.close()
+
+
 def test_mma_certification_fallback_on_mass_ties(frb):
     """More exact duplicates than the k' = 32 selection slots: the tensor-core selection cannot be
     certified, so the query must be re-scanned by the stream kernel and still return the LOWEST
@@ -459,6 +493,7 @@ def test_mma_certification_fallback_on_mass_ties(frb):
     d_s, k_s = ix.search(queries, k)
     ix.set_path("mma")
     d_m, k_m = ix.search(queries, k)
+    assert ix.stat("mma_uncertified_queries") >= 2  # queries 1 and 4 went through the re-scan
     np.testing.assert_array_equal(keys_to_rows(k_m[1], KEY_BASE), dup_rows[:k])
     np.testing.assert_array_equal(k_m[1], k_s[1])
     np.testing.assert_array_equal(k_m[4], k_s[4])
@@ -489,11 +524,11 @@ def test_mma_path_with_deletes_and_eligibility(frb):
     ix.set_path("auto")
     d2, k2 = ix.search(queries, k)
     np.testing.assert_array_equal(k2, k1)
-    d3, k3 = ix.search(queries, 33)  # k' would not fit 2k: auto serves it with the stream kernel
+    d3, k3 = ix.search(queries, 101)  # k' = 128 leaves no margin: auto serves it with the stream kernel
     np.testing.assert_array_equal(k3[:, :k], k1)
     ix.set_path("mma")
     with pytest.raises(FrError):
-        ix.search(queries, 33)
+        ix.search(queries, 101)
     ix.close()
     for kw in ({"dtype": "f32"}, {"space": "l2"}, {"dim": 768}):
         args = {"dim": 384, "space": "cosine", "dtype": "bf16"}

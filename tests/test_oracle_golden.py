@@ -159,3 +159,24 @@ def test_edge_cases():
     live = np.array([True, False, True])
     d, r = ox.exact_topk(q, c, 3, live=live)
     assert r.tolist() == [[0, 2, -1], [0, 2, -1]]
+
+
+def test_thresholded_cpu_scan_equals_exact_scan():
+    """bench.py's CPU arm (sgemm per chunk + running-threshold compare) returns exactly what the
+    plain oracle scan returns, ties and ragged last chunk included."""
+    from oracle import exact_scan as ox
+
+    rng = np.random.default_rng(5)
+    corpus = rng.standard_normal((5000, 64)).astype(np.float32)
+    corpus[4000] = corpus[17]
+    corpus[1234] = corpus[17]
+    corpus = ox.prepare_corpus(corpus, "cosine", "f32")
+    q = ox.prepare_queries(np.concatenate([rng.standard_normal((6, 64)).astype(np.float32), corpus[17:18]]), "cosine")
+    for k in (1, 10, 33):
+        d0, r0 = ox.exact_topk(q, corpus, k, "cosine", "f32", prepared=True)
+        d1, r1 = ox.exact_topk_thresholded(q, corpus, k, "cosine", chunk_rows=700)
+        # sgemm over a different chunk shape may round the last bit differently
+        assert (r0 == r1).all() and np.abs(d0 - d1).max() <= 5e-7
+    d2, r2 = ox.exact_topk_thresholded(q, corpus[:7], 10, "cosine", chunk_rows=3)
+    d3, r3 = ox.exact_topk(q, corpus[:7], 10, "cosine", "f32", prepared=True)
+    assert (r2 == r3).all() and np.allclose(d2, d3, rtol=0, atol=5e-7)
