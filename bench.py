@@ -204,7 +204,7 @@ def roofline_of(batch, path, k, rows_local, elem, scan_ms, scan_launches, search
         "peak": tf_sustained if tensor_bound else hbm_peak,
         "unit": "TFLOP/s" if tensor_bound else "GB/s",
         "frac": (tfs / tf_sustained) if tensor_bound else (gbs / hbm_peak),
-        "traffic": ncu_traffic(kind, rows_local),
+        "traffic": ncu_traffic(kind + ("_co2" if kind == "mma_cg2" and q_per_launch > MMA_GROUP else ""), rows_local),
         "peak_kind": (f"{peak_kind} (MEASURED_PEAKS.json bf16_tflops_sustained: the kernel runs inside a long step; "
                       f"burst {tf_burst})" if tensor_bound else f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)"),
         "kernel": kernel,
@@ -335,6 +335,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL_DEBUG=VERSION/INFO makes NCCL print to stdout, which must carry exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("FR_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
 
     import financial_rag_b200 as frb

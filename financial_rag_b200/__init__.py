@@ -6,11 +6,13 @@ fallback: importing the compute entry points without libfrb200.so raises ImportE
 """
 from .child_store import B200ChildStore
 from .collection import B200Client, B200Collection, PersistentClient, reset_registry
-from .index import ShardIndex, canonical_space, merge_shards_device, rrf_fuse_device, rrf_fuse_host
+from .index import (ShardIndex, canonical_space, maxsim_aggregate_device, maxsim_aggregate_host, merge_shards_device,
+                    rrf_fuse_device, rrf_fuse_host)
+from .multivector_store import B200MultiVectorChildStore
 from .vector_store_factory import get_child_vector_store
 
 __all__ = [
-    "B200ChildStore", "B200Client", "B200Collection", "PersistentClient", "ShardIndex",
-    "canonical_space", "get_child_vector_store", "merge_shards_device", "reset_registry",
-    "rrf_fuse_device", "rrf_fuse_host",
+    "B200ChildStore", "B200Client", "B200Collection", "B200MultiVectorChildStore", "PersistentClient", "ShardIndex",
+    "canonical_space", "get_child_vector_store", "maxsim_aggregate_device", "maxsim_aggregate_host",
+    "merge_shards_device", "reset_registry", "rrf_fuse_device", "rrf_fuse_host",
 ]

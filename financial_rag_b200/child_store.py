@@ -62,8 +62,8 @@ class B200ChildStore:
                 project_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
                 self.persist_dir = os.path.join(project_root, ".chroma_children")
         self.collection_name = collection or os.getenv("CHILD_VECTOR_COLLECTION", "parent_child_children")
-        # The registry key is the directory NAME; nothing is written there until persistence lands
-        # ("next" rows), so the directory is not created.
+        # The registry key is the directory name; the collection persists itself under
+        # <persist_dir>/<collection>.b200/ at its first mutation (collection.py).
         self.client = B200Client(path=self.persist_dir)
         self.col = self.client.get_or_create_collection(name=self.collection_name, metadata={"hnsw:space": "cosine"})
 
@@ -80,6 +80,8 @@ class B200ChildStore:
             meta = {"parent_id": str(c.parent_id), "snippet": c.content}
             if getattr(c, "context", None):
                 meta["context"] = c.context
+            if getattr(c, "document_id", None) is not None:  # extension: lets the doc-level helpers below work
+                meta["document_id"] = str(c.document_id)
             metadatas.append(meta)
             if hasattr(emb, "detach"):
                 emb = emb.detach().cpu().numpy()
@@ -118,3 +120,14 @@ class B200ChildStore:
             return int(self.col.count())
         except Exception:
             return -1
+
+    # The reference probes both with hasattr() and finds neither on ChromaChildStore
+    # (api_server.py:230-231, 267-270); children ingested with a ``document_id`` attribute support them.
+    def count_for_document(self, doc_id) -> int:
+        return len(self.col.keys_where("document_id", str(doc_id)))
+
+    def delete_by_document_id(self, doc_id) -> int:
+        keys = self.col.keys_where("document_id", str(doc_id))
+        if keys:
+            self.col.delete(where={"document_id": str(doc_id)})
+        return len(keys)

@@ -14,10 +14,23 @@ Vectors live in HBM inside the ShardIndex; ids / metadata (the payload the refer
 ``{"parent_id", "snippet", "context"}``) stay on the host keyed by the int64 row key.  The GPU index
 must outlive the per-request store objects the reference constructs (rag_backend.py:611-643), so
 collections live in a process-global registry keyed by (persist_dir, name).
+
+Persistence replaces chromadb's ``.chroma_children/`` (sqlite WAL + HNSW bin files)
+with one directory per collection, ``<persist_dir>/<name>.b200/``:
+    meta.json        format version, name, space, dtype, dim, number of valid rows, key counter
+    rows.bin         [rows][dim] bf16/fp32 -- the rows bit for bit as they sit in HBM
+    keys.bin         [rows] int64 row keys in insertion order (INT64_MIN = deleted row)
+    payload.sqlite3  payload(key INTEGER PRIMARY KEY, id TEXT, metadata TEXT, document TEXT)
+Restart = mmap rows.bin/keys.bin + one H2D copy (fr_index_import_raw): a reloaded collection returns
+bit-identical results.  Like chromadb's PersistentClient, every mutation is flushed before the call
+returns (``B200_CHILD_AUTOPERSIST=0`` turns that off; ``persist()`` flushes on demand); flushes are
+incremental -- appended rows are appended, overwritten / deleted rows are patched in place.
 """
 from __future__ import annotations
 
+import json
 import os
+import sqlite3
 import threading
 from typing import Any, Dict, List, Optional, Sequence
 
@@ -26,6 +39,12 @@ import numpy as np
 from .index import FR_MAX_K, ShardIndex, canonical_space
 
 _INT64_MAX = (1 << 63) - 1
+_INT64_MIN = -(1 << 63)
+FORMAT_VERSION = 1
+
+
+def _autopersist() -> bool:
+    return os.getenv("B200_CHILD_AUTOPERSIST", "1").strip().lower() not in ("0", "false", "no", "off")
 
 
 def _as_matrix(embeddings, dim: Optional[int]) -> np.ndarray:
@@ -48,8 +67,12 @@ def _as_matrix(embeddings, dim: Optional[int]) -> np.ndarray:
 
 class B200Collection:
     def __init__(self, name: str, metadata: Optional[Dict[str, Any]] = None, *, dtype: Optional[str] = None,
-                 device: Optional[int] = None):
+                 device: Optional[int] = None, directory: Optional[str] = None):
         self.name = name
+        self.directory = directory          # <persist_dir>/<name>.b200, None = memory only
+        self._persisted_rows = 0            # rows already in rows.bin / keys.bin
+        self._dirty_rows: set = set()       # physical rows < _persisted_rows whose bits or key changed
+        self._dirty_payload: set = set()    # keys whose payload row must be rewritten (or removed)
         self.metadata = dict(metadata or {})
         self.space = canonical_space(self.metadata.get("hnsw:space"))
         self.dtype = dtype or os.getenv("B200_CHILD_DTYPE", "bf16")
@@ -82,9 +105,10 @@ class B200Collection:
         self._key_of_id[id_str] = key
         return key
 
-    def _ensure_index(self, dim: int) -> ShardIndex:
+    def _ensure_index(self, dim: int, reserve_rows: int = 0) -> ShardIndex:
         if self._index is None:
-            self._index = ShardIndex(dim=dim, space=self.space, dtype=self.dtype, device=self.device)
+            self._index = ShardIndex(dim=dim, space=self.space, dtype=self.dtype, device=self.device,
+                                     reserve_rows=reserve_rows)
         return self._index
 
     # -- chromadb.Collection surface -------------------------------------------------------------
@@ -92,8 +116,20 @@ class B200Collection:
         with self._lock:
             return 0 if self._index is None else self._index.count()
 
+    def key_of(self, id_str: str) -> Optional[int]:
+        with self._lock:
+            k = self._key_of_id.get(str(id_str))
+            return k if k is not None and k in self._payload else None
+
+    def metadata_of_key(self, key: int) -> Optional[dict]:
+        with self._lock:
+            p = self._payload.get(int(key))
+            return p["metadata"] if p is not None else None
+
     def upsert(self, ids: Sequence[str], embeddings=None, metadatas: Optional[Sequence[Optional[dict]]] = None,
-               documents: Optional[Sequence[Optional[str]]] = None) -> None:
+               documents: Optional[Sequence[Optional[str]]] = None, keys: Optional[Sequence[int]] = None) -> None:
+        """``keys`` (ours, not chromadb's): explicit int64 row keys for the ids, for callers that encode
+        structure in them (multivector_store.py: (child_ordinal << 16) | token_idx)."""
         if embeddings is None:
             raise ValueError("B200Collection needs explicit embeddings (the reference always passes them)")
         ids = [str(i) for i in ids]
@@ -104,6 +140,14 @@ class B200Collection:
             if m.shape[0] != len(ids):
                 raise ValueError("ids and embeddings differ in length")
             idx = self._ensure_index(m.shape[1])
+            if keys is not None:
+                if len(keys) != len(ids):
+                    raise ValueError("ids and keys differ in length")
+                for i, k in zip(ids, keys):
+                    old = self._key_of_id.get(i)
+                    if old is not None and old != int(k) and old in self._payload:
+                        raise ValueError(f"id {i!r} is already stored under key {old}")
+                    self._key_of_id[i] = int(k)
             keys = np.array([self._key_for(i) for i in ids], dtype=np.int64)
             idx.upsert(m, keys)
             for j, (i, k) in enumerate(zip(ids, keys.tolist())):
@@ -112,6 +156,12 @@ class B200Collection:
                     "metadata": dict(metadatas[j]) if metadatas is not None and metadatas[j] is not None else None,
                     "document": documents[j] if documents is not None else None,
                 }
+            if self.directory is not None:
+                rows = idx.lookup_rows(keys)
+                self._dirty_rows.update(int(r) for r in rows.tolist() if 0 <= r < self._persisted_rows)
+                self._dirty_payload.update(keys.tolist())
+                if _autopersist():
+                    self.persist()
 
     def add(self, ids: Sequence[str], embeddings=None, metadatas=None, documents=None) -> None:
         """chromadb ``add`` leaves existing ids untouched; only new ids are inserted."""
@@ -149,11 +199,18 @@ class B200Collection:
                     if all(md.get(f) == v for f, v in where.items()):
                         keys.append(k)
             if keys:
-                self._index.delete(np.array(keys, dtype=np.int64))
+                karr = np.array(keys, dtype=np.int64)
+                if self.directory is not None:
+                    rows = self._index.lookup_rows(karr)
+                    self._dirty_rows.update(int(r) for r in rows.tolist() if 0 <= r < self._persisted_rows)
+                    self._dirty_payload.update(keys)
+                self._index.delete(karr)
                 for k in keys:
                     p = self._payload.pop(k, None)
                     if p is not None:
                         self._key_of_id.pop(p["id"], None)
+                if self.directory is not None and _autopersist():
+                    self.persist()
 
     def get(self, ids: Optional[Sequence[str]] = None, include: Optional[Sequence[str]] = None,
             where: Optional[dict] = None, limit: Optional[int] = None) -> Dict[str, Any]:
@@ -216,6 +273,129 @@ class B200Collection:
                 "included": include,
             }
 
+    # -- persistence ------------------------------------------------------------------------------
+    def _paths(self):
+        d = self.directory
+        return (os.path.join(d, "meta.json"), os.path.join(d, "rows.bin"), os.path.join(d, "keys.bin"),
+                os.path.join(d, "payload.sqlite3"))
+
+    def persist(self) -> None:
+        """Flush the collection to ``self.directory`` (incremental; see the module docstring)."""
+        if self.directory is None:
+            raise ValueError("collection was created without a persist directory")
+        with self._lock:
+            os.makedirs(self.directory, exist_ok=True)
+            meta_p, rows_p, keys_p, pay_p = self._paths()
+            idx = self._index
+            n_rows = idx.rows() if idx is not None else 0
+            if idx is not None:
+                rb = idx.row_bytes
+                # (1) rows appended since the last flush
+                if n_rows > self._persisted_rows:
+                    with open(rows_p, "r+b" if os.path.exists(rows_p) else "w+b") as fr, \
+                            open(keys_p, "r+b" if os.path.exists(keys_p) else "w+b") as fk:
+                        fr.truncate(self._persisted_rows * rb)
+                        fk.truncate(self._persisted_rows * 8)
+                        fr.seek(self._persisted_rows * rb)
+                        fk.seek(self._persisted_rows * 8)
+                        step = max(1, (64 << 20) // rb)
+                        for lo in range(self._persisted_rows, n_rows, step):
+                            rows, keys = idx.export_raw(lo, min(step, n_rows - lo))
+                            fr.write(rows.tobytes())
+                            fk.write(keys.tobytes())
+                # (2) rows overwritten in place or deleted since the last flush
+                dirty = sorted(r for r in self._dirty_rows if r < self._persisted_rows)
+                if dirty:
+                    mm_r = np.memmap(rows_p, dtype=np.uint8, mode="r+", shape=(n_rows, rb))
+                    mm_k = np.memmap(keys_p, dtype=np.int64, mode="r+", shape=(n_rows,))
+                    for r in dirty:
+                        rows, keys = idx.export_raw(r, 1)
+                        mm_r[r] = rows[0]
+                        mm_k[r] = keys[0]
+                    mm_r.flush()
+                    mm_k.flush()
+                    del mm_r, mm_k
+            # (3) payload rows
+            db = sqlite3.connect(pay_p)
+            try:
+                db.execute("CREATE TABLE IF NOT EXISTS payload (key INTEGER PRIMARY KEY, id TEXT NOT NULL, "
+                           "metadata TEXT, document TEXT)")
+                gone = [(k,) for k in self._dirty_payload if k not in self._payload]
+                live = [(k, self._payload[k]["id"],
+                         json.dumps(self._payload[k]["metadata"]) if self._payload[k]["metadata"] is not None else None,
+                         self._payload[k]["document"]) for k in self._dirty_payload if k in self._payload]
+                if gone:
+                    db.executemany("DELETE FROM payload WHERE key = ?", gone)
+                if live:
+                    db.executemany("INSERT OR REPLACE INTO payload (key, id, metadata, document) VALUES (?,?,?,?)", live)
+                db.commit()
+            finally:
+                db.close()
+            # (4) the meta file names how many rows are valid; it is replaced atomically, last
+            meta = {"format": FORMAT_VERSION, "name": self.name, "metadata": self.metadata, "space": self.space,
+                    "dtype": self.dtype, "dim": self.dim, "rows": n_rows, "next_synthetic": self._next_synthetic}
+            tmp = meta_p + ".tmp"
+            with open(tmp, "w") as f:
+                json.dump(meta, f)
+            os.replace(tmp, meta_p)
+            self._persisted_rows = n_rows
+            self._dirty_rows.clear()
+            self._dirty_payload.clear()
+
+    @classmethod
+    def load(cls, directory: str, *, device: Optional[int] = None) -> "B200Collection":
+        """Reopen a persisted collection: mmap the shard files, one H2D copy, payload from sqlite.
+        Rows deleted before the flush are dropped on the way in (the shard comes back compacted, in the
+        same insertion order), after which the files are rewritten to match."""
+        with open(os.path.join(directory, "meta.json")) as f:
+            meta = json.load(f)
+        if meta.get("format") != FORMAT_VERSION:
+            raise ValueError(f"{directory}: unknown shard format {meta.get('format')!r}")
+        col = cls(meta["name"], meta.get("metadata") or {"hnsw:space": meta["space"]}, dtype=meta["dtype"],
+                  device=device, directory=directory)
+        col._next_synthetic = int(meta.get("next_synthetic", -2))
+        n_rows, dim = int(meta["rows"]), meta.get("dim")
+        _, rows_p, keys_p, pay_p = col._paths()
+        compacted = False
+        if n_rows > 0 and dim:
+            idx = col._ensure_index(int(dim), reserve_rows=n_rows)
+            mm_r = np.memmap(rows_p, dtype=np.uint8, mode="r", shape=(n_rows, idx.row_bytes))
+            mm_k = np.memmap(keys_p, dtype=np.int64, mode="r", shape=(n_rows,))
+            keys = np.array(mm_k)
+            live = keys != _INT64_MIN
+            if live.all():
+                idx.import_raw(mm_r, keys)
+            else:
+                compacted = True
+                sel = np.flatnonzero(live)
+                step = max(1, (64 << 20) // idx.row_bytes)
+                for lo in range(0, sel.size, step):
+                    part = sel[lo:lo + step]
+                    idx.import_raw(np.ascontiguousarray(mm_r[part]), keys[part])
+            del mm_r, mm_k
+        if os.path.exists(pay_p):
+            db = sqlite3.connect(pay_p)
+            try:
+                for key, id_str, md, doc in db.execute("SELECT key, id, metadata, document FROM payload"):
+                    col._payload[int(key)] = {"id": id_str, "metadata": json.loads(md) if md is not None else None,
+                                              "document": doc}
+                    col._key_of_id[id_str] = int(key)
+            finally:
+                db.close()
+        if compacted:
+            for p in (rows_p, keys_p):
+                os.remove(p)
+            col._persisted_rows = 0
+            col.persist()
+        else:
+            col._persisted_rows = n_rows
+        return col
+
+    # -- document-level helpers the reference probes with hasattr (api_server.py:230-231, 267-270) --------
+    def keys_where(self, field: str, value) -> List[int]:
+        with self._lock:
+            return [k for k, p in self._payload.items() if (p.get("metadata") or {}).get(field) == value]
+
     def close(self) -> None:
         with self._lock:
             if self._index is not None:
@@ -236,18 +416,28 @@ class B200Client:
     def __init__(self, path: str = "."):
         self.path = os.path.abspath(path)
 
+    def _dir_of(self, name: str) -> str:
+        return os.path.join(self.path, f"{name}.b200")
+
     def get_or_create_collection(self, name: str, metadata: Optional[Dict[str, Any]] = None, **kw) -> B200Collection:
         key = (self.path, name)
         with _REGISTRY_LOCK:
             col = _REGISTRY.get(key)
             if col is None:
-                col = B200Collection(name, metadata, **kw)
+                d = self._dir_of(name)
+                if os.path.exists(os.path.join(d, "meta.json")):
+                    col = B200Collection.load(d, device=kw.get("device"))  # restart: mmap + H2D
+                else:
+                    col = B200Collection(name, metadata, directory=d, **kw)
                 _REGISTRY[key] = col
             return col
 
     def get_collection(self, name: str) -> B200Collection:
         with _REGISTRY_LOCK:
             col = _REGISTRY.get((self.path, name))
+            if col is None and os.path.exists(os.path.join(self._dir_of(name), "meta.json")):
+                col = B200Collection.load(self._dir_of(name))
+                _REGISTRY[(self.path, name)] = col
         if col is None:
             raise ValueError(f"Collection {name} does not exist.")
         return col
@@ -257,10 +447,13 @@ class B200Client:
             return [c for (p, _), c in _REGISTRY.items() if p == self.path]
 
     def delete_collection(self, name: str) -> None:
+        import shutil
+
         with _REGISTRY_LOCK:
             col = _REGISTRY.pop((self.path, name), None)
         if col is not None:
             col.close()
+        shutil.rmtree(self._dir_of(name), ignore_errors=True)
 
 
 def PersistentClient(path: str = ".") -> B200Client:  # noqa: N802 - chromadb's spelling
@@ -268,7 +461,8 @@ def PersistentClient(path: str = ".") -> B200Client:  # noqa: N802 - chromadb's 
 
 
 def reset_registry() -> None:
-    """Drop every collection (tests)."""
+    """Drop every collection from memory (tests; also simulates a process restart -- persisted
+    collections are reloaded from their directory by the next get_or_create_collection)."""
     with _REGISTRY_LOCK:
         cols = list(_REGISTRY.values())
         _REGISTRY.clear()

@@ -152,6 +152,35 @@ class ShardIndex:
                                           keys.ctypes.data))
         return vecs, keys
 
+    # -- persistence: rows exactly as stored in HBM -------------------------------
+    @property
+    def row_bytes(self) -> int:
+        return self.dim * (2 if self.dtype == "bf16" else 4)
+
+    def export_raw(self, first_row: int, n: int) -> Tuple[np.ndarray, np.ndarray]:
+        """(rows [n, row_bytes] uint8 -- the stored bf16/fp32 bits -- , keys [n] int64; INT64_MIN = deleted)."""
+        rows = np.empty((n, self.row_bytes), dtype=np.uint8)
+        keys = np.empty((n,), dtype=np.int64)
+        check(self._lib.fr_index_export_raw(self._handle(), int(first_row), int(n), rows.ctypes.data, keys.ctypes.data))
+        return rows, keys
+
+    def import_raw(self, rows, keys) -> None:
+        """Append rows verbatim (already prepared storage bits, e.g. a memory-mapped shard file)."""
+        k = np.ascontiguousarray(keys, dtype=np.int64).reshape(-1)
+        r = np.asarray(rows)
+        if r.dtype != np.uint8 or r.ndim != 2 or r.shape[1] != self.row_bytes or r.shape[0] != k.shape[0]:
+            raise ValueError(f"expected uint8 rows of shape ({k.shape[0]}, {self.row_bytes}), got {r.dtype} {r.shape}")
+        if not r.flags.c_contiguous:
+            r = np.ascontiguousarray(r)
+        check(self._lib.fr_index_import_raw(self._handle(), r.ctypes.data, k.ctypes.data, k.shape[0]))
+
+    def lookup_rows(self, keys) -> np.ndarray:
+        """Physical row of each key (-1 = absent)."""
+        k = np.ascontiguousarray(keys, dtype=np.int64).reshape(-1)
+        out = np.empty_like(k)
+        check(self._lib.fr_index_lookup_rows(self._handle(), k.ctypes.data, k.shape[0], out.ctypes.data))
+        return out
+
     # -- device entry points (torch tensors own the memory) --------------------------------------
     def _check_dev(self, t, dtype, what):
         import torch
@@ -221,6 +250,37 @@ def rrf_fuse_host(keys: np.ndarray, k_rrf: int = 60, k_out: int = 10, device: in
     return sc, ok
 
 
+def maxsim_aggregate_host(dist: np.ndarray, keys: np.ndarray, group_shift: int, k_out: int = 24, device: int = 0):
+    """dist/keys: [B, T, kp] per-token hit lists of B queries.  Returns (score [B,k_out] fp64, group [B,k_out])."""
+    lib = _lib.load()
+    d = np.ascontiguousarray(dist, dtype=np.float32)
+    k = np.ascontiguousarray(keys, dtype=np.int64)
+    if d.ndim != 3 or d.shape != k.shape:
+        raise ValueError("dist and keys must both be [B, T, kp]")
+    b, t, kp = d.shape
+    sc = np.zeros((b, k_out), dtype=np.float64)
+    og = np.full((b, k_out), -1, dtype=np.int64)
+    check(lib.fr_maxsim_aggregate(int(device), d.ctypes.data, k.ctypes.data, b, t, kp, int(group_shift), int(k_out),
+                                  sc.ctypes.data, og.ctypes.data))
+    return sc, og
+
+
+def maxsim_aggregate_device(dist, keys, group_shift: int, k_out: int = 24, stream=None):
+    """CUDA tensors [B, T, kp] (fp32 dist, int64 keys) -> CUDA tensors (score fp64 [B,k_out], group [B,k_out])."""
+    import torch
+
+    lib = _lib.load()
+    if not (dist.is_cuda and keys.is_cuda and dist.dtype == torch.float32 and keys.dtype == torch.int64
+            and dist.is_contiguous() and keys.is_contiguous() and dist.ndim == 3 and dist.shape == keys.shape):
+        raise ValueError("dist (fp32) and keys (int64) must be contiguous CUDA tensors [B, T, kp]")
+    b, t, kp = dist.shape
+    sc = torch.empty((b, k_out), dtype=torch.float64, device=dist.device)
+    og = torch.empty((b, k_out), dtype=torch.int64, device=dist.device)
+    check(lib.fr_maxsim_aggregate_device(dist.device.index, dist.data_ptr(), keys.data_ptr(), b, t, kp, int(group_shift),
+                                         int(k_out), sc.data_ptr(), og.data_ptr(), _stream_ptr(stream)))
+    return sc, og
+
+
 def rrf_fuse_device(keys, k_rrf: int = 60, k_out: int = 10, stream=None):
     """keys: CUDA int64 tensor [L, B, kp].  Returns CUDA tensors (score fp64 [B,k_out], keys)."""
     import torch
@@ -236,4 +296,5 @@ def rrf_fuse_device(keys, k_rrf: int = 60, k_out: int = 10, stream=None):
     return sc, ok
 
 
-__all__ = ["ShardIndex", "canonical_space", "merge_shards_device", "rrf_fuse_host", "rrf_fuse_device", "FR_MAX_K"]
+__all__ = ["ShardIndex", "canonical_space", "merge_shards_device", "rrf_fuse_host", "rrf_fuse_device",
+           "maxsim_aggregate_host", "maxsim_aggregate_device", "FR_MAX_K"]

@@ -180,3 +180,34 @@ def test_thresholded_cpu_scan_equals_exact_scan():
     d2, r2 = ox.exact_topk_thresholded(q, corpus[:7], 10, "cosine", chunk_rows=3)
     d3, r3 = ox.exact_topk(q, corpus[:7], 10, "cosine", "f32", prepared=True)
     assert (r2 == r3).all() and np.allclose(d2, d3, rtol=0, atol=5e-7)
+
+
+def test_bm25_restatement_known_answer_and_product_host_logic():
+    """rank_bm25 is absent (requirements.txt dependency, not vendored): the oracle restates BM25Okapi and is
+    pinned by a hand-computed case; the product's host-side BM25 (financial_rag_b200/hybrid.py, numpy
+    vectors like rank_bm25) must agree with the oracle's scalar loops bit for bit."""
+    import math
+
+    from financial_rag_b200.hybrid import BM25Okapi
+    from oracle import bm25 as obm
+
+    docs = [d.split() for d in ["the cat sat on the mat", "the dog ate the cat food", "revenue grew in fiscal 2023",
+                                "cat cat cat"]]
+    # N = 4, avgdl = 5.  "revenue": df = 1 -> idf = ln 3.5 - ln 1.5; doc 2 has f = 1, dl = avgdl
+    #   -> idf * 1 * 2.5 / (1 + 1.5 * 1) = idf.
+    s = obm.bm25_okapi_scores(docs, ["revenue"])
+    assert s == [0.0, 0.0, math.log(3.5) - math.log(1.5), 0.0]
+    # "cat": df = 3 -> idf < 0 -> epsilon * mean idf.  "the": df = 2 -> idf = ln 2.5 - ln 2.5 = 0 (kept).
+    idfs = {"cat": math.log(1.5) - math.log(3.5), "the": 0.0}
+    for w in ("sat", "on", "mat", "dog", "ate", "food", "revenue", "grew", "in", "fiscal", "2023"):
+        idfs[w] = math.log(3.5) - math.log(1.5)
+    eps = 0.25 * (sum(idfs.values()) / len(idfs))
+    s = obm.bm25_okapi_scores(docs, ["cat"])
+    assert s[3] == eps * (3 * 2.5 / (3 + 1.5 * (1 - 0.75 + 0.75 * 3 / 5)))
+    assert s[2] == 0.0 and s[0] == s[1] > 0
+    rng = np.random.default_rng(0)
+    vocab = [f"t{i}" for i in range(40)]
+    for _ in range(20):
+        corpus = [list(rng.choice(vocab, size=int(rng.integers(1, 30)))) for _ in range(int(rng.integers(1, 25)))]
+        query = list(rng.choice(vocab + ["unseen"], size=5))
+        assert BM25Okapi(corpus).get_scores(query).tolist() == obm.bm25_okapi_scores(corpus, query)
