@@ -160,6 +160,7 @@ struct fr_index {
     cudaEvent_t last_use = nullptr;  // orders scratch reuse across caller streams
     DevBuf q_raw, q_prep, q_keys, partials, out_dist, out_keys, stage_vecs, stage_keys, stage_rows;
     DevBuf q_bf16, err_bound, sel, sel_keys, flags, fail, fb_partials, tau;  // K2 path
+    DevBuf kth_exact, r_q, r_misc, r_tau, r_partials, r_sel, r_sel_keys;     // K2 second-chance pass
     int mma_min_batch = 2;  // FR_PATH_AUTO: batches at least this large go to the tensor-core scan
     int mma_debug = 0;      // diagnostics (scripts/ablate_mma.py): results are wrong when non-zero
     int mma_co_groups = 2;  // K2: query groups of 256 that share one corpus stream through L2
@@ -392,6 +393,26 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
         FR_CUDA(fr::launch_merge_topk(ma));
     }
 
+    // second-chance buffers: one more query block of RETRY_MAX queries
+    const int R = fr::scan_mma_retry_max();
+    const int ksel_r = fr::scan_mma_retry_ksel(ksel);
+    const fr::MmaPlan rplan = fr::scan_mma_plan(ix->sm_count, ix->rows, R, 1);
+    FR_CUDA(ix->kth_exact.need(static_cast<size_t>(B) * sizeof(float)));
+    FR_CUDA(ix->r_q.need(static_cast<size_t>(R) * ix->dim * 2));
+    FR_CUDA(ix->r_misc.need(static_cast<size_t>(R) * sizeof(float) + (static_cast<size_t>(B) + 2) * sizeof(int)));
+    FR_CUDA(ix->r_tau.need(static_cast<size_t>(R) * ksel_r * sizeof(uint32_t)));
+    FR_CUDA(ix->r_partials.need(static_cast<size_t>(rplan.lists_max) * R * ksel_r * sizeof(uint64_t)));
+    FR_CUDA(ix->r_sel.need(static_cast<size_t>(R) * ksel_r * sizeof(uint64_t)));
+    FR_CUDA(ix->r_sel_keys.need(static_cast<size_t>(R) * ksel_r * sizeof(int64_t)));
+    float *tau0 = static_cast<float *>(ix->r_misc.p);
+    int *retry_n = reinterpret_cast<int *>(tau0 + R);
+    int *fail_count2 = retry_n + 1;
+    int *fail_list2 = fail_count2 + 1;
+    FR_CUDA(cudaMemsetAsync(retry_n, 0, 2 * sizeof(int), s));
+    unsigned long long *stat_uncertified = static_cast<unsigned long long *>(ix->stats.p);
+    unsigned long long *stat_rescanned = stat_uncertified + 1;
+
+    // first rescore pass: exact fp32-query scores of the k' candidates, certification
     fr::RescoreArgs ra{};
     ra.sel = static_cast<const uint64_t *>(ix->sel.p);
     ra.ksel = ksel;
@@ -407,9 +428,70 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     ra.flags = static_cast<uint8_t *>(ix->flags.p);
     ra.fail_count = fail_count;
     ra.fail_list = fail_list;
-    ra.fail_total = static_cast<unsigned long long *>(ix->stats.p);
+    ra.fail_total = stat_uncertified;
+    ra.kth_exact = static_cast<float *>(ix->kth_exact.p);
     ra.stream = s;
     FR_CUDA(fr::launch_rescore(ra));
+
+    // second chance on the tensor cores for what could not be certified (all four launches return at once
+    // when nothing failed): gather -> scan above a fixed threshold -> merge -> rescore
+    fr::RetryPrepArgs rp{};
+    rp.queries = q;
+    rp.err_bound = ra.err_bound;
+    rp.kth_exact = ra.kth_exact;
+    rp.fail_count = fail_count;
+    rp.fail_list = fail_list;
+    rp.qb_retry = ix->r_q.p;
+    rp.tau0 = tau0;
+    rp.retry_n = retry_n;
+    rp.tau_g_retry = static_cast<uint32_t *>(ix->r_tau.p);
+    rp.ksel = ksel_r;
+    rp.fail_count2 = fail_count2;
+    rp.fail_list2 = fail_list2;
+    rp.flags = ra.flags;
+    rp.rescan_total = stat_rescanned;
+    rp.stream = s;
+    FR_CUDA(fr::launch_retry_prep(rp));
+
+    fr::MmaScanArgs rs = ms;
+    rs.queries_bf16 = ix->r_q.p;
+    rs.nq_pad = R;
+    rs.nq_total = R;
+    rs.ksel = ksel_r;
+    rs.partials = static_cast<uint64_t *>(ix->r_partials.p);
+    rs.plan = rplan;
+    rs.tau_g = rp.tau_g_retry;
+    rs.nq_dev = retry_n;
+    rs.tau0 = tau0;
+    FR_CUDA(fr::launch_scan_mma(rs));
+
+    fr::MergeArgs mr{};
+    mr.packed = rs.partials;
+    mr.P = rplan.lists;
+    mr.shard_stride = static_cast<int64_t>(R) * ksel_r;
+    mr.B = R;
+    mr.k = ksel_r;
+    mr.shards = false;
+    mr.row_keys = ix->keys;
+    mr.l2 = false;
+    mr.out_packed = static_cast<uint64_t *>(ix->r_sel.p);
+    mr.out_keys = static_cast<int64_t *>(ix->r_sel_keys.p);
+    mr.limit = retry_n;
+    mr.stream = s;
+    FR_CUDA(fr::launch_merge_topk(mr));
+
+    fr::RescoreArgs rr = ra;
+    rr.sel = static_cast<const uint64_t *>(ix->r_sel.p);
+    rr.ksel = ksel_r;
+    rr.B = R;
+    rr.fail_count = fail_count2;
+    rr.fail_list = fail_list2;
+    rr.fail_total = stat_rescanned;
+    rr.kth_exact = nullptr;
+    rr.idx_list = fail_list;
+    rr.limit = retry_n;
+    rr.tau0 = tau0;
+    FR_CUDA(fr::launch_rescore(rr));
 
     // safety net: both launches return immediately when every query was certified
     fr::ScanArgs sa{};
@@ -426,7 +508,7 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     sa.grid = fr::scan_stream_fallback_grid(sa, ix->sm_count);
     FR_CUDA(ix->fb_partials.need(static_cast<size_t>(sa.grid) * B * k * sizeof(uint64_t)));
     sa.partials = static_cast<uint64_t *>(ix->fb_partials.p);
-    FR_CUDA(fr::launch_scan_stream_fallback(sa, fail_count, fail_list));
+    FR_CUDA(fr::launch_scan_stream_fallback(sa, fail_count2, fail_list2));
     fr::MergeArgs mf{};
     mf.packed = sa.partials;
     mf.P = sa.grid;
@@ -542,7 +624,8 @@ int fr_index_destroy(fr_index *ix) {
         DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist,
                           &ix->out_keys, &ix->stage_vecs, &ix->stage_keys, &ix->stage_rows,
                           &ix->q_bf16, &ix->err_bound, &ix->sel, &ix->sel_keys, &ix->flags, &ix->fail,
-                          &ix->fb_partials, &ix->tau, &ix->stats};
+                          &ix->fb_partials, &ix->tau, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau,
+                          &ix->r_partials, &ix->r_sel, &ix->r_sel_keys};
         for (DevBuf *b : bufs) b->release();
         ix->pin.release();
         for (auto &pr : ix->prof_events) {
@@ -629,14 +712,15 @@ int fr_index_get_stat(fr_index *ix, const char *name, int64_t *out) {
         *out = ix->n_mma_queries;
         return FR_OK;
     }
-    if (std::strcmp(name, "mma_uncertified_queries") == 0) {
+    const bool unc = std::strcmp(name, "mma_uncertified_queries") == 0;
+    if (unc || std::strcmp(name, "mma_rescanned_queries") == 0) {
         *out = 0;
         if (!ix->stats.p) return FR_OK;
         DeviceGuard g(ix->device);
         FR_CUDA(cudaDeviceSynchronize());
-        unsigned long long v = 0;
-        FR_CUDA(cudaMemcpy(&v, ix->stats.p, sizeof(v), cudaMemcpyDeviceToHost));
-        *out = static_cast<int64_t>(v);
+        unsigned long long v[2] = {0, 0};
+        FR_CUDA(cudaMemcpy(v, ix->stats.p, sizeof(v), cudaMemcpyDeviceToHost));
+        *out = static_cast<int64_t>(unc ? v[0] : v[1]);
         return FR_OK;
     }
     return fail(FR_EINVAL, "unknown stat '%s'", name);

@@ -56,6 +56,8 @@ struct MmaScanArgs {
     uint64_t *partials;         // [plan.lists_max][nq_total][ksel]; queries < plan.tail_q0 get plan.lists lists,
                                 // the others plan.lists_tail
     MmaPlan plan;
+    const int *nq_dev;          // optional: the launch serves *nq_dev queries (second-chance pass), 0 = exit at once
+    const float *tau0;          // optional [nq_total]: fixed initial threshold per query (second-chance pass)
     int dbg;                    // diagnostics only (option "mma_debug"): 1 = no corpus loads, 2 = no accumulator reads
     uint32_t *tau_g;            // [ksel][nq_total] shared threshold slots (order_bits of a score), zeroed before the launches
     cudaStream_t stream;
@@ -80,9 +82,35 @@ struct RescoreArgs {
     int *fail_count;
     int *fail_list;        // [B]
     unsigned long long *fail_total;  // cumulative count of uncertified queries (fr_index_get_stat)
+    float *kth_exact;      // [B] out (first pass): k-th exact score, the anchor of the second-chance threshold
+    const int *idx_list;   // second pass: CTA j answers query idx_list[j] from sel[j] ...
+    const int *limit;      // ... for j < *limit
+    const float *tau0;     // ... whose list was collected above tau0[j]
     cudaStream_t stream;
 };
 cudaError_t launch_rescore(const RescoreArgs &a);
+
+// Gathers the uncertified queries of the first pass into the second-chance query block (scan_mma.cu).
+struct RetryPrepArgs {
+    const float *queries;     // [B][384] fp32 prepared queries
+    const float *err_bound;   // [B]
+    const float *kth_exact;   // [B]
+    const int *fail_count;    // first-pass failures
+    const int *fail_list;
+    void *qb_retry;           // [RETRY_MAX][384] bf16 out
+    float *tau0;              // [RETRY_MAX] out
+    int *retry_n;             // out: min(*fail_count, RETRY_MAX)
+    uint32_t *tau_g_retry;    // [ksel][RETRY_MAX] zeroed here
+    int ksel;
+    int *fail_count2;         // failures that did not fit the block are appended here (pre-zeroed by the caller)
+    int *fail_list2;
+    uint8_t *flags;
+    unsigned long long *rescan_total;  // += failures that did not fit the block
+    cudaStream_t stream;
+};
+int scan_mma_retry_max();
+int scan_mma_retry_ksel(int ksel);
+cudaError_t launch_retry_prep(const RetryPrepArgs &a);
 
 // ---- K3 merge_topk --------------------------------------------------------------------------
 struct MergeArgs {
@@ -103,6 +131,7 @@ struct MergeArgs {
     uint64_t *out_packed;       // [B][k] or null (mergeable form for the all-gather)
     int64_t *out_keys;          // [B][k]
     const uint8_t *only_flagged;  // optional [B]: CTAs of unflagged queries exit at once (K2 fallback)
+    const int *limit;             // optional: CTAs b >= *limit exit at once (K2 second-chance pass)
     cudaStream_t stream;
 };
 cudaError_t launch_merge_topk(const MergeArgs &a);

@@ -19,10 +19,12 @@ __global__ void __launch_bounds__(128)
 merge_topk_kernel(const uint64_t *__restrict__ packed, int P, int64_t shard_stride, int B, int k,
                   const int64_t *__restrict__ row_keys, const int64_t *__restrict__ shard_keys, bool l2,
                   float *__restrict__ out_dist, uint64_t *__restrict__ out_packed,
-                  int64_t *__restrict__ out_keys, const uint8_t *__restrict__ only_flagged) {
+                  int64_t *__restrict__ out_keys, const uint8_t *__restrict__ only_flagged,
+                  const int *__restrict__ limit) {
     __shared__ uint64_t lists[4 * 32 * KPL];
     const int b = blockIdx.x;
     if (only_flagged != nullptr && only_flagged[b] == 0) return;  // uniform per CTA
+    if (limit != nullptr && b >= *limit) return;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
@@ -81,11 +83,15 @@ cudaError_t launch_merge_topk(const MergeArgs &a) {
 #define FR_MERGE(KPL, SH)                                                                          \
     merge_topk_kernel<KPL, SH><<<grid, block, 0, a.stream>>>(a.packed, a.P, a.shard_stride, a.B, a.k, \
                                                              a.row_keys, a.shard_keys, a.l2, a.out_dist, \
-                                                             a.out_packed, a.out_keys, a.only_flagged)
+                                                             a.out_packed, a.out_keys, a.only_flagged, a.limit)
     if (a.k <= 32) {
         if (a.shards) FR_MERGE(1, true); else FR_MERGE(1, false);
-    } else {
+    } else if (a.k <= 128) {
         if (a.shards) FR_MERGE(4, true); else FR_MERGE(4, false);
+    } else if (a.k <= 256 && !a.shards) {
+        FR_MERGE(8, false);  // K2 second-chance lists
+    } else {
+        return cudaErrorInvalidValue;
     }
 #undef FR_MERGE
     count_launch();

@@ -35,11 +35,11 @@
 // time of the tile (128 rows x 768 B): HBM-bound like K1, but for 128 queries at once.  At 256
 // queries per pass (CG = 2) MMA time per 256-row tile (24 x 128 cycles per pair) matches its HBM time.
 //
-// Exactness.  The tensor cores need bf16 queries; the reference semantics (and K1) use fp32 queries.
-// So K2 only SELECTS: it keeps k' = 32*KPL >= 2k candidates per query, ranked by the bf16-query
-// score; rescore_kernel then recomputes the k' scores with the fp32 query (fp32 FMA), sorts them
+// Exactness.  The tensor cores need bf16 queries (q16 below); the reference semantics (and K1) use
+// fp32 queries.  So K2 only SELECTS: it keeps k' = 32*KPL > k candidates per query, ranked by the
+// q16-query score; rescore_kernel then recomputes the k' scores with the fp32 query (fp32 FMA), sorts them
 // by the exact key and CERTIFIES the top-k:  every row outside the candidate set has
-//     exact score <= (k'-th selection score) + |q - bf16(q)|_2 * |c|_2  (+ fp32 accumulation slack),
+//     exact score <= (k'-th selection score) + |q - q16|_2 * |c|_2  (+ fp32 accumulation slack),
 // so if the k-th exact score is above that bound the result equals the fp32-query scan; otherwise
 // the query is flagged and re-scanned by the stream kernel (scan_stream_fallback_kernel).
 #include <cuda.h>
@@ -61,6 +61,7 @@ constexpr int TMEM_COLS = 512;                 // the whole tensor memory: 4 x 1
 constexpr int THREADS = 192;                   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
 
 constexpr int PEND = 16;                       // unsorted pending candidates per query between compactions
+constexpr int RETRY_MAX = M_TILE;              // uncertified queries that get a second tensor-core pass
 
 // Per-query candidate lists hold CAP = 32*KPL = k' entries.  For k' <= 64 they live in shared memory;
 // for k' = 128 (k up to 100) 128 queries x 1 KB would not fit beside the 96 KB query block, so the CTA
@@ -69,7 +70,7 @@ constexpr int PEND = 16;                       // unsorted pending candidates pe
 template <int KPL>
 struct SmemPlan {
     static constexpr bool LISTS_IN_SMEM = KPL <= 2;
-    static constexpr int STAGES = (KPL == 1) ? 5 : (KPL == 2 ? 3 : 6);
+    static constexpr int STAGES = (KPL == 1) ? 5 : (KPL == 2 ? 3 : 6);  // KPL 4 and 8: lists are not in smem
     static constexpr int CAP = 32 * KPL;
     static constexpr size_t A_OFF = 0;
     static constexpr size_t B_OFF = A_OFF + size_t(K_CHUNKS) * CHUNK_BYTES;
@@ -79,7 +80,8 @@ struct SmemPlan {
     static constexpr size_t TOTAL = BAR_OFF + 256;
     static constexpr size_t ALLOC = TOTAL + 1024;  // slack to align the base to 1024 B
 };
-static_assert(SmemPlan<1>::ALLOC <= 232448 && SmemPlan<2>::ALLOC <= 232448 && SmemPlan<4>::ALLOC <= 232448,
+static_assert(SmemPlan<1>::ALLOC <= 232448 && SmemPlan<2>::ALLOC <= 232448 && SmemPlan<4>::ALLOC <= 232448 &&
+                  SmemPlan<8>::ALLOC <= 232448,
               "exceeds 227 KB of shared memory");
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -226,6 +228,8 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6), A=BF16 [7,10), B=BF16 [10,13),
 // A,B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29).
+// (Measured on B200: an fp16 A with a bf16 B -- which would shrink the query rounding error eightfold --
+//  raises "illegal instruction": kind::f16 wants both operands in one format.)
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
            (static_cast<uint32_t>(m >> 4) << 24);
@@ -308,7 +312,8 @@ template <int KPL, int CG>
 __global__ void __launch_bounds__(THREADS, 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                 const int64_t *__restrict__ keys_or_null, int64_t n_rows, int nq_launch, int q_row0_launch, int ksel,
-                uint64_t *__restrict__ partials, int nq_total, int co, uint32_t *__restrict__ tau_g, int dbg) {
+                uint64_t *__restrict__ partials, int nq_total, int co, uint32_t *__restrict__ tau_g, int dbg,
+                const int *__restrict__ nq_dev, const float *__restrict__ tau0) {
     using Plan = SmemPlan<KPL>;
     constexpr int STAGES = Plan::STAGES;
     constexpr int CAP = Plan::CAP;
@@ -339,6 +344,11 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int npairs = gridDim.x / (CG * co);
     const int q_row0 = q_row0_launch + grp * (M_TILE * CG);  // first query row of the group
     const int q_offset = q_row0;
+    // second-chance launches learn their query count on the device (every CTA reads the same value)
+    if (nq_dev != nullptr) {
+        nq_launch = *nq_dev;
+        if (nq_launch <= 0) return;
+    }
     const int nq = min(M_TILE * CG, nq_launch - grp * (M_TILE * CG));
 
     if (threadIdx.x == 0) {
@@ -459,7 +469,8 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         uint64_t *my_lists = lists + static_cast<size_t>(quarter) * 32 * CAP;
         uint64_t *pend_w = pend_all + static_cast<size_t>(warp - 2) * PEND * 32;  // entry j of lane q: [j][(q + j) & 31]
         const bool live = my_q < nq_local;
-        float tau = live ? -INFINITY : INFINITY;   // padded query rows never pass the gate
+        // padded query rows never pass the gate; a second-chance query starts at its fixed threshold
+        float tau = live ? (tau0 != nullptr ? tau0[q_offset + static_cast<int>(rank) * M_TILE + my_q] : -INFINITY) : INFINITY;
         int cnt = 0;                               // this query's pending (unsorted) candidates
         // shared thresholds: slot[j][query], j < k'.  With at least k' streams, stream s raises slot s % k'
         // to the best score it holds.  With fewer streams, stream s owns the slots s, s + S, s + 2S, ... and
@@ -613,7 +624,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
 // ---------------------------------------------------------------------------------------------
 // Query preparation for K2: bf16 copy (zero-padded to a multiple of 128 rows) and the per-query
-// selection error bound |q - bf16(q)|_2.
+// selection error bound |q - q16|_2.
 __global__ void prep_queries_kernel(const float *__restrict__ q, int nq, int nq_pad, __nv_bfloat16 *__restrict__ qb,
                                     float *__restrict__ err_bound) {
     const int row = blockIdx.x;
@@ -635,21 +646,30 @@ __global__ void prep_queries_kernel(const float *__restrict__ q, int nq, int nq_
 // ---------------------------------------------------------------------------------------------
 // rescore_kernel: exact fp32-query scores of the k' selected rows, exact order, certification.
 // One CTA (4 warps) per query.  sel: [B][ksel] packed keys sorted by selection score.
+//   first pass : CTA j handles query j; an uncertified query is flagged, appended to fail_list and its k-th
+//                exact score kept (kth_exact_out) for the second-chance pass.
+//   second pass: CTA j < *limit handles query idx_list[j], whose selection list (sel[j]) was collected above the
+//                fixed threshold tau0[j].  A list that did not fill up holds EVERY row above tau0[j]; everything
+//                else scores at most tau0[j] + bound, so the query is certified iff its k-th exact score beats that.
 template <int KPL>
 __global__ void __launch_bounds__(128)
 rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restrict__ queries,
                const uint8_t *__restrict__ corpus, const int64_t *__restrict__ row_keys,
                const float *__restrict__ err_bound, int k, float *__restrict__ out_dist,
                uint64_t *__restrict__ out_packed, int64_t *__restrict__ out_keys, uint8_t *__restrict__ flags,
-               int *__restrict__ fail_count, int *__restrict__ fail_list, unsigned long long *__restrict__ fail_total) {
+               int *__restrict__ fail_count, int *__restrict__ fail_list, unsigned long long *__restrict__ fail_total,
+               float *__restrict__ kth_exact_out, const int *__restrict__ idx_list, const int *__restrict__ limit,
+               const float *__restrict__ tau0) {
     __shared__ float sq[DIM];
     __shared__ uint64_t exact[32 * KPL];
-    const int b = blockIdx.x;
+    const int j_cta = blockIdx.x;
+    if (limit != nullptr && j_cta >= *limit) return;
+    const int b = idx_list != nullptr ? idx_list[j_cta] : j_cta;  // the query this CTA answers
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int e = threadIdx.x; e < DIM; e += blockDim.x) sq[e] = queries[static_cast<size_t>(b) * DIM + e];
     for (int i = threadIdx.x; i < 32 * KPL; i += blockDim.x) exact[i] = 0ull;
     __syncthreads();
-    const uint64_t *s = sel + static_cast<size_t>(b) * ksel;
+    const uint64_t *s = sel + static_cast<size_t>(j_cta) * ksel;
     for (int j = warp; j < ksel; j += 4) {
         const uint64_t key = s[j];
         if (key == 0ull) continue;  // warp-uniform
@@ -681,14 +701,17 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
         ++n_valid;
         lst.insert(key, 32 * KPL, lane);
     }
-    // certification: anything outside the candidate set scores at most (last selection score + bound)
-    bool certified = true;
+    // certification: anything outside the candidate set scores at most (its selection-score ceiling + bound);
+    // |c|_2 <= 1 + 2^-9 for a bf16-rounded unit row, 1e-5 covers the fp32 accumulation of 384 products
+    const float bound = err_bound[b] * 1.004f + 1e-5f;
     const uint64_t last_sel = s[ksel - 1];
-    if (last_sel != 0ull && n_valid >= k) {
-        const float cut = key_score(last_sel) + err_bound[b] * 1.004f + 4e-6f;
-        const float kth_exact = key_score(lst.kth(k));
-        certified = kth_exact > cut;
-    }
+    const float kth_exact = n_valid >= k ? key_score(lst.kth(k)) : -INFINITY;
+    bool certified = true;
+    if (last_sel != 0ull) {                       // list full: ceiling = the k'-th selection score
+        certified = n_valid >= k && kth_exact > key_score(last_sel) + bound;
+    } else if (tau0 != nullptr) {                 // not full, but only rows above tau0 were collected
+        certified = n_valid >= k && kth_exact > tau0[j_cta] + bound;
+    }                                             // not full and no threshold: every live row is a candidate
 #pragma unroll
     for (int j = 0; j < KPL; ++j) {
         const int i = j * 32 + lane;
@@ -707,10 +730,46 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
     }
     if (lane == 0) {
         flags[b] = certified ? 0 : 1;
+        if (kth_exact_out) kth_exact_out[b] = kth_exact;
         if (!certified) {
             fail_list[atomicAdd(fail_count, 1)] = b;
             if (fail_total) atomicAdd(fail_total, 1ull);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Second chance for uncertified queries.  A query fails when its k-th exact score is within the rounding
+// bound of its k'-th selection score -- crowded score neighbourhoods (near-duplicate chunks, k close to k').
+// Everything that could still belong to its top-k scores above  T = (k-th exact score) - bound  in selection
+// terms, and only a handful of rows do.  So the failed queries (up to RETRY_MAX of them) are gathered into
+// one more query block and scanned again by the same tensor-core kernel with the threshold FIXED at T from
+// the first tile on and a longer list (scan_mma_retry_ksel): the list then holds every row above T unless it
+// overflows, which is exactly what the second rescore pass certifies.  Only what still fails (or did not fit the block) goes to the stream kernel.
+// One CTA per retry slot.
+__global__ void retry_prep_kernel(const float *__restrict__ queries, const float *__restrict__ err_bound,
+                                  const float *__restrict__ kth_exact, const int *__restrict__ fail_count,
+                                  const int *__restrict__ fail_list, __nv_bfloat16 *__restrict__ qb_retry,
+                                  float *__restrict__ tau0, int *__restrict__ retry_n, uint32_t *__restrict__ tau_g_retry,
+                                  int ksel, int *__restrict__ fail_count2, int *__restrict__ fail_list2,
+                                  uint8_t *__restrict__ flags, unsigned long long *__restrict__ rescan_total) {
+    const int j = blockIdx.x;  // retry slot, < RETRY_MAX
+    const int lane = threadIdx.x;
+    const int nf = *fail_count;
+    const int n = nf < RETRY_MAX ? nf : RETRY_MAX;
+    if (j == 0 && lane == 0) {
+        *retry_n = n;
+        for (int f = RETRY_MAX; f < nf; ++f) fail_list2[atomicAdd(fail_count2, 1)] = fail_list[f];  // no room: stream kernel
+        if (nf > RETRY_MAX && rescan_total) atomicAdd(rescan_total, static_cast<unsigned long long>(nf - RETRY_MAX));
+    }
+    for (int g = lane; g < ksel; g += 32) tau_g_retry[static_cast<size_t>(g) * RETRY_MAX + j] = 0u;
+    const bool on = j < n;
+    const int b = on ? fail_list[j] : 0;
+    for (int e = lane; e < DIM; e += 32)
+        qb_retry[static_cast<size_t>(j) * DIM + e] = __float2bfloat16_rn(on ? queries[static_cast<size_t>(b) * DIM + e] : 0.0f);
+    if (lane == 0) {
+        tau0[j] = on ? kth_exact[b] - (err_bound[b] * 1.004f + 1e-5f) - 1e-5f : INFINITY;
+        if (on) flags[b] = 1;  // stays flagged until the second rescore pass certifies it
     }
 }
 
@@ -732,14 +791,14 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // [rows][384] bf16 row-major -> boxes of [64 elements x 128 rows], 128-byte swizzle, OOB rows read as zero
-static bool make_row_major_map(CUtensorMap *map, const void *base, int64_t rows) {
+static bool make_row_major_map(CUtensorMap *map, const void *base, int64_t rows, CUtensorMapDataType dt) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return false;
     const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(DIM), static_cast<cuuint64_t>(rows)};
     const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(DIM * 2)};
     const cuuint32_t box[2] = {K_CHUNK, N_TILE};
     const cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+    return fn(map, dt, 2, const_cast<void *>(base), gdim, gstride, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -780,7 +839,7 @@ cudaError_t launch_one(const MmaScanArgs &a, const CUtensorMap &tq, const CUtens
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     e = cudaLaunchKernelEx(&cfg, kern, tq, tc, a.keys_or_null, a.n_rows, nq, q0, a.ksel, a.partials, a.nq_total, co,
-                           a.tau_g, a.dbg);
+                           a.tau_g, a.dbg, a.nq_dev, a.tau0);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }
@@ -814,7 +873,8 @@ MmaPlan scan_mma_plan(int sm_count, int64_t n_rows, int nq_total, int co_max) {
 
 cudaError_t launch_scan_mma(const MmaScanArgs &a) {
     CUtensorMap tq, tc;
-    if (!mma::make_row_major_map(&tq, a.queries_bf16, a.nq_pad) || !mma::make_row_major_map(&tc, a.corpus, a.n_rows))
+    if (!mma::make_row_major_map(&tq, a.queries_bf16, a.nq_pad, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) ||
+        !mma::make_row_major_map(&tc, a.corpus, a.n_rows, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16))
         return cudaErrorNotSupported;
     const MmaPlan &p = a.plan;
     const int per_launch = p.group * p.co;  // queries served by one full launch
@@ -825,9 +885,12 @@ cudaError_t launch_scan_mma(const MmaScanArgs &a) {
         const int lists = tail ? p.lists_tail : p.lists;
         cudaError_t e;
         if (p.group == mma::M_TILE)
-            e = a.ksel <= 32   ? launch_one<1, 1>(a, tq, tc, nq, q0, co, lists)
-                : a.ksel <= 64 ? launch_one<2, 1>(a, tq, tc, nq, q0, co, lists)
-                               : launch_one<4, 1>(a, tq, tc, nq, q0, co, lists);
+            e = a.ksel <= 32    ? launch_one<1, 1>(a, tq, tc, nq, q0, co, lists)
+                : a.ksel <= 64  ? launch_one<2, 1>(a, tq, tc, nq, q0, co, lists)
+                : a.ksel <= 128 ? launch_one<4, 1>(a, tq, tc, nq, q0, co, lists)
+                                : launch_one<8, 1>(a, tq, tc, nq, q0, co, lists);  // second-chance pass of k' = 128
+        else if (a.ksel > 128)
+            e = cudaErrorNotSupported;
         else
             e = a.ksel <= 32   ? launch_one<1, 2>(a, tq, tc, nq, q0, co, lists)
                 : a.ksel <= 64 ? launch_one<2, 2>(a, tq, tc, nq, q0, co, lists)
@@ -842,11 +905,27 @@ cudaError_t launch_rescore(const RescoreArgs &a) {
 #define FR_RESCORE(KPL)                                                                                       \
     mma::rescore_kernel<KPL><<<a.B, 128, 0, a.stream>>>(a.sel, a.ksel, a.queries, a.corpus, a.row_keys, a.err_bound, \
                                                        a.k, a.out_dist, a.out_packed, a.out_keys, a.flags,       \
-                                                       a.fail_count, a.fail_list, a.fail_total)
+                                                       a.fail_count, a.fail_list, a.fail_total, a.kth_exact,     \
+                                                       a.idx_list, a.limit, a.tau0)
     if (a.ksel <= 32) FR_RESCORE(1);
     else if (a.ksel <= 64) FR_RESCORE(2);
-    else FR_RESCORE(4);
+    else if (a.ksel <= 128) FR_RESCORE(4);
+    else FR_RESCORE(8);
 #undef FR_RESCORE
+    count_launch();
+    return cudaGetLastError();
+}
+
+int scan_mma_retry_max() { return mma::RETRY_MAX; }
+// the second-chance pass needs MORE room than the first (the first failed because at least k' rows sit
+// above the threshold): four times the candidates for k' = 32, twice for 64 and 128
+int scan_mma_retry_ksel(int ksel) { return ksel >= 128 ? 256 : 128; }
+
+cudaError_t launch_retry_prep(const RetryPrepArgs &a) {
+    mma::retry_prep_kernel<<<mma::RETRY_MAX, 32, 0, a.stream>>>(a.queries, a.err_bound, a.kth_exact, a.fail_count,
+                                                              a.fail_list, static_cast<__nv_bfloat16 *>(a.qb_retry),
+                                                              a.tau0, a.retry_n, a.tau_g_retry, a.ksel, a.fail_count2,
+                                                              a.fail_list2, a.flags, a.rescan_total);
     count_launch();
     return cudaGetLastError();
 }

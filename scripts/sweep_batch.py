@@ -15,7 +15,7 @@ for c in range((n + 499_999) // 500_000):
     ix.append_device(torch.randn((rows, 384), generator=g, device=dev), None, first_key=c * 500_000)
 torch.cuda.synchronize()
 out = []
-for path in ("stream", "mma"):
+for path in (os.environ.get("SWEEP_PATHS", "stream,mma").split(",")):
     ix.set_path(path)
     for b in batches:
         if path == "stream" and b > 16:
@@ -39,6 +39,6 @@ for path in ("stream", "mma"):
         r = {"path": path, "rows": n, "batch": b, "k": k, "ms_per_step": round(ms, 4), "qps": round(b / ms * 1e3, 1),
              "scan_ms_per_launch": round(scan_ms / launches, 4), "launches_per_step": launches // steps,
              "scan_gbs": round(n * 768 / (scan_ms / launches) / 1e6, 1),
-             "tflops": round(2.0 * n * 384 * b / ms / 1e9, 1)}
+             "tflops": round(2.0 * n * 384 * b / ms / 1e9, 1), "uncertified_total": ix.stat("mma_uncertified_queries")}
         out.append(r)
         print(json.dumps(r), flush=True)

@@ -493,13 +493,51 @@ def test_mma_certification_fallback_on_mass_ties(frb):
     d_s, k_s = ix.search(queries, k)
     ix.set_path("mma")
     d_m, k_m = ix.search(queries, k)
-    assert ix.stat("mma_uncertified_queries") >= 2  # queries 1 and 4 went through the re-scan
+    assert ix.stat("mma_uncertified_queries") >= 2  # queries 1 and 4 failed the first pass ...
+    assert ix.stat("mma_rescanned_queries") >= 2    # ... overflowed the second (133 exact ties) and were re-scanned
     np.testing.assert_array_equal(keys_to_rows(k_m[1], KEY_BASE), dup_rows[:k])
     np.testing.assert_array_equal(k_m[1], k_s[1])
     np.testing.assert_array_equal(k_m[4], k_s[4])
     np.testing.assert_allclose(d_m, d_s, rtol=0, atol=2e-6)
     assert_matches_oracle(d_m, keys_to_rows(k_m, KEY_BASE), queries, corpus, k, "cosine", "bf16",
                           stored=stored_rows(ix), label="mma mass ties")
+    ix.close()
+
+
+def test_mma_second_chance_pass_resolves_crowded_neighbourhoods(frb):
+    """60 near-duplicates within 3e-4 of the query's best score: more than the k' = 32 selection slots hold, so
+    the first tensor-core pass cannot be certified; the second-chance pass (fixed threshold, 128 slots) collects
+    the whole crowd and certifies it -- no stream re-scan -- and the answer is the exact fp32-query order."""
+    n, k = 30000, 10
+    corpus = make_corpus(n, 384, seed=501)
+    rng = np.random.default_rng(502)
+    crowd = np.arange(200, 200 + 60 * 300, 300)
+    for i, r in enumerate(crowd):
+        noise = rng.standard_normal(384).astype(np.float32)
+        corpus[r] = corpus[100] + 0.024 * (i + 1) / 60.0 * np.linalg.norm(corpus[100]) / np.sqrt(384) * noise
+    queries = make_queries(8, corpus, seed=503)
+    queries[1] = corpus[100]
+    queries[6] = corpus[100] * 0.5  # same direction: cosine ignores the scale
+    ix = build_index(frb, corpus, "cosine", "bf16")
+    ix.set_path("stream")
+    d_s, k_s = ix.search(queries, k)
+    ix.set_path("mma")
+    d_m, k_m = ix.search(queries, k)
+    assert ix.stat("mma_uncertified_queries") >= 2, "the crowd must defeat the first pass"
+    assert ix.stat("mma_rescanned_queries") == 0, "the second-chance pass must certify it without a stream re-scan"
+    assert_matches_oracle(d_m, keys_to_rows(k_m, KEY_BASE), queries, corpus, k, "cosine", "bf16",
+                          stored=stored_rows(ix), label="mma second chance")
+    np.testing.assert_allclose(d_m, d_s, rtol=0, atol=2e-6)
+    mism = k_m != k_s
+    if mism.any():
+        assert np.abs(d_m[mism] - d_s[mism]).max() <= 2e-6
+    assert set(keys_to_rows(k_m[1], KEY_BASE)) <= set(crowd.tolist()) | {100}
+    # k = 100 with k' = 128 (second chance: 256 slots) on the same crowd
+    d_s, k_s = (ix.set_path("stream"), ix.search(queries, 100))[1]
+    d_m, k_m = (ix.set_path("mma"), ix.search(queries, 100))[1]
+    assert_matches_oracle(d_m, keys_to_rows(k_m, KEY_BASE), queries, corpus, 100, "cosine", "bf16",
+                          stored=stored_rows(ix), label="mma second chance k=100")
+    np.testing.assert_allclose(d_m, d_s, rtol=0, atol=2e-6)
     ix.close()
 
 
