@@ -287,7 +287,7 @@ def cpu_scan_qps(n_rows_full, batch, k, sample_rows, steps, warmup, torch=None, 
     }
 
 
-def run_reference(args):
+def run_reference(args, out=sys.stdout):
     """--impl reference: the CPU exact scan (oracle port; chromadb is not installable offline)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -315,11 +315,11 @@ def run_reference(args):
         "e2e": {"value": r["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
-def run_ours(args):
+def run_ours(args, out=sys.stdout):
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -480,9 +480,12 @@ def run_ours(args):
             "clocks": clocks,
             "verified": verified,
             "mma_uncertified_queries": uncertified,
+            "reference_chroma": {"recall_at_10": None, "qps": None,
+                                 "note": "Chroma HNSW CPU path not runnable offline: the chromadb wheel is neither in the "
+                                         "reference tree nor in this image (SURVEY.md 8c/8d); the CPU arm is the exact scan"},
             "sweep": sweep,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     ix.close()
     if world > 1:
         dist.destroy_process_group()
@@ -490,10 +493,21 @@ def run_ours(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout must carry exactly ONE JSON line, but libraries print there too (NCCL announces its version on
+    # stdout at communicator creation whatever NCCL_DEBUG says on some boxes): park fd 1 on stderr for the
+    # whole run and hand the real stdout only to the final print.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real_stdout, "w")
+    try:
+        if args.impl == "reference":
+            run_reference(args, out)
+        else:
+            run_ours(args, out)
+    finally:
+        sys.stdout.flush()
+        out.flush()
 
 
 if __name__ == "__main__":

@@ -4,7 +4,7 @@ One hot path only: child-chunk similarity scan + top-k + c
 fusion, as hand-written sm_100a CUDA behind the C ABI of include/fr_index.h.  There is no CPU
 fallback: importing the compute entry points without libfrb200.so raises ImportError.
 """
-from .child_store import B200ChildStore
+from .child_store import B200ChildStore, ChildChunk
 from .collection import B200Client, B200Collection, PersistentClient, reset_registry
 from .index import (ShardIndex, canonical_space, maxsim_aggregate_device, maxsim_aggregate_host, merge_shards_device,
                     rrf_fuse_device, rrf_fuse_host)
@@ -12,7 +12,7 @@ from .multivector_store import B200MultiVectorChildStore
 from .vector_store_factory import get_child_vector_store
 
 __all__ = [
-    "B200ChildStore", "B200Client", "B200Collection", "B200MultiVectorChildStore", "PersistentClient", "ShardIndex",
+    "B200ChildStore", "ChildChunk", "B200Client", "B200Collection", "B200MultiVectorChildStore", "PersistentClient", "ShardIndex",
     "canonical_space", "get_child_vector_store", "maxsim_aggregate_device", "maxsim_aggregate_host",
     "merge_shards_device", "reset_registry", "rrf_fuse_device", "rrf_fuse_host",
 ]

@@ -11,11 +11,23 @@ exceptions, ``count`` swallows them and returns -1.
 from __future__ import annotations
 
 import os
-from typing import Any, Dict, List
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional
 
 import numpy as np
 
 from .collection import B200Client
+
+
+@dataclass
+class ChildChunk:
+    """The record ``upsert_children`` consumes -- same fields as the reference's
+    parent_child/parent_child_chunker.py:38-44 (any object with these attributes works)."""
+    child_id: int
+    parent_id: int
+    content: str
+    embedding: Optional[List[float]] = None
+    context: Optional[str] = None
 
 
 def _has_embedding(e) -> bool:

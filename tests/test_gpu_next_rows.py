@@ -302,3 +302,84 @@ def test_hybrid_retrieval_matches_reference_pipeline(frb, tmp_path, monkeypatch)
     # (the batched scan and the one-by-one scans are different kernels: scores agree to fp32 summation noise)
     np.testing.assert_allclose([c["retrieval_score"] for c in chunks_avg], [s for _, s in want_avg], rtol=1e-5)
     frb.reset_registry()
+
+
+def test_cfg3_dual_encoder_ensemble_on_device(frb):
+    """cfg3 in miniature: two collections, per-collection top-50 for a query batch, RRF(k=60) to top-10 with
+    nothing leaving the GPU between the scans and the fusion; ids and fp64 scores equal the oracle pipeline."""
+    n, B, kp = 60000, 33, 50
+    dev = torch.device("cuda", 0)
+    corp = [make_corpus(n, 384, seed=s) for s in (61, 62)]
+    corp[1][:2000] = corp[0][:2000] + 0.05 * make_corpus(2000, 384, seed=63)  # the encoders agree on some children
+    qs = [make_queries(B, c, seed=70) for c in corp]
+    cols = []
+    for c in corp:
+        ix = frb.ShardIndex(dim=384, space="cosine", dtype="bf16")
+        ix.upsert(c, np.arange(n, dtype=np.int64))
+        cols.append(ix)
+    keys = torch.empty((2, B, kp), dtype=torch.int64, device=dev)
+    for i, ix in enumerate(cols):
+        ix.search_device(torch.tensor(qs[i]).to(dev), kp, None, keys[i])
+    sc, fused = frb.rrf_fuse_device(keys, 60, 10)
+    sc, fused = sc.cpu().numpy(), fused.cpu().numpy()
+    ref_rows = []
+    for i, ix in enumerate(cols):  # oracle: exact fp32 scan of what each collection stores
+        _, r = ox.exact_topk(ox.prepare_queries(qs[i], "cosine"), ix.get_rows(0, n)[0], kp, "cosine", "f32", prepared=True)
+        ref_rows.append(r)
+    for b in range(B):
+        lists = [[str(int(x)) for x in ref_rows[i][b]] for i in range(2)]
+        want = ofusion.rrf_fuse(lists, 60, 10)
+        assert [str(int(x)) for x in fused[b]] == [c for c, _ in want], f"query {b}"
+        assert [float(s) for s in sc[b]] == [s for _, s in want]
+    for ix in cols:
+        ix.close()
+
+
+def test_concurrent_search_and_upsert_threads(frb, tmp_path, monkeypatch):
+    """The reference serves requests from Flask threads + an executor thread + a daemon ingest thread
+    (api_server.py:851-866, 1342-1371), each constructing its own store object: concurrent search and
+    upsert_children on one collection must stay consistent (threading)."""
+    import threading
+
+    monkeypatch.setenv("CHROMA_CHILD_PERSIST_DIR", str(tmp_path))
+    monkeypatch.setenv("B200_CHILD_AUTOPERSIST", "0")
+    frb.reset_registry()
+    n0, n_add = 4000, 2000
+    corpus = make_corpus(n0 + n_add, 384, seed=31)
+    store = frb.get_child_vector_store(collection="children_threads")
+    store.upsert_children([_Child(i + 1, 0, f"t{i}", corpus[i].tolist()) for i in range(n0)])
+    errors, done = [], threading.Event()
+
+    def searcher(tid):
+        try:
+            s = frb.get_child_vector_store(collection="children_threads")  # a store object per request
+            rng = np.random.default_rng(tid)
+            while not done.is_set():
+                j = int(rng.integers(0, n0))
+                hits = s.search(corpus[j], top_k=5)
+                assert hits[0]["child_id"] == str(j + 1) and hits[0]["score"] > 0.99, (j, hits[0])
+                multi = s.search_batch(corpus[j:j + 3], top_k=5)
+                assert [m[0]["child_id"] for m in multi] == [str(j + 1 + t) for t in range(len(multi))]
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    def writer():
+        try:
+            s = frb.get_child_vector_store(collection="children_threads")
+            for lo in range(n0, n0 + n_add, 100):
+                s.upsert_children([_Child(i + 1, 0, f"t{i}", corpus[i].tolist()) for i in range(lo, lo + 100)])
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=searcher, args=(t,)) for t in range(4)]
+    w = threading.Thread(target=writer)
+    for t in threads + [w]:
+        t.start()
+    w.join()
+    done.set()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    assert store.count() == n0 + n_add
+    assert store.search(corpus[n0 + n_add - 1], top_k=1)[0]["child_id"] == str(n0 + n_add)
+    frb.reset_registry()
