@@ -42,8 +42,8 @@ CHUNK_ROWS = 500_000          # global generation chunk; seed = 1234 + chunk ind
 DEFAULT_ROWS = 100_000_000    # BASELINE.json: "exact top-10 over 100M x 384"
 DEFAULT_BATCH = 1024          # cfg4 spans batch 1-4096; QPS is quoted in the batched (tensor-core) regime,
                               # the HBM-streaming regime (batch 1 ... 128) is in "sweep" of the same line
-DEFAULT_SWEEP = "1,8,64,128,256,4096"
-MMA_GROUP = 256               # queries per K2 corpus pass above 128 (CTA pairs); K1 serves batch 1
+DEFAULT_SWEEP = "1,1s,8,64,128,256,4096"   # "1s" = batch 1 through the K1 streaming kernel (path stream)
+MMA_GROUP = 256               # queries per K2 corpus pass above 128 (CTA pairs)
 METRIC = "QPS exact top-10 over 100Mx384 bf16 (cosine), row-sharded"
 
 
@@ -171,25 +171,29 @@ def ncu_traffic(path_kind, rows_local):
         return None
 
 
-def scan_kernel_of(batch, path, k):
+def scan_kernel_of(batch, path, k, dtype="bf16"):
     """Which scan kernel a batch runs on (mirrors search_on_stream in csrc/api.cu) and the queries
     one launch of it serves."""
-    mma_ok = k <= 32
-    use_mma = mma_ok and (path == "mma" or (path == "auto" and batch >= 2))
+    mma_ok = k <= 100 and dtype == "bf16"
+    use_mma = mma_ok and path in ("mma", "auto")
     if not use_mma:
         return "scan_stream_kernel", "stream", min(batch, 4)
+    if batch <= 64 and k <= 32 and not (batch > 32 and k > 16):
+        nq = 16 if batch <= 16 else (32 if batch <= 32 else 64)
+        return f"scan_mma_small_kernel<{nq},*> (tcgen05, corpus rows as M, queries as N)", "mma_small", batch
     if batch <= 128:
         return "scan_mma_kernel<1,1> (tcgen05, one CTA per SM)", "mma_cg1", batch
     return "scan_mma_kernel<1,2> (tcgen05 cta_group::2, CTA pairs)", "mma_cg2", None  # per launch: from the count
 
 
 def roofline_of(batch, path, k, rows_local, elem, scan_ms, scan_launches, searches, step_ms_total):
+    dtype = "bf16" if elem == 2 else "f32"
     """Roofline of the dominant (scan) kernel from its CUDA-event time inside the library.
     Algorithmic work per launch (DESIGN.md 4): bytes = rows_per_gpu * 384 * sizeof(elem) -- the corpus is
     read once per launch whatever the number of queries; flops = 2 * rows_per_gpu * 384 * queries the
     launch serves.  The bound is whichever of bytes/hbm_peak and flops/tensor_peak is the longer."""
     hbm_peak, tf_sustained, tf_burst, peak_kind = measured_peaks()
-    kernel, kind, _ = scan_kernel_of(batch, path, k)
+    kernel, kind, _ = scan_kernel_of(batch, path, k, dtype)
     avg_launch_s = (scan_ms / max(scan_launches, 1)) / 1e3
     q_per_launch = batch * max(searches, 1) / max(scan_launches, 1)
     bytes_per_launch = rows_local * DIM * elem
@@ -446,13 +450,17 @@ def run_ours(args, out=sys.stdout):
 
     # ---- brief sweep over the other batch sizes of cfg4 (each with its own roofline) ------------------
     sweep = []
-    for sb in [int(x) for x in args.sweep.split(",") if x.strip()]:
-        if sb == b:
+    for item in [x.strip() for x in args.sweep.split(",") if x.strip()]:
+        spath = "stream" if item.endswith("s") else args.path
+        sb = int(item.rstrip("s"))
+        if sb == b and spath == args.path:
             continue
         st = max(3, min(10, args.steps))
+        ix.set_path(spath)
         sms, _, sscan, _ = measure(sb, st, 3, profile=True)
-        r = roofline_of(sb, args.path, k, rows_local, elem, sscan[0], sscan[1], sscan[2], sms)
-        sweep.append({"batch": sb, "qps": sb * st / (sms / 1e3), "ms_per_step": sms / st,
+        ix.set_path(args.path)
+        r = roofline_of(sb, spath, k, rows_local, elem, sscan[0], sscan[1], sscan[2], sms)
+        sweep.append({"batch": sb, "path": spath, "qps": sb * st / (sms / 1e3), "ms_per_step": sms / st,
                       "kernel": r["kernel"], "bound": r["bound"], "frac": r["frac"], "achieved": r["achieved"],
                       "unit": r["unit"], "hbm_gbs": r["hbm_gbs"], "hbm_frac": r["hbm_frac"],
                       "tensor_tflops": r["tensor_tflops"], "tensor_frac_sustained": r["tensor_frac_sustained"]})

@@ -161,7 +161,9 @@ struct fr_index {
     DevBuf q_raw, q_prep, q_keys, partials, out_dist, out_keys, stage_vecs, stage_keys, stage_rows;
     DevBuf q_bf16, err_bound, sel, sel_keys, flags, fail, fb_partials, tau;  // K2 path
     DevBuf kth_exact, r_q, r_misc, r_tau, r_partials, r_sel, r_sel_keys;     // K2 second-chance pass
-    int mma_min_batch = 2;  // FR_PATH_AUTO: batches at least this large go to the tensor-core scan
+    int mma_min_batch = 2;  // FR_PATH_AUTO: batches at least this large go to the tensor-core scans; smaller ones
+                            // too when the swapped-operand kernel K2s serves them (it out-streams K1: TMA ring)
+    int mma_small_max = 64;  // K2s serves batches up to this size (0 = never)
     int mma_debug = 0;      // diagnostics (scripts/ablate_mma.py): results are wrong when non-zero
     int mma_co_groups = 2;  // K2: query groups of 256 that share one corpus stream through L2
     DevBuf stats;           // [0] queries K2 could not certify (re-scanned by the stream kernel), cumulative
@@ -332,6 +334,8 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     const int ksel = fr::scan_mma_ksel(k);
     const int group = fr::scan_mma_group(B);
     const int nq_pad = ((B + group - 1) / group) * group;
+    // small batches take the swapped-operand kernel (tensor work proportional to the batch)
+    const bool small = ix->mma_small_max > 0 && B <= ix->mma_small_max && fr::scan_mma_small_nq(B, ksel) != 0;
     const fr::MmaPlan plan = fr::scan_mma_plan(ix->sm_count, ix->rows, B, ix->mma_co_groups);
     const int grid = plan.lists_max;  // partial lists per query (at most)
     FR_CUDA(ix->q_bf16.need(static_cast<size_t>(nq_pad) * ix->dim * 2));
@@ -369,7 +373,10 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     ProfScope prof{ix, s};
     int rc = prof.begin();
     if (rc != FR_OK) return rc;
-    FR_CUDA(fr::launch_scan_mma(ms));
+    if (small)
+        FR_CUDA(fr::launch_scan_mma_small(ms));
+    else
+        FR_CUDA(fr::launch_scan_mma(ms));
     rc = prof.end();
     if (rc != FR_OK) return rc;
 
@@ -539,7 +546,8 @@ int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *
                     "FR_PATH_MMA serves bf16 x 384 cosine collections with k <= 100 and at least one row "
                     "(this one: dtype %d, dim %d, metric %d, k %d, rows %lld)",
                     ix->dtype, ix->dim, ix->metric, k, (long long)ix->rows);
-    const bool use_mma = eligible && (ix->path == FR_PATH_MMA || (ix->path == FR_PATH_AUTO && B >= ix->mma_min_batch));
+    const bool k2s = ix->mma_small_max > 0 && B <= ix->mma_small_max && fr::scan_mma_small_nq(B, fr::scan_mma_ksel(k)) != 0;
+    const bool use_mma = eligible && (ix->path == FR_PATH_MMA || (ix->path == FR_PATH_AUTO && (B >= ix->mma_min_batch || k2s)));
     const size_t qbytes = static_cast<size_t>(B) * ix->dim * sizeof(float);
     const float *q = d_queries;
     if (ix->metric == FR_COSINE) {
@@ -658,6 +666,11 @@ int fr_index_set_option(fr_index *ix, const char *name, int64_t value) {
     if (std::strcmp(name, "mma_co_groups") == 0) {
         if (value < 1 || value > 8) return fail(FR_EINVAL, "mma_co_groups must be in [1, 8]");
         ix->mma_co_groups = static_cast<int>(value);
+        return FR_OK;
+    }
+    if (std::strcmp(name, "mma_small_max") == 0) {
+        if (value < 0 || value > 64) return fail(FR_EINVAL, "mma_small_max must be in [0, 64]");
+        ix->mma_small_max = static_cast<int>(value);
         return FR_OK;
     }
     if (std::strcmp(name, "mma_debug") == 0) {

@@ -59,13 +59,18 @@ struct MmaScanArgs {
     const int *nq_dev;          // optional: the launch serves *nq_dev queries (second-chance pass), 0 = exit at once
     const float *tau0;          // optional [nq_total]: fixed initial threshold per query (second-chance pass)
     int dbg;                    // diagnostics only (option "mma_debug"): 1 = no corpus loads, 2 = no accumulator reads
-    uint32_t *tau_g;            // [ksel][nq_total] shared threshold slots (order_bits of a score), zeroed before the launches
+    uint32_t *tau_g;            // ksel * nq_total shared threshold slots (order_bits of a score), zeroed before the launches;
+                                // K2 lays them out [ksel][nq_total], K2s [nq_total][ksel]
     cudaStream_t stream;
 };
 int scan_mma_ksel(int k);  // 0 = k not served by the tensor-core path
 int scan_mma_group(int nq_total);  // queries per corpus pass: 128 (one CTA per SM) or 256 (CTA pairs)
 cudaError_t launch_prep_queries(const float *q, int nq, int nq_pad, void *qb, float *err_bound, cudaStream_t s);
 cudaError_t launch_scan_mma(const MmaScanArgs &a);
+// K2s (scan_mma_small.cu): operands swapped for 2..64 queries, k' <= 64.  Uses plan.lists CTAs, one launch,
+// queries_bf16 padded to scan_mma_small_nq() rows; writes partials [plan.lists][nq_total][ksel].
+int scan_mma_small_nq(int nq_total, int ksel);  // padded query count (16/32/64), 0 = not served
+cudaError_t launch_scan_mma_small(const MmaScanArgs &a);
 
 struct RescoreArgs {
     const uint64_t *sel;  // [B][ksel] selection lists (K3 output, packed)

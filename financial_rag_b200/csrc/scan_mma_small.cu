@@ -1,0 +1,345 @@
+// K2s scan_topk_mma_small -- the tensor-core scan for SMALL query batches (2 ... 64 queries), operands swapped.
+//
+// Replaces the arithmetic behind chromadb Collection.query (parent_child/chroma_child_store.py:63,
+// parent_child/multivector_store.py:151) in the HBM-bound regime, where the scan must cost nothing but the
+// corpus read.  Measured on B200 (profiles/r01_ablate_small_batch.jsonl): the TMA-fed ring alone streams the
+// corpus at 7.2 TB/s with the board already near its 1 kW cap; the [128 queries x 128 rows] MMAs of K2 pull
+// the clocks down and cost 17-27 % of that bandwidth -- even when 120 of the 128 query rows are zero padding.
+// So here the CORPUS tile is the M operand and the QUERIES are the N operand:
+//     D[128 rows x NQ queries] += A[128 rows x 16] * B[NQ queries x 16]^T        (NQ = 16, 32 or 64)
+// and the tensor work (and its energy) shrinks with the batch: 1/8 of K2's at 16 queries.
+//   * A = corpus tiles, streamed by TMA exactly as in K2 ([64 x 128] boxes, SWIZZLE_128B, K-major) through
+//     an mbarrier ring;  B = the query block, loaded once ([64 x NQ] boxes, six K-chunks);
+//   * accumulators: 4 x NQ TMEM columns; one TMEM lane = one corpus ROW, one column = one query;
+//   * epilogue (4 warps, a thread per row): tcgen05.ld its NQ scores, release the accumulator at once, then
+//     max_q (score_q - tau_q) > 0 ?  -- NQ FADDs + NQ/2 FMNMX per row; only then the insert path: the queries
+//     with a passing row are walked one by one, a ballot over the 32 rows, warp-cooperative sorted insert into
+//     that warp's list for the query (shared memory), new threshold.  No score ever goes to HBM;
+//   * thresholds are shared between CTAs through tau_g slots as in K2 (slot = stream % k'), laid out
+//     [query][slot] so a warp refreshes a query with one coalesced read and a warp-min;
+//   * at the end the four warps' lists of each query are merged and written to `partials` in K2's format, so
+//     everything downstream (K3 merge, exact rescoring + certification, second chance, stream re-scan) is shared.
+// Roofline: HBM.  Algorithmic bytes per launch = rows * 768.
+#include "fr_kernels.h"
+#include "mma_common.cuh"
+
+namespace fr {
+namespace mma {
+
+constexpr int S_THREADS = 192;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
+constexpr int S_TMEM_COLS = 256; // 4 accumulators at a 64-column stride
+constexpr int S_ACC_STRIDE = 64;
+constexpr int S_TMEM_BUFS = 4;
+
+template <int NQ, int KPL>
+struct SmallPlan {
+    static constexpr int CAP = 32 * KPL;
+    static constexpr size_t Q_CHUNK = size_t(NQ) * K_CHUNK * 2;                  // [NQ x 64] bf16
+    static constexpr size_t Q_BYTES = size_t(K_CHUNKS) * Q_CHUNK;
+    static constexpr size_t LIST_BYTES = size_t(4) * NQ * CAP * 8;               // [4 warps][NQ][CAP]
+    static constexpr size_t STASH_BYTES = size_t(4) * NQ * 32 * 4;               // [4 warps][NQ][32 rows] fp32
+    static constexpr size_t FIXED = Q_BYTES + LIST_BYTES + STASH_BYTES + 256 + 1024;  // + barriers + alignment slack
+    static constexpr int STAGES_FIT = int((232448 - FIXED) / STAGE_BYTES);
+    static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+    static constexpr size_t Q_OFF = 0;
+    static constexpr size_t RING_OFF = Q_BYTES;                                  // NQ*768 is a multiple of 1024
+    static constexpr size_t LIST_OFF = RING_OFF + size_t(STAGES) * STAGE_BYTES;
+    static constexpr size_t STASH_OFF = LIST_OFF + LIST_BYTES;
+    static constexpr size_t BAR_OFF = STASH_OFF + STASH_BYTES;
+    static constexpr size_t ALLOC = BAR_OFF + 256 + 1024;
+    static_assert(STAGES >= 3, "ring too shallow");
+    static_assert(Q_CHUNK % 1024 == 0, "query chunks must keep the 1024-byte swizzle alignment");
+};
+
+// 16 consecutive fp32 columns of this thread's TMEM lane (no wait: the caller waits once for all its loads)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+// grid = P CTAs (P = partial lists per query); CTA p takes corpus tiles p, p + P, ... of 128 rows.
+// partials: [P][nq_total][ksel].
+template <int NQ, int KPL>
+__global__ void __launch_bounds__(S_THREADS, 1)
+scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
+                      const int64_t *__restrict__ keys_or_null, int64_t n_rows, int nq, int ksel,
+                      uint64_t *__restrict__ partials, int nq_total, uint32_t *__restrict__ tau_g) {
+    using Plan = SmallPlan<NQ, KPL>;
+    constexpr int STAGES = Plan::STAGES;
+    constexpr int CAP = Plan::CAP;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem_q = smem + Plan::Q_OFF;
+    uint8_t *smem_ring = smem + Plan::RING_OFF;
+    uint64_t *lists = reinterpret_cast<uint64_t *>(smem + Plan::LIST_OFF);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Plan::BAR_OFF);
+    // barrier slots: full[STAGES] | empty[STAGES] | tmem_full[4] | tmem_empty[4] | q_full | tmem_ptr
+    const uint32_t bar_full = smem_u32(bars);
+    const uint32_t bar_empty = smem_u32(bars + STAGES);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES);
+    const uint32_t bar_tempty = smem_u32(bars + 2 * STAGES + 4);
+    const uint32_t bar_qfull = smem_u32(bars + 2 * STAGES + 8);
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 9);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int cta = blockIdx.x;
+    const int ncta = gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int b = 0; b < S_TMEM_BUFS; ++b) {
+            mbar_init(bar_tfull + 8 * b, 1);
+            mbar_init(bar_tempty + 8 * b, 4);  // one arrival per epilogue warp
+        }
+        mbar_init(bar_qfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                     "r"(S_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < 4 * NQ * CAP; i += 128) lists[i] = 0ull;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int64_t num_tiles = (n_rows + TILE_ROWS_CTA - 1) / TILE_ROWS_CTA;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(bar_qfull, Plan::Q_BYTES);
+#pragma unroll
+            for (int kc = 0; kc < K_CHUNKS; ++kc)
+                tma_load_2d<1>(smem_u32(smem_q + kc * Plan::Q_CHUNK), &tmap_q, bar_qfull, kc * K_CHUNK, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t t = cta; t < num_tiles; t += ncta) {
+                const int row0 = static_cast<int>(t * TILE_ROWS_CTA);
+#pragma unroll 1
+                for (int kc = 0; kc < K_CHUNKS; ++kc) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
+                    tma_load_2d<1>(smem_u32(smem_ring + stage * STAGE_BYTES), &tmap_c, bar_full + 8 * stage, kc * K_CHUNK, row0);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: D[128 rows x NQ] += corpus chunk * queries^T =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(TILE_ROWS_CTA, NQ);
+            mbar_wait(bar_qfull, 0);
+            tc_fence_after();
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t it = 0;
+            for (int64_t t = cta; t < num_tiles; t += ncta, ++it) {
+                const uint32_t buf = it % S_TMEM_BUFS;
+                const uint32_t bphase = (it / S_TMEM_BUFS) & 1;
+                mbar_wait(bar_tempty + 8 * buf, bphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * S_ACC_STRIDE;
+#pragma unroll 1
+                for (int kc = 0; kc < K_CHUNKS; ++kc) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem_ring + stage * STAGE_BYTES);
+                    const uint32_t b_addr = smem_u32(smem_q + kc * Plan::Q_CHUNK);
+#pragma unroll
+                    for (int k4 = 0; k4 < K_CHUNK / UMMA_K; ++k4) {
+                        const uint64_t adesc = make_kmajor_sw128_desc(a_addr + k4 * UMMA_K * 2);
+                        const uint64_t bdesc = make_kmajor_sw128_desc(b_addr + k4 * UMMA_K * 2);
+                        tc_mma_bf16<1>(d_tmem, adesc, bdesc, idesc, (kc | k4) != 0 ? 1u : 0u);
+                    }
+                    tc_commit<1>(bar_empty + 8 * stage);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                tc_commit<1>(bar_tfull + 8 * buf);
+            }
+        }
+    } else {
+        // ===================== epilogue: one TMEM lane = one corpus row =====================
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access = rows [32 quarter, +32) of the tile
+        uint64_t *my_lists = lists + static_cast<size_t>(warp - 2) * NQ * CAP;  // [NQ][CAP], sorted descending
+        float *my_stash = reinterpret_cast<float *>(smem + Plan::STASH_OFF) + static_cast<size_t>(warp - 2) * NQ * 32;
+        float tau[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) tau[q] = q < nq ? -INFINITY : INFINITY;  // padded queries never pass
+        // shared thresholds (see scan_mma.cu): this CTA raises slot cta % k' of a query to the best score it holds
+        uint32_t *my_slots = tau_g + (cta % ksel);  // + q * ksel
+        uint32_t it = 0;
+        for (int64_t t = cta; t < num_tiles; t += ncta, ++it) {
+            const uint32_t buf = it % S_TMEM_BUFS;
+            const uint32_t bphase = (it / S_TMEM_BUFS) & 1;
+            // refresh from the other CTAs.  tau_g is laid out [query][k' slots] here, so the k' slots of a query
+            // are one or two coalesced 128-byte reads for the warp (lane j reads slot j) and a warp min: one L2
+            // request per query instead of k' (the requests of all CTAs meet on the same few lines)
+            if (it < 8u || (it & 7u) == 0u) {
+                uint32_t x[NQ];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    x[q] = 0u;
+                    if (q < nq) {  // warp-uniform
+                        const uint32_t *sp = tau_g + static_cast<size_t>(q) * ksel + lane;
+                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(x[q]) : "l"(sp));
+                        if (KPL == 2) {
+                            uint32_t y;
+                            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(y) : "l"(sp + 32));
+                            x[q] = min(x[q], y);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    if (q < nq) {
+                        const uint32_t m = __reduce_min_sync(FULL_MASK, x[q]);
+                        if (m != 0u) tau[q] = fmaxf(tau[q], unorder_bits(m));
+                    }
+                }
+            }
+            mbar_wait(bar_tfull + 8 * buf, bphase);
+            tc_fence_after();
+            uint32_t r[NQ];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * S_ACC_STRIDE;
+#pragma unroll
+            for (int c = 0; c < NQ / 16; ++c) tmem_ld16_nowait(taddr + c * 16, r + c * 16);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // the scores are in registers: hand the accumulator back before looking at them
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+            float v[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) v[q] = __uint_as_float(r[q]);
+            float m0 = v[0] - tau[0], m1 = v[1] - tau[1];
+#pragma unroll
+            for (int q = 2; q < NQ; q += 2) {
+                m0 = fmaxf(m0, v[q] - tau[q]);
+                m1 = fmaxf(m1, v[q + 1] - tau[q + 1]);
+            }
+            if (!__any_sync(FULL_MASK, fmaxf(m0, m1) > 0.0f)) continue;  // the common case
+            // ---- candidate path (one copy of the insert code whatever NQ: the queries with a passing row are
+            //      walked with a run-time index, so the scores go through shared memory) ----
+            const uint32_t row = static_cast<uint32_t>(t * TILE_ROWS_CTA) + quarter * 32 + lane;
+            bool valid = row < n_rows;  // rows past the end arrive as zeros from TMA
+            if (valid && keys_or_null != nullptr) valid = keys_or_null[row] != KEY_TOMBSTONE;
+            uint32_t pm[(NQ + 31) / 32];  // this row's passing queries
+#pragma unroll
+            for (int h = 0; h < (NQ + 31) / 32; ++h) pm[h] = 0u;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                my_stash[q * 32 + lane] = v[q];
+                pm[q / 32] |= (valid && v[q] > tau[q]) ? (1u << (q & 31)) : 0u;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < (NQ + 31) / 32; ++h) {
+                uint32_t qm = __reduce_or_sync(FULL_MASK, pm[h]);  // queries with at least one passing row
+                while (qm != 0u) {
+                    const int qb = __ffs(qm) - 1;
+                    qm &= qm - 1;
+                    const int q = h * 32 + qb;
+                    unsigned mask = __ballot_sync(FULL_MASK, (pm[h] >> qb) & 1u);
+                    uint64_t *lp = my_lists + q * CAP;
+                    WarpTopK<KPL> lst;
+#pragma unroll
+                    for (int j = 0; j < KPL; ++j) lst.e[j] = lp[j * 32 + lane];
+                    const uint64_t mine = pack_key(my_stash[q * 32 + lane], row);
+                    uint32_t best = 0;
+                    while (mask) {
+                        const int src = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const uint32_t lo = __shfl_sync(FULL_MASK, static_cast<uint32_t>(mine), src);
+                        const uint32_t hi = __shfl_sync(FULL_MASK, static_cast<uint32_t>(mine >> 32), src);
+                        lst.insert((static_cast<uint64_t>(hi) << 32) | lo, CAP, lane);
+                        best = max(best, hi);
+                    }
+#pragma unroll
+                    for (int j = 0; j < KPL; ++j) lp[j * 32 + lane] = lst.e[j];
+                    const float nt = key_threshold(lst.kth(CAP));
+#pragma unroll
+                    for (int qq = 0; qq < NQ; ++qq)  // tau lives in registers: predicated update of entry q
+                        tau[qq] = (qq == q) ? fmaxf(tau[qq], nt) : tau[qq];
+                    if (lane == 0) atomicMax(my_slots + static_cast<size_t>(q) * ksel, best);
+                }
+            }
+            __syncwarp();
+        }
+        // ---- merge the four warps' lists of each query, write the CTA's partial lists ----
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+        for (int q = warp - 2; q < nq; q += 4) {
+            WarpTopK<KPL> lst;
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) lst.e[j] = lists[static_cast<size_t>(q) * CAP + j * 32 + lane];
+            for (int w = 1; w < 4; ++w) lst.merge_sorted(lists + (static_cast<size_t>(w) * NQ + q) * CAP, CAP, CAP, lane);
+            uint64_t *dst = partials + (static_cast<size_t>(cta) * nq_total + q) * ksel;
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) dst[j * 32 + lane] = lst.e[j];
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(S_TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace mma
+
+namespace {
+template <int NQ, int KPL>
+cudaError_t launch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CUtensorMap &tc) {
+    auto kern = mma::scan_mma_small_kernel<NQ, KPL>;
+    constexpr size_t smem = mma::SmallPlan<NQ, KPL>::ALLOC;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    kern<<<a.plan.lists, mma::S_THREADS, smem, a.stream>>>(tq, tc, a.keys_or_null, a.n_rows, a.nq_total, a.ksel, a.partials,
+                                                          a.nq_total, a.tau_g);
+    count_launch();
+    return cudaGetLastError();
+}
+}  // namespace
+
+int scan_mma_small_nq(int nq_total, int ksel) {
+    if (nq_total < 1 || nq_total > 64 || ksel > 64) return 0;
+    if (nq_total > 32 && ksel > 32) return 0;  // 64 queries x 64-entry lists x 4 warps do not fit beside the ring
+    return nq_total <= 16 ? 16 : (nq_total <= 32 ? 32 : 64);
+}
+
+cudaError_t launch_scan_mma_small(const MmaScanArgs &a) {
+    const int nq_pad = scan_mma_small_nq(a.nq_total, a.ksel);
+    if (nq_pad == 0 || a.nq_pad < nq_pad) return cudaErrorInvalidValue;
+    CUtensorMap tq, tc;
+    if (!mma::make_row_major_map(&tq, a.queries_bf16, a.nq_pad, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, nq_pad) ||
+        !mma::make_row_major_map(&tc, a.corpus, a.n_rows, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16))
+        return cudaErrorNotSupported;
+    const bool k1 = a.ksel <= 32;
+    switch (nq_pad) {
+        case 16: return k1 ? launch_small<16, 1>(a, tq, tc) : launch_small<16, 2>(a, tq, tc);
+        case 32: return k1 ? launch_small<32, 1>(a, tq, tc) : launch_small<32, 2>(a, tq, tc);
+        default: return k1 ? launch_small<64, 1>(a, tq, tc) : cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace fr

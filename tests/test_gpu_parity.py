@@ -477,6 +477,36 @@ def test_mma_co_resident_groups_do_not_change_results(frb):
     ix.close()
 
 
+@pytest.mark.parametrize("B,k", [(2, 10), (16, 10), (17, 16), (32, 32), (33, 10), (64, 16), (64, 32)])
+def test_small_batch_swapped_operand_kernel_equals_k2(frb, B, k):
+    """K2s (corpus rows as the MMA's M operand, queries as N; batches <= 64) and K2 select the same candidates:
+    after the shared exact rescoring the answers are bit-identical, with and without deleted rows."""
+    n = 45000
+    corpus = make_corpus(n, 384, seed=900 + B, dup_pairs=[(11, 30000)])
+    queries = make_queries(B, corpus, seed=901 + k)
+    queries[1] = corpus[11]
+    ix = build_index(frb, corpus, "cosine", "bf16")
+    ix.set_path("mma")
+    for round_ in range(2):
+        ix.set_option("mma_small_max", 64)
+        d_s, k_s = ix.search(queries, k)
+        ix.set_option("mma_small_max", 0)
+        d_b, k_b = ix.search(queries, k)
+        np.testing.assert_array_equal(k_s, k_b)
+        np.testing.assert_array_equal(d_s, d_b)
+        live = None
+        if round_ == 1:
+            live = np.ones(n, bool)
+            live[victims - KEY_BASE] = False
+        assert_matches_oracle(d_s, keys_to_rows(k_s, KEY_BASE), queries, corpus, k, "cosine", "bf16",
+                              stored=stored_rows(ix), live=live, label=f"k2s B={B} k={k} round {round_}")
+        if round_ == 0:
+            assert keys_to_rows(k_s[1], KEY_BASE)[0] == 11 and (k < 2 or keys_to_rows(k_s[1], KEY_BASE)[1] == 30000)
+            victims = np.unique(k_s[:, 0])
+            ix.delete(victims)
+    ix.close()
+
+
 def test_mma_certification_fallback_on_mass_ties(frb):
     """More exact duplicates than the k' = 32 selection slots: the tensor-core selection cannot be
     certified, so the query must be re-scanned by the stream kernel and still return the LOWEST
