@@ -455,12 +455,16 @@ def run_ours(args, out=sys.stdout):
         sb = int(item.rstrip("s"))
         if sb == b and spath == args.path:
             continue
-        st = max(3, min(10, args.steps))
         ix.set_path(spath)
+        # size each entry to ~0.5 s of device time (>= 3 steps) after a short pause, so that it is neither a cold
+        # burst nor riding on the power state the previous (much heavier or lighter) entry left behind
+        probe_ms, _, _, _ = measure(sb, 2, 3)
+        st = max(3, min(60, int(500.0 / max(probe_ms / 2, 1e-3))))
+        time.sleep(0.5)
         sms, _, sscan, _ = measure(sb, st, 3, profile=True)
         ix.set_path(args.path)
         r = roofline_of(sb, spath, k, rows_local, elem, sscan[0], sscan[1], sscan[2], sms)
-        sweep.append({"batch": sb, "path": spath, "qps": sb * st / (sms / 1e3), "ms_per_step": sms / st,
+        sweep.append({"batch": sb, "path": spath, "steps": st, "qps": sb * st / (sms / 1e3), "ms_per_step": sms / st,
                       "kernel": r["kernel"], "bound": r["bound"], "frac": r["frac"], "achieved": r["achieved"],
                       "unit": r["unit"], "hbm_gbs": r["hbm_gbs"], "hbm_frac": r["hbm_frac"],
                       "tensor_tflops": r["tensor_tflops"], "tensor_frac_sustained": r["tensor_frac_sustained"]})
@@ -488,6 +492,7 @@ def run_ours(args, out=sys.stdout):
             "clocks": clocks,
             "verified": verified,
             "mma_uncertified_queries": uncertified,
+            "mma_rescanned_queries": ix.stat("mma_rescanned_queries"),
             "reference_chroma": {"recall_at_10": None, "qps": None,
                                  "note": "Chroma HNSW CPU path not runnable offline: the chromadb wheel is neither in the "
                                          "reference tree nor in this image (SURVEY.md 8c/8d); the CPU arm is the exact scan"},

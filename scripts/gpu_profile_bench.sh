@@ -9,12 +9,15 @@ python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytes
 tail -3 $OUT/pytest_gpu_$TAG.log
 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "ref rc=$?"
-SHORT="python bench.py --steps 2 --warmup 3 --sweep 1,128 --no-cpu-baseline"
+SHORT="python bench.py --steps 2 --warmup 3 --sweep 1,1s,8,128 --no-cpu-baseline"
 $SHORT > $OUT/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'scan_|merge_|rescore|prep_q|ingest|rrf' -c 600 \
     --csv --log-file $OUT/launches_$TAG.csv $SHORT > $OUT/ncu_launch_$TAG.log 2>&1
 echo "launch list rc=$?"
 $SHORT > $OUT/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:scan_mma -s 6 -c 2 -o $OUT/prof_mma_bench_$TAG -f \
+ncu --set full --clock-control none --import-source on -k regex:scan_mma_kernel -s 6 -c 2 -o $OUT/prof_mma_bench_$TAG -f \
     $SHORT > $OUT/ncu_full_$TAG.log 2>&1
 echo "full capture rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:scan_mma_small -s 6 -c 2 -o $OUT/prof_mma_small_bench_$TAG -f \
+    $SHORT > $OUT/ncu_full_small_$TAG.log 2>&1
+echo "full capture (K2s) rc=$?"
