@@ -126,6 +126,18 @@ class B200Collection:
             p = self._payload.get(int(key))
             return p["metadata"] if p is not None else None
 
+    def set_metadata(self, id_str: str, metadata: Optional[dict]) -> None:
+        """Replace the metadata of an existing id (chromadb ``update`` without embeddings)."""
+        with self._lock:
+            k = self.key_of(id_str)
+            if k is None:
+                return
+            self._payload[k]["metadata"] = dict(metadata) if metadata is not None else None
+            if self.directory is not None:
+                self._dirty_payload.add(k)
+                if _autopersist():
+                    self.persist()
+
     def upsert(self, ids: Sequence[str], embeddings=None, metadatas: Optional[Sequence[Optional[dict]]] = None,
                documents: Optional[Sequence[Optional[str]]] = None, keys: Optional[Sequence[int]] = None) -> None:
         """``keys`` (ours, not chromadb's): explicit int64 row keys for the ids, for callers that encode

@@ -538,6 +538,20 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
 int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *d_out_dist,
                      uint64_t *d_out_packed, int64_t *d_out_keys, cudaStream_t s) {
     if (B == 0) return FR_OK;
+    // very large batches go through in slices so the per-call scratch (partial lists: streams x B x k' x 8 B)
+    // stays bounded; a slice is still 16 corpus passes of 512 queries
+    constexpr int MAX_SLICE = 8192;
+    if (B > MAX_SLICE) {
+        for (int b0 = 0; b0 < B; b0 += MAX_SLICE) {
+            const int nb = B - b0 < MAX_SLICE ? B - b0 : MAX_SLICE;
+            const size_t o = static_cast<size_t>(b0) * k;
+            int rc = search_on_stream(ix, d_queries + static_cast<size_t>(b0) * ix->dim, nb, k,
+                                      d_out_dist ? d_out_dist + o : nullptr, d_out_packed ? d_out_packed + o : nullptr,
+                                      d_out_keys + o, s);
+            if (rc != FR_OK) return rc;
+        }
+        return FR_OK;
+    }
     ix->n_searches += 1;
     ix->n_queries += B;
     const bool eligible = mma_eligible(ix, k);

@@ -13,6 +13,11 @@ h = next(i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r)
 hdr = rows[h]
 si, ai, ei, ad = hdr.index("# Samples"), hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("Address")
 data = rows[h + 1:]
+for cut, r in enumerate(data):  # a report may hold several launches: keep the first one
+    if r and r[0] == "Kernel Name":
+        data = data[:cut]
+        break
+data = [r for r in data if len(r) > max(si, ai, ei, ad)]
 tot = sum(int(r[si]) for r in data)
 print(f"{rows[0][1][:90] if len(rows[0]) > 1 else ''}\ntotal samples {tot}, {len(data)} instructions")
 # who branches to each spin loop (labels mbarrier waits by their call site)

@@ -383,3 +383,60 @@ def test_concurrent_search_and_upsert_threads(frb, tmp_path, monkeypatch):
     assert store.count() == n0 + n_add
     assert store.search(corpus[n0 + n_add - 1], top_k=1)[0]["child_id"] == str(n0 + n_add)
     frb.reset_registry()
+
+
+def test_migrate_chroma_wal_replay(frb, golden, tmp_path, monkeypatch):
+    """A Chroma persist directory with the schema of the reference's .chroma_children/chroma.sqlite3 (built here
+    from the golden fixture: same 18 WAL rows, same blobs) is replayed into B200 collections; the migrated
+    collections answer the known-answer query of SURVEY.md 8c (A1 A2 A3 B1 B2 B3 C1 C2 C3, insertion order)."""
+    import sqlite3
+
+    from financial_rag_b200.migrate_chroma import replay_wal
+
+    src = tmp_path / "chroma_src"
+    src.mkdir()
+    con = sqlite3.connect(str(src / "chroma.sqlite3"))
+    con.executescript("""
+        create table collections (id text primary key, name text not null, dimension integer, database_id text not null,
+                                  config_json_str text);
+        create table collection_metadata (collection_id text, key text, str_value text, int_value integer,
+                                          float_value real, bool_value integer);
+        create table segments (id text primary key, type text not null, scope text not null, collection text not null);
+        create table embeddings (id integer primary key, segment_id text not null, embedding_id text not null,
+                                 seq_id blob not null);
+        create table embeddings_queue (seq_id integer primary key, operation integer not null, topic text not null,
+                                       id text not null, vector blob, encoding text, metadata text);
+    """)
+    uuid_of = {}
+    for i, (name, cfg) in enumerate(golden["raw"]["collections"].items()):
+        uuid_of[name] = f"0000000{i}-aaaa-bbbb-cccc-00000000000{i}"
+        con.execute("insert into collections values (?,?,?,?,?)",
+                    (uuid_of[name], name, cfg["dimension"], "db", json.dumps(cfg["config"])))
+        con.execute("insert into segments values (?,?,?,?)", (f"seg{i}", "urn:vector", "VECTOR", uuid_of[name]))
+    for r in golden["raw"]["rows"]:
+        con.execute("insert into embeddings_queue values (?,?,?,?,?,?,?)",
+                    (r["seq_id"], r["operation"], f"persistent://default/default/{uuid_of[r['collection']]}", r["id"],
+                     bytes.fromhex(r["vector_f32le_hex"]), "FLOAT32", json.dumps(r["metadata"]) if r["metadata"] else None))
+    # one delete + one re-upsert at the end of the log, to exercise every operation
+    first = golden["raw"]["rows"][0]
+    topic = f"persistent://default/default/{uuid_of[first['collection']]}"
+    con.execute("insert into embeddings_queue values (100, 3, ?, ?, null, null, null)", (topic, first["id"]))
+    con.execute("insert into embeddings_queue values (101, 2, ?, ?, ?, 'FLOAT32', ?)",
+                (topic, first["id"], bytes.fromhex(first["vector_f32le_hex"]), json.dumps(first["metadata"])))
+    con.commit()
+    con.close()
+
+    frb.reset_registry()
+    dst = frb.PersistentClient(path=str(tmp_path / "b200_dst"))
+    report = replay_wal(str(src), dst)
+    for name, col in golden["collections"].items():
+        assert report[name]["count"] == 9, report
+        got = dst.get_collection(name)
+        assert got.space == "cosine"
+        res = got.query(query_embeddings=[col["vectors"][1].tolist()], n_results=9, include=["metadatas", "distances"])
+        want = [col["ids"][i] for i in (1, 4, 7, 0, 3, 6, 2, 5, 8)]
+        if name == first["collection"]:  # the deleted + re-upserted id moved to the end of the insertion order
+            want = [col["ids"][i] for i in (1, 4, 7, 3, 6, 0, 2, 5, 8)]
+        assert res["ids"][0] == want
+        assert res["metadatas"][0][0] == col["metadatas"][1]
+    frb.reset_registry()

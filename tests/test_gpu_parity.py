@@ -507,6 +507,24 @@ def test_small_batch_swapped_operand_kernel_equals_k2(frb, B, k):
     ix.close()
 
 
+def test_huge_batch_is_sliced(frb):
+    """A batch above the 8192-query slice size is served slice by slice with bounded scratch and equals the
+    per-slice answers."""
+    n, B, k = 3000, 8192 + 300, 5
+    corpus = make_corpus(n, 384, seed=123)
+    queries = make_queries(B, corpus, seed=124)
+    ix = build_index(frb, corpus, "cosine", "bf16")
+    d, kk = ix.search(queries, k)
+    d0, k0 = ix.search(queries[:8192], k)
+    d1, k1 = ix.search(queries[8192:], k)
+    np.testing.assert_array_equal(kk, np.concatenate([k0, k1]))
+    np.testing.assert_array_equal(d, np.concatenate([d0, d1]))
+    rows = keys_to_rows(kk[8190:8200], KEY_BASE)
+    assert_matches_oracle(d[8190:8200], rows, queries[8190:8200], corpus, k, "cosine", "bf16", stored=stored_rows(ix),
+                          label="sliced batch")
+    ix.close()
+
+
 def test_mma_certification_fallback_on_mass_ties(frb):
     """More exact duplicates than the k' = 32 selection slots: the tensor-core selection cannot be
     certified, so the query must be re-scanned by the stream kernel and still return the LOWEST
