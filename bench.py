@@ -252,12 +252,19 @@ def cpu_scan_qps(n_rows_full, batch, k, sample_rows, steps, warmup, torch=None, 
     corpus = ox.prepare_corpus(corpus, "cosine", "f32")
     q = ox.prepare_queries(q, "cosine")
     cores = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all the host threads it can
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=cores)
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write(f"[bench] threadpoolctl unavailable ({e}); BLAS keeps its default thread count\n")
 
     def run_numpy():
         return ox.exact_topk_thresholded(q, corpus, k, "cosine", chunk_rows=max(16384, min(1 << 20, (1 << 26) // batch)))
 
     def run_c():
-        return cscan.exact_topk_prepared(corpus, q, k, "cosine")
+        return cscan.exact_topk_prepared(corpus, q, k, "cosine", nthreads=cores)
 
     results = {}
     arms = [("numpy_sgemm", run_numpy)]

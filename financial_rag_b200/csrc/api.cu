@@ -281,10 +281,17 @@ struct ProfScope {
     }
 };
 
-bool mma_eligible(const fr_index *ix, int k) {
-    return ix->dtype == FR_BF16 && ix->dim == 384 && ix->metric == FR_COSINE && fr::scan_mma_ksel(k) != 0 &&
-           ix->rows > 0;
+// The tensor-core scans serve bf16 cosine collections: K2 and K2s at width 384, K2s alone (small batches, larger
+// ones in slices) at width 768 -- the multi-vector store's bert-base token vectors (multivector_store.py:70).
+int mma_slice(const fr_index *ix, int k) {  // 0 = not eligible, else the largest batch one pass may take
+    const int ksel = fr::scan_mma_ksel(k);
+    if (ix->dtype != FR_BF16 || ix->metric != FR_COSINE || ksel == 0 || ix->rows <= 0) return 0;
+    if (ix->dim == 384) return 1 << 30;
+    if (ix->dim != 768) return 0;  // the re-scan safety net exists for 384 and 768 only
+    const int m = fr::scan_mma_small_max_batch(ksel, ix->dim);
+    return m < ix->mma_small_max ? m : ix->mma_small_max;
 }
+bool mma_eligible(const fr_index *ix, int k) { return mma_slice(ix, k) > 0; }
 
 // K1 path: CUDA-core streaming scan, ceil(B/4) corpus passes.
 int search_stream(fr_index *ix, const float *q, int B, int k, float *d_out_dist, uint64_t *d_out_packed,
@@ -335,7 +342,9 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     const int group = fr::scan_mma_group(B);
     const int nq_pad = ((B + group - 1) / group) * group;
     // small batches take the swapped-operand kernel (tensor work proportional to the batch)
-    const bool small = ix->mma_small_max > 0 && B <= ix->mma_small_max && fr::scan_mma_small_nq(B, ksel) != 0;
+    const bool small = ix->mma_small_max > 0 && B <= ix->mma_small_max && fr::scan_mma_small_nq(B, ksel, ix->dim) != 0;
+    if (!small && ix->dim != 384) return fail(FR_EUNSUP, "internal: width %d needs the small-batch kernel", ix->dim);
+    const bool second_chance = ix->dim == 384;  // the second-chance pass runs on K2, which is 384-wide
     const fr::MmaPlan plan = fr::scan_mma_plan(ix->sm_count, ix->rows, B, ix->mma_co_groups);
     const int grid = plan.lists_max;  // partial lists per query (at most)
     FR_CUDA(ix->q_bf16.need(static_cast<size_t>(nq_pad) * ix->dim * 2));
@@ -355,10 +364,11 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     int *fail_count = static_cast<int *>(ix->fail.p);
     int *fail_list = fail_count + 1;
     FR_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), s));
-    FR_CUDA(fr::launch_prep_queries(q, B, nq_pad, ix->q_bf16.p, static_cast<float *>(ix->err_bound.p), s));
+    FR_CUDA(fr::launch_prep_queries(q, B, nq_pad, ix->dim, ix->q_bf16.p, static_cast<float *>(ix->err_bound.p), s));
 
     fr::MmaScanArgs ms{};
     ms.corpus = ix->corpus;
+    ms.dim = ix->dim;
     ms.keys_or_null = ix->n_deleted > 0 ? ix->keys : nullptr;
     ms.queries_bf16 = ix->q_bf16.p;
     ms.nq_pad = nq_pad;
@@ -424,6 +434,7 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     ra.sel = static_cast<const uint64_t *>(ix->sel.p);
     ra.ksel = ksel;
     ra.queries = q;
+    ra.dim = ix->dim;
     ra.corpus = ix->corpus;
     ra.row_keys = ix->keys;
     ra.err_bound = static_cast<const float *>(ix->err_bound.p);
@@ -433,72 +444,76 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     ra.out_packed = d_out_packed;
     ra.out_keys = d_out_keys;
     ra.flags = static_cast<uint8_t *>(ix->flags.p);
-    ra.fail_count = fail_count;
-    ra.fail_list = fail_list;
+    ra.fail_count = second_chance ? fail_count : fail_count2;  // without a second chance: straight to the re-scan
+    ra.fail_list = second_chance ? fail_list : fail_list2;
     ra.fail_total = stat_uncertified;
+    ra.fail_total2 = second_chance ? nullptr : stat_rescanned;
     ra.kth_exact = static_cast<float *>(ix->kth_exact.p);
     ra.stream = s;
     FR_CUDA(fr::launch_rescore(ra));
 
-    // second chance on the tensor cores for what could not be certified (all four launches return at once
-    // when nothing failed): gather -> scan above a fixed threshold -> merge -> rescore
-    fr::RetryPrepArgs rp{};
-    rp.queries = q;
-    rp.err_bound = ra.err_bound;
-    rp.kth_exact = ra.kth_exact;
-    rp.fail_count = fail_count;
-    rp.fail_list = fail_list;
-    rp.qb_retry = ix->r_q.p;
-    rp.tau0 = tau0;
-    rp.retry_n = retry_n;
-    rp.tau_g_retry = static_cast<uint32_t *>(ix->r_tau.p);
-    rp.ksel = ksel_r;
-    rp.fail_count2 = fail_count2;
-    rp.fail_list2 = fail_list2;
-    rp.flags = ra.flags;
-    rp.rescan_total = stat_rescanned;
-    rp.stream = s;
-    FR_CUDA(fr::launch_retry_prep(rp));
+    if (second_chance) {
+        // second chance on the tensor cores for what could not be certified (all four launches return at once
+        // when nothing failed): gather -> scan above a fixed threshold -> merge -> rescore
+        fr::RetryPrepArgs rp{};
+        rp.queries = q;
+        rp.err_bound = ra.err_bound;
+        rp.kth_exact = ra.kth_exact;
+        rp.fail_count = fail_count;
+        rp.fail_list = fail_list;
+        rp.qb_retry = ix->r_q.p;
+        rp.tau0 = tau0;
+        rp.retry_n = retry_n;
+        rp.tau_g_retry = static_cast<uint32_t *>(ix->r_tau.p);
+        rp.ksel = ksel_r;
+        rp.fail_count2 = fail_count2;
+        rp.fail_list2 = fail_list2;
+        rp.flags = ra.flags;
+        rp.rescan_total = stat_rescanned;
+        rp.stream = s;
+        FR_CUDA(fr::launch_retry_prep(rp));
 
-    fr::MmaScanArgs rs = ms;
-    rs.queries_bf16 = ix->r_q.p;
-    rs.nq_pad = R;
-    rs.nq_total = R;
-    rs.ksel = ksel_r;
-    rs.partials = static_cast<uint64_t *>(ix->r_partials.p);
-    rs.plan = rplan;
-    rs.tau_g = rp.tau_g_retry;
-    rs.nq_dev = retry_n;
-    rs.tau0 = tau0;
-    FR_CUDA(fr::launch_scan_mma(rs));
+        fr::MmaScanArgs rs = ms;
+        rs.queries_bf16 = ix->r_q.p;
+        rs.nq_pad = R;
+        rs.nq_total = R;
+        rs.ksel = ksel_r;
+        rs.partials = static_cast<uint64_t *>(ix->r_partials.p);
+        rs.plan = rplan;
+        rs.tau_g = rp.tau_g_retry;
+        rs.nq_dev = retry_n;
+        rs.tau0 = tau0;
+        FR_CUDA(fr::launch_scan_mma(rs));
 
-    fr::MergeArgs mr{};
-    mr.packed = rs.partials;
-    mr.P = rplan.lists;
-    mr.shard_stride = static_cast<int64_t>(R) * ksel_r;
-    mr.B = R;
-    mr.k = ksel_r;
-    mr.shards = false;
-    mr.row_keys = ix->keys;
-    mr.l2 = false;
-    mr.out_packed = static_cast<uint64_t *>(ix->r_sel.p);
-    mr.out_keys = static_cast<int64_t *>(ix->r_sel_keys.p);
-    mr.limit = retry_n;
-    mr.stream = s;
-    FR_CUDA(fr::launch_merge_topk(mr));
+        fr::MergeArgs mr{};
+        mr.packed = rs.partials;
+        mr.P = rplan.lists;
+        mr.shard_stride = static_cast<int64_t>(R) * ksel_r;
+        mr.B = R;
+        mr.k = ksel_r;
+        mr.shards = false;
+        mr.row_keys = ix->keys;
+        mr.l2 = false;
+        mr.out_packed = static_cast<uint64_t *>(ix->r_sel.p);
+        mr.out_keys = static_cast<int64_t *>(ix->r_sel_keys.p);
+        mr.limit = retry_n;
+        mr.stream = s;
+        FR_CUDA(fr::launch_merge_topk(mr));
 
-    fr::RescoreArgs rr = ra;
-    rr.sel = static_cast<const uint64_t *>(ix->r_sel.p);
-    rr.ksel = ksel_r;
-    rr.B = R;
-    rr.fail_count = fail_count2;
-    rr.fail_list = fail_list2;
-    rr.fail_total = stat_rescanned;
-    rr.kth_exact = nullptr;
-    rr.idx_list = fail_list;
-    rr.limit = retry_n;
-    rr.tau0 = tau0;
-    FR_CUDA(fr::launch_rescore(rr));
+        fr::RescoreArgs rr = ra;
+        rr.sel = static_cast<const uint64_t *>(ix->r_sel.p);
+        rr.ksel = ksel_r;
+        rr.B = R;
+        rr.fail_count = fail_count2;
+        rr.fail_list = fail_list2;
+        rr.fail_total = stat_rescanned;
+        rr.fail_total2 = nullptr;
+        rr.kth_exact = nullptr;
+        rr.idx_list = fail_list;
+        rr.limit = retry_n;
+        rr.tau0 = tau0;
+        FR_CUDA(fr::launch_rescore(rr));
+    }
 
     // safety net: both launches return immediately when every query was certified
     fr::ScanArgs sa{};
@@ -512,6 +527,8 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     sa.k = k;
     sa.nq_total = B;
     sa.stream = s;
+    if (!fr::scan_stream_fallback_serves(sa))
+        return fail(FR_EUNSUP, "internal: no re-scan kernel for width %d", ix->dim);
     sa.grid = fr::scan_stream_fallback_grid(sa, ix->sm_count);
     FR_CUDA(ix->fb_partials.need(static_cast<size_t>(sa.grid) * B * k * sizeof(uint64_t)));
     sa.partials = static_cast<uint64_t *>(ix->fb_partials.p);
@@ -540,7 +557,11 @@ int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *
     if (B == 0) return FR_OK;
     // very large batches go through in slices so the per-call scratch (partial lists: streams x B x k' x 8 B)
     // stays bounded; a slice is still 16 corpus passes of 512 queries
-    constexpr int MAX_SLICE = 8192;
+    int MAX_SLICE = 8192;
+    {
+        const int ms_ = mma_slice(ix, k);  // widths other than 384 go through K2s in slices it can hold
+        if (ms_ > 0 && ms_ < MAX_SLICE && ix->path != FR_PATH_STREAM) MAX_SLICE = ms_;
+    }
     if (B > MAX_SLICE) {
         for (int b0 = 0; b0 < B; b0 += MAX_SLICE) {
             const int nb = B - b0 < MAX_SLICE ? B - b0 : MAX_SLICE;
@@ -557,10 +578,11 @@ int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *
     const bool eligible = mma_eligible(ix, k);
     if (ix->path == FR_PATH_MMA && !eligible)
         return fail(FR_EUNSUP,
-                    "FR_PATH_MMA serves bf16 x 384 cosine collections with k <= 100 and at least one row "
+                    "FR_PATH_MMA serves bf16 cosine collections of width 384 (k <= 100) or 768 (k <= 32) with at least one row "
                     "(this one: dtype %d, dim %d, metric %d, k %d, rows %lld)",
                     ix->dtype, ix->dim, ix->metric, k, (long long)ix->rows);
-    const bool k2s = ix->mma_small_max > 0 && B <= ix->mma_small_max && fr::scan_mma_small_nq(B, fr::scan_mma_ksel(k)) != 0;
+    const bool k2s = ix->mma_small_max > 0 && B <= ix->mma_small_max &&
+                     fr::scan_mma_small_nq(B, fr::scan_mma_ksel(k), ix->dim) != 0;
     const bool use_mma = eligible && (ix->path == FR_PATH_MMA || (ix->path == FR_PATH_AUTO && (B >= ix->mma_min_batch || k2s)));
     const size_t qbytes = static_cast<size_t>(B) * ix->dim * sizeof(float);
     const float *q = d_queries;

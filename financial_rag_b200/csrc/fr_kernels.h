@@ -30,6 +30,7 @@ cudaError_t launch_scan_stream(const ScanArgs &a);
 // Re-scan of the queries K2 could not certify: one launch, loops over fail_list[0..*fail_count),
 // exits at once when the count is zero.  partials: [grid][nq_total][k], grid from
 // scan_stream_fallback_grid.
+bool scan_stream_fallback_serves(const ScanArgs &a);  // bf16 dot-product rows of width 384 or 768
 int scan_stream_fallback_grid(const ScanArgs &a, int sm_count);
 cudaError_t launch_scan_stream_fallback(const ScanArgs &a, const int *fail_count, const int *fail_list);
 
@@ -46,7 +47,8 @@ struct MmaPlan {
 MmaPlan scan_mma_plan(int sm_count, int64_t n_rows, int nq_total, int co_max);
 
 struct MmaScanArgs {
-    const void *corpus;         // [rows][384] bf16
+    const void *corpus;         // [rows][dim] bf16
+    int dim;                    // 384 for K2; K2s takes any multiple of 64 up to 1024
     const int64_t *keys_or_null;
     const void *queries_bf16;   // [nq_pad][384] bf16, nq_pad multiple of scan_mma_group(), zero padded
     int nq_pad;
@@ -65,17 +67,19 @@ struct MmaScanArgs {
 };
 int scan_mma_ksel(int k);  // 0 = k not served by the tensor-core path
 int scan_mma_group(int nq_total);  // queries per corpus pass: 128 (one CTA per SM) or 256 (CTA pairs)
-cudaError_t launch_prep_queries(const float *q, int nq, int nq_pad, void *qb, float *err_bound, cudaStream_t s);
+cudaError_t launch_prep_queries(const float *q, int nq, int nq_pad, int dim, void *qb, float *err_bound, cudaStream_t s);
 cudaError_t launch_scan_mma(const MmaScanArgs &a);
 // K2s (scan_mma_small.cu): operands swapped for 2..64 queries, k' <= 64.  Uses plan.lists CTAs, one launch,
 // queries_bf16 padded to scan_mma_small_nq() rows; writes partials [plan.lists][nq_total][ksel].
-int scan_mma_small_nq(int nq_total, int ksel);  // padded query count (16/32/64), 0 = not served
+int scan_mma_small_nq(int nq_total, int ksel, int dim);  // padded query count (16/32/64), 0 = not served
+int scan_mma_small_max_batch(int ksel, int dim);         // largest batch one K2s launch serves (0 = none)
 cudaError_t launch_scan_mma_small(const MmaScanArgs &a);
 
 struct RescoreArgs {
     const uint64_t *sel;  // [B][ksel] selection lists (K3 output, packed)
     int ksel;
-    const float *queries;  // [B][384] fp32 prepared queries
+    const float *queries;  // [B][dim] fp32 prepared queries
+    int dim;
     const uint8_t *corpus;
     const int64_t *row_keys;
     const float *err_bound;  // [B] |q - bf16(q)|_2
@@ -87,6 +91,7 @@ struct RescoreArgs {
     int *fail_count;
     int *fail_list;        // [B]
     unsigned long long *fail_total;  // cumulative count of uncertified queries (fr_index_get_stat)
+    unsigned long long *fail_total2; // optional second counter bumped with it (failures that go straight to the re-scan)
     float *kth_exact;      // [B] out (first pass): k-th exact score, the anchor of the second-chance threshold
     const int *idx_list;   // second pass: CTA j answers query idx_list[j] from sel[j] ...
     const int *limit;      // ... for j < *limit

@@ -184,13 +184,13 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// [rows][384] bf16 row-major -> boxes of [64 elements x box_rows rows], 128-byte swizzle, OOB rows read as zero
+// [rows][dim] bf16 row-major -> boxes of [64 elements x box_rows rows], 128-byte swizzle, OOB rows read as zero
 static bool make_row_major_map(CUtensorMap *map, const void *base, int64_t rows, CUtensorMapDataType dt,
-                               int box_rows = TILE_ROWS_CTA) {
+                               int box_rows = TILE_ROWS_CTA, int dim = DIM) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return false;
-    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(DIM), static_cast<cuuint64_t>(rows)};
-    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(DIM * 2)};
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dim) * 2};
     const cuuint32_t box[2] = {K_CHUNK, static_cast<cuuint32_t>(box_rows)};
     const cuuint32_t estr[2] = {1, 1};
     return fn(map, dt, 2, const_cast<void *>(base), gdim, gstride, box, estr,

@@ -56,6 +56,7 @@ constexpr int THREADS = 192;                   // warp 0 TMA, warp 1 MMA + TMEM 
 
 constexpr int PEND = 16;                       // unsorted pending candidates per query between compactions
 constexpr int RETRY_MAX = M_TILE;              // uncertified queries that get a second tensor-core pass
+constexpr int RESCORE_MAX_DIM = 1024;          // widest vectors the rescoring kernel stages in shared memory
 
 // Per-query candidate lists hold CAP = 32*KPL = k' entries.  For k' <= 64 they live in shared memory;
 // for k' = 128 (k up to 100) 128 queries x 1 KB would not fit beside the 96 KB query block, so the CTA
@@ -469,15 +470,15 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 // ---------------------------------------------------------------------------------------------
 // Query preparation for K2: bf16 copy (zero-padded to a multiple of 128 rows) and the per-query
 // selection error bound |q - q16|_2.
-__global__ void prep_queries_kernel(const float *__restrict__ q, int nq, int nq_pad, __nv_bfloat16 *__restrict__ qb,
-                                    float *__restrict__ err_bound) {
+__global__ void prep_queries_kernel(const float *__restrict__ q, int nq, int nq_pad, int dim,
+                                    __nv_bfloat16 *__restrict__ qb, float *__restrict__ err_bound) {
     const int row = blockIdx.x;
     const int lane = threadIdx.x;  // 32 threads
     float ss = 0.0f;
-    for (int e = lane; e < DIM; e += 32) {
-        const float x = row < nq ? q[static_cast<size_t>(row) * DIM + e] : 0.0f;
+    for (int e = lane; e < dim; e += 32) {
+        const float x = row < nq ? q[static_cast<size_t>(row) * dim + e] : 0.0f;
         const __nv_bfloat16 h = __float2bfloat16_rn(x);
-        qb[static_cast<size_t>(row) * DIM + e] = h;
+        qb[static_cast<size_t>(row) * dim + e] = h;
         const float d = x - __bfloat162float(h);
         ss = fmaf(d, d, ss);
     }
@@ -503,14 +504,14 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
                uint64_t *__restrict__ out_packed, int64_t *__restrict__ out_keys, uint8_t *__restrict__ flags,
                int *__restrict__ fail_count, int *__restrict__ fail_list, unsigned long long *__restrict__ fail_total,
                float *__restrict__ kth_exact_out, const int *__restrict__ idx_list, const int *__restrict__ limit,
-               const float *__restrict__ tau0) {
-    __shared__ float sq[DIM];
+               const float *__restrict__ tau0, int dim, unsigned long long *__restrict__ fail_total2) {
+    __shared__ float sq[RESCORE_MAX_DIM];
     __shared__ uint64_t exact[32 * KPL];
     const int j_cta = blockIdx.x;
     if (limit != nullptr && j_cta >= *limit) return;
     const int b = idx_list != nullptr ? idx_list[j_cta] : j_cta;  // the query this CTA answers
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int e = threadIdx.x; e < DIM; e += blockDim.x) sq[e] = queries[static_cast<size_t>(b) * DIM + e];
+    for (int e = threadIdx.x; e < dim; e += blockDim.x) sq[e] = queries[static_cast<size_t>(b) * dim + e];
     for (int i = threadIdx.x; i < 32 * KPL; i += blockDim.x) exact[i] = 0ull;
     __syncthreads();
     const uint64_t *s = sel + static_cast<size_t>(j_cta) * ksel;
@@ -518,13 +519,12 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
         const uint64_t key = s[j];
         if (key == 0ull) continue;  // warp-uniform
         const uint32_t row = key_row(key);
-        // lane l owns elements [12 l, 12 l + 12): three 8-byte loads
-        const uint2 *rp = reinterpret_cast<const uint2 *>(corpus + static_cast<size_t>(row) * (DIM * 2) + lane * 24);
+        // 8-byte pieces (4 bf16) of the row, lane-strided: coalesced 256 bytes per warp step
+        const uint2 *rp = reinterpret_cast<const uint2 *>(corpus + static_cast<size_t>(row) * (static_cast<size_t>(dim) * 2));
         float acc = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const uint2 w = rp[i];
-            const float *qq = sq + lane * 12 + i * 4;
+        for (int c = lane; c < dim / 4; c += 32) {
+            const uint2 w = rp[c];
+            const float *qq = sq + c * 4;
             acc = fmaf(__uint_as_float(w.x << 16), qq[0], acc);
             acc = fmaf(__uint_as_float(w.x & 0xffff0000u), qq[1], acc);
             acc = fmaf(__uint_as_float(w.y << 16), qq[2], acc);
@@ -546,8 +546,8 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
         lst.insert(key, 32 * KPL, lane);
     }
     // certification: anything outside the candidate set scores at most (its selection-score ceiling + bound);
-    // |c|_2 <= 1 + 2^-9 for a bf16-rounded unit row, 1e-5 covers the fp32 accumulation of 384 products
-    const float bound = err_bound[b] * 1.004f + 1e-5f;
+    // |c|_2 <= 1 + 2^-9 for a bf16-rounded unit row, 1e-5 (per 384 products) covers the fp32 accumulation
+    const float bound = err_bound[b] * 1.004f + 1e-5f * static_cast<float>((dim + 383) / 384);
     const uint64_t last_sel = s[ksel - 1];
     const float kth_exact = n_valid >= k ? key_score(lst.kth(k)) : -INFINITY;
     bool certified = true;
@@ -578,6 +578,7 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
         if (!certified) {
             fail_list[atomicAdd(fail_count, 1)] = b;
             if (fail_total) atomicAdd(fail_total, 1ull);
+            if (fail_total2) atomicAdd(fail_total2, 1ull);
         }
     }
 }
@@ -626,8 +627,8 @@ int scan_mma_ksel(int k) { return k <= 16 ? 32 : (k <= 32 ? 64 : (k <= 100 ? 128
 // queries served by one corpus pass: a single CTA per SM up to 128, CTA pairs (cta_group::2) above
 int scan_mma_group(int nq_total) { return nq_total <= mma::M_TILE ? mma::M_TILE : 2 * mma::M_TILE; }
 
-cudaError_t launch_prep_queries(const float *q, int nq, int nq_pad, void *qb, float *err_bound, cudaStream_t s) {
-    mma::prep_queries_kernel<<<nq_pad, 32, 0, s>>>(q, nq, nq_pad, static_cast<__nv_bfloat16 *>(qb), err_bound);
+cudaError_t launch_prep_queries(const float *q, int nq, int nq_pad, int dim, void *qb, float *err_bound, cudaStream_t s) {
+    mma::prep_queries_kernel<<<nq_pad, 32, 0, s>>>(q, nq, nq_pad, dim, static_cast<__nv_bfloat16 *>(qb), err_bound);
     count_launch();
     return cudaGetLastError();
 }
@@ -716,11 +717,12 @@ cudaError_t launch_scan_mma(const MmaScanArgs &a) {
 
 cudaError_t launch_rescore(const RescoreArgs &a) {
     if (a.B <= 0) return cudaSuccess;
+    if (a.dim > mma::RESCORE_MAX_DIM || a.dim % 4 != 0) return cudaErrorInvalidValue;
 #define FR_RESCORE(KPL)                                                                                       \
     mma::rescore_kernel<KPL><<<a.B, 128, 0, a.stream>>>(a.sel, a.ksel, a.queries, a.corpus, a.row_keys, a.err_bound, \
                                                        a.k, a.out_dist, a.out_packed, a.out_keys, a.flags,       \
                                                        a.fail_count, a.fail_list, a.fail_total, a.kth_exact,     \
-                                                       a.idx_list, a.limit, a.tau0)
+                                                       a.idx_list, a.limit, a.tau0, a.dim, a.fail_total2)
     if (a.ksel <= 32) FR_RESCORE(1);
     else if (a.ksel <= 64) FR_RESCORE(2);
     else if (a.ksel <= 128) FR_RESCORE(4);

@@ -31,25 +31,32 @@ constexpr int S_TMEM_COLS = 256; // 4 accumulators at a 64-column stride
 constexpr int S_ACC_STRIDE = 64;
 constexpr int S_TMEM_BUFS = 4;
 
+// Shared-memory plan.  The vector width is a run-time property (k_chunks = dim / 64: 6 for the 384-d
+// bge-small / gte-small embeddings, 12 for 768-d bert-base token vectors of the multi-vector store), so the
+// offsets are computed, identically, on the host (launch size) and in the kernel.
+constexpr int S_MAX_STAGES = 8;
 template <int NQ, int KPL>
 struct SmallPlan {
     static constexpr int CAP = 32 * KPL;
     static constexpr size_t Q_CHUNK = size_t(NQ) * K_CHUNK * 2;                  // [NQ x 64] bf16
-    static constexpr size_t Q_BYTES = size_t(K_CHUNKS) * Q_CHUNK;
     static constexpr size_t LIST_BYTES = size_t(4) * NQ * CAP * 8;               // [4 warps][NQ][CAP]
     static constexpr size_t STASH_BYTES = size_t(4) * NQ * 32 * 4;               // [4 warps][NQ][32 rows] fp32
-    static constexpr size_t FIXED = Q_BYTES + LIST_BYTES + STASH_BYTES + 256 + 1024;  // + barriers + alignment slack
-    static constexpr int STAGES_FIT = int((232448 - FIXED) / STAGE_BYTES);
-    static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
-    static constexpr size_t Q_OFF = 0;
-    static constexpr size_t RING_OFF = Q_BYTES;                                  // NQ*768 is a multiple of 1024
-    static constexpr size_t LIST_OFF = RING_OFF + size_t(STAGES) * STAGE_BYTES;
-    static constexpr size_t STASH_OFF = LIST_OFF + LIST_BYTES;
-    static constexpr size_t BAR_OFF = STASH_OFF + STASH_BYTES;
-    static constexpr size_t ALLOC = BAR_OFF + 256 + 1024;
-    static_assert(STAGES >= 3, "ring too shallow");
     static_assert(Q_CHUNK % 1024 == 0, "query chunks must keep the 1024-byte swizzle alignment");
+    size_t q_bytes, ring_off, list_off, stash_off, bar_off, alloc;
+    int stages;
+    __host__ __device__ explicit SmallPlan(int k_chunks) {
+        q_bytes = size_t(k_chunks) * Q_CHUNK;                                    // a multiple of 1024
+        const size_t fixed = q_bytes + LIST_BYTES + STASH_BYTES + 256 + 1024;    // + barriers + alignment slack
+        const long fit = fixed < 232448 ? long((232448 - fixed) / STAGE_BYTES) : 0;
+        stages = fit > S_MAX_STAGES ? S_MAX_STAGES : int(fit);
+        ring_off = q_bytes;
+        list_off = ring_off + size_t(stages) * STAGE_BYTES;
+        stash_off = list_off + LIST_BYTES;
+        bar_off = stash_off + STASH_BYTES;
+        alloc = bar_off + 256 + 1024;
+    }
 };
+constexpr int S_MIN_STAGES = 4;  // a shallower ring cannot cover the HBM latency
 
 // 16 consecutive fp32 columns of this thread's TMEM lane (no wait: the caller waits once for all its loads)
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *r) {
@@ -67,23 +74,24 @@ template <int NQ, int KPL>
 __global__ void __launch_bounds__(S_THREADS, 1)
 scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                       const int64_t *__restrict__ keys_or_null, int64_t n_rows, int nq, int ksel,
-                      uint64_t *__restrict__ partials, int nq_total, uint32_t *__restrict__ tau_g) {
+                      uint64_t *__restrict__ partials, int nq_total, uint32_t *__restrict__ tau_g, int k_chunks) {
     using Plan = SmallPlan<NQ, KPL>;
-    constexpr int STAGES = Plan::STAGES;
+    const Plan plan(k_chunks);
+    const int STAGES = plan.stages;
     constexpr int CAP = Plan::CAP;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *smem_q = smem + Plan::Q_OFF;
-    uint8_t *smem_ring = smem + Plan::RING_OFF;
-    uint64_t *lists = reinterpret_cast<uint64_t *>(smem + Plan::LIST_OFF);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Plan::BAR_OFF);
-    // barrier slots: full[STAGES] | empty[STAGES] | tmem_full[4] | tmem_empty[4] | q_full | tmem_ptr
+    uint8_t *smem_q = smem;
+    uint8_t *smem_ring = smem + plan.ring_off;
+    uint64_t *lists = reinterpret_cast<uint64_t *>(smem + plan.list_off);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + plan.bar_off);
+    // barrier slots: full[8] | empty[8] | tmem_full[4] | tmem_empty[4] | q_full | tmem_ptr
     const uint32_t bar_full = smem_u32(bars);
-    const uint32_t bar_empty = smem_u32(bars + STAGES);
-    const uint32_t bar_tfull = smem_u32(bars + 2 * STAGES);
-    const uint32_t bar_tempty = smem_u32(bars + 2 * STAGES + 4);
-    const uint32_t bar_qfull = smem_u32(bars + 2 * STAGES + 8);
-    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 9);
+    const uint32_t bar_empty = smem_u32(bars + S_MAX_STAGES);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * S_MAX_STAGES);
+    const uint32_t bar_tempty = smem_u32(bars + 2 * S_MAX_STAGES + 4);
+    const uint32_t bar_qfull = smem_u32(bars + 2 * S_MAX_STAGES + 8);
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * S_MAX_STAGES + 9);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -120,16 +128,15 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_expect_tx(bar_qfull, Plan::Q_BYTES);
-#pragma unroll
-            for (int kc = 0; kc < K_CHUNKS; ++kc)
+            mbar_expect_tx(bar_qfull, static_cast<uint32_t>(plan.q_bytes));
+            for (int kc = 0; kc < k_chunks; ++kc)
                 tma_load_2d<1>(smem_u32(smem_q + kc * Plan::Q_CHUNK), &tmap_q, bar_qfull, kc * K_CHUNK, 0);
             int stage = 0;
             uint32_t phase = 0;
             for (int64_t t = cta; t < num_tiles; t += ncta) {
                 const int row0 = static_cast<int>(t * TILE_ROWS_CTA);
 #pragma unroll 1
-                for (int kc = 0; kc < K_CHUNKS; ++kc) {
+                for (int kc = 0; kc < k_chunks; ++kc) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
                     tma_load_2d<1>(smem_u32(smem_ring + stage * STAGE_BYTES), &tmap_c, bar_full + 8 * stage, kc * K_CHUNK, row0);
@@ -156,7 +163,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * S_ACC_STRIDE;
 #pragma unroll 1
-                for (int kc = 0; kc < K_CHUNKS; ++kc) {
+                for (int kc = 0; kc < k_chunks; ++kc) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem_ring + stage * STAGE_BYTES);
@@ -180,7 +187,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         // ===================== epilogue: one TMEM lane = one corpus row =====================
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access = rows [32 quarter, +32) of the tile
         uint64_t *my_lists = lists + static_cast<size_t>(warp - 2) * NQ * CAP;  // [NQ][CAP], sorted descending
-        float *my_stash = reinterpret_cast<float *>(smem + Plan::STASH_OFF) + static_cast<size_t>(warp - 2) * NQ * 32;
+        float *my_stash = reinterpret_cast<float *>(smem + plan.stash_off) + static_cast<size_t>(warp - 2) * NQ * 32;
         float tau[NQ];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) tau[q] = q < nq ? -INFINITY : INFINITY;  // padded queries never pass
@@ -309,37 +316,61 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 
 namespace {
 template <int NQ, int KPL>
-cudaError_t launch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CUtensorMap &tc) {
+cudaError_t launch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CUtensorMap &tc, int k_chunks, size_t *alloc_out) {
+    const mma::SmallPlan<NQ, KPL> plan(k_chunks);
+    if (alloc_out) {  // planning only: does this instance fit, and with how deep a ring?
+        *alloc_out = plan.stages >= mma::S_MIN_STAGES ? plan.alloc : 0;
+        return cudaSuccess;
+    }
+    if (plan.stages < mma::S_MIN_STAGES) return cudaErrorInvalidValue;
     auto kern = mma::scan_mma_small_kernel<NQ, KPL>;
-    constexpr size_t smem = mma::SmallPlan<NQ, KPL>::ALLOC;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.alloc));
     if (e != cudaSuccess) return e;
-    kern<<<a.plan.lists, mma::S_THREADS, smem, a.stream>>>(tq, tc, a.keys_or_null, a.n_rows, a.nq_total, a.ksel, a.partials,
-                                                          a.nq_total, a.tau_g);
+    kern<<<a.plan.lists, mma::S_THREADS, plan.alloc, a.stream>>>(tq, tc, a.keys_or_null, a.n_rows, a.nq_total, a.ksel,
+                                                                a.partials, a.nq_total, a.tau_g, k_chunks);
     count_launch();
     return cudaGetLastError();
 }
+
+cudaError_t dispatch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CUtensorMap &tc, int nq_pad, int ksel,
+                           int k_chunks, size_t *alloc_out) {
+    const bool k1 = ksel <= 32;
+    switch (nq_pad) {
+        case 16: return k1 ? launch_small<16, 1>(a, tq, tc, k_chunks, alloc_out) : launch_small<16, 2>(a, tq, tc, k_chunks, alloc_out);
+        case 32: return k1 ? launch_small<32, 1>(a, tq, tc, k_chunks, alloc_out) : launch_small<32, 2>(a, tq, tc, k_chunks, alloc_out);
+        case 64: return k1 ? launch_small<64, 1>(a, tq, tc, k_chunks, alloc_out) : launch_small<64, 2>(a, tq, tc, k_chunks, alloc_out);
+        default: return cudaErrorInvalidValue;
+    }
+}
 }  // namespace
 
-int scan_mma_small_nq(int nq_total, int ksel) {
-    if (nq_total < 1 || nq_total > 64 || ksel > 64) return 0;
-    if (nq_total > 32 && ksel > 32) return 0;  // 64 queries x 64-entry lists x 4 warps do not fit beside the ring
-    return nq_total <= 16 ? 16 : (nq_total <= 32 ? 32 : 64);
+// Padded query count (16 / 32 / 64) of the instance that serves `nq_total` queries of width `dim` with k' = ksel,
+// 0 when none fits (too many queries for the shared memory left beside a ring of at least S_MIN_STAGES stages).
+int scan_mma_small_nq(int nq_total, int ksel, int dim) {
+    if (nq_total < 1 || nq_total > 64 || ksel > 64 || dim < 64 || dim % 64 != 0 || dim > 1024) return 0;
+    const int nq_pad = nq_total <= 16 ? 16 : (nq_total <= 32 ? 32 : 64);
+    size_t alloc = 0;
+    MmaScanArgs dummy{};
+    CUtensorMap none{};
+    if (dispatch_small(dummy, none, none, nq_pad, ksel, dim / mma::K_CHUNK, &alloc) != cudaSuccess || alloc == 0) return 0;
+    return nq_pad;
+}
+
+// largest batch one K2s launch can serve for this width and k' (0 = none)
+int scan_mma_small_max_batch(int ksel, int dim) {
+    for (int nq : {64, 32, 16})
+        if (scan_mma_small_nq(nq, ksel, dim) != 0) return nq;
+    return 0;
 }
 
 cudaError_t launch_scan_mma_small(const MmaScanArgs &a) {
-    const int nq_pad = scan_mma_small_nq(a.nq_total, a.ksel);
+    const int nq_pad = scan_mma_small_nq(a.nq_total, a.ksel, a.dim);
     if (nq_pad == 0 || a.nq_pad < nq_pad) return cudaErrorInvalidValue;
     CUtensorMap tq, tc;
-    if (!mma::make_row_major_map(&tq, a.queries_bf16, a.nq_pad, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, nq_pad) ||
-        !mma::make_row_major_map(&tc, a.corpus, a.n_rows, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16))
+    if (!mma::make_row_major_map(&tq, a.queries_bf16, a.nq_pad, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, nq_pad, a.dim) ||
+        !mma::make_row_major_map(&tc, a.corpus, a.n_rows, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, mma::TILE_ROWS_CTA, a.dim))
         return cudaErrorNotSupported;
-    const bool k1 = a.ksel <= 32;
-    switch (nq_pad) {
-        case 16: return k1 ? launch_small<16, 1>(a, tq, tc) : launch_small<16, 2>(a, tq, tc);
-        case 32: return k1 ? launch_small<32, 1>(a, tq, tc) : launch_small<32, 2>(a, tq, tc);
-        default: return k1 ? launch_small<64, 1>(a, tq, tc) : cudaErrorInvalidValue;
-    }
+    return dispatch_small(a, tq, tc, nq_pad, a.ksel, a.dim / mma::K_CHUNK, nullptr);
 }
 
 }  // namespace fr

@@ -451,12 +451,12 @@ int scan_stream_plan_grid(const ScanArgs &a, int sm_count) {
 
 cudaError_t launch_scan_stream(const ScanArgs &a) { return dispatch(a, nullptr); }
 
-// fallback: bf16 x 384 rows, dot metrics only (the only layout K2 serves)
+// fallback: bf16 rows of 768 B (width 384, two per unit) or 1536 B (width 768), dot metrics only
 namespace {
-template <int KPL>
+template <int KPL, int RU>
 cudaError_t fallback_impl(const ScanArgs &a, const int *fail_count, const int *fail_list, int *occ_out) {
     const size_t smem = static_cast<size_t>(THREADS / 32) * 32 * KPL * sizeof(uint64_t);
-    auto kern = scan_stream_fallback_kernel<true, 2, KPL, false>;
+    auto kern = scan_stream_fallback_kernel<true, RU, KPL, false>;
     cudaError_t e = prepare_kernel(kern, smem, occ_out);
     if (e != cudaSuccess || occ_out) return e;
     kern<<<a.grid, THREADS, smem, a.stream>>>(a.corpus, a.keys_or_null, a.queries, a.n_rows, a.k, a.partials,
@@ -464,11 +464,18 @@ cudaError_t fallback_impl(const ScanArgs &a, const int *fail_count, const int *f
     count_launch();
     return cudaGetLastError();
 }
+cudaError_t fallback_dispatch(const ScanArgs &a, const int *fail_count, const int *fail_list, int *occ_out) {
+    if (a.dim == 384)
+        return a.k <= 32 ? fallback_impl<1, 2>(a, fail_count, fail_list, occ_out) : fallback_impl<4, 2>(a, fail_count, fail_list, occ_out);
+    return a.k <= 32 ? fallback_impl<1, 1>(a, fail_count, fail_list, occ_out) : fallback_impl<4, 1>(a, fail_count, fail_list, occ_out);
+}
 }  // namespace
+
+bool scan_stream_fallback_serves(const ScanArgs &a) { return a.bf16 && !a.l2 && (a.dim == 384 || a.dim == 768); }
 
 int scan_stream_fallback_grid(const ScanArgs &a, int sm_count) {
     int occ = 1 << 20;
-    cudaError_t e = a.k <= 32 ? fallback_impl<1>(a, nullptr, nullptr, &occ) : fallback_impl<4>(a, nullptr, nullptr, &occ);
+    cudaError_t e = fallback_dispatch(a, nullptr, nullptr, &occ);
     if (e != cudaSuccess || occ == (1 << 20)) occ = 1;
     int64_t want = ((a.n_rows + 31) / 32 + (THREADS / 32) - 1) / (THREADS / 32);
     if (want < 1) want = 1;
@@ -477,8 +484,7 @@ int scan_stream_fallback_grid(const ScanArgs &a, int sm_count) {
 }
 
 cudaError_t launch_scan_stream_fallback(const ScanArgs &a, const int *fail_count, const int *fail_list) {
-    return a.k <= 32 ? fallback_impl<1>(a, fail_count, fail_list, nullptr)
-                     : fallback_impl<4>(a, fail_count, fail_list, nullptr);
+    return fallback_dispatch(a, fail_count, fail_list, nullptr);
 }
 
 }  // namespace fr

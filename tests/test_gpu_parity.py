@@ -507,6 +507,42 @@ def test_small_batch_swapped_operand_kernel_equals_k2(frb, B, k):
     ix.close()
 
 
+@pytest.mark.parametrize("B,k", [(1, 10), (14, 10), (32, 32), (33, 10), (100, 5)])
+def test_width_768_on_the_swapped_operand_kernel(frb, B, k):
+    """bert-base token vectors (768-d, the multi-vector store's default model, multivector_store.py:70) take K2s
+    with a run-time width; batches above what one launch holds (32 queries at this width) go through in slices;
+    uncertified queries skip the 384-wide second chance and are re-scanned by the stream kernel."""
+    n = 20000
+    corpus = make_corpus(n, 768, seed=1700 + B, dup_pairs=[(9, 15000)])
+    dup_rows = np.arange(300, 300 + 80 * 100, 100)  # 80 exact copies: more than k' (32 or 64) holds -> stream re-scan
+    corpus[dup_rows] = corpus[300]
+    queries = make_queries(B, corpus, seed=1701 + k)
+    queries[0] = corpus[9]
+    if B > 2:
+        queries[2] = corpus[300]
+    ix = build_index(frb, corpus, "cosine", "bf16")
+    ix.set_path("stream")
+    d_s, k_s = ix.search(queries, k)
+    ix.set_path("mma")
+    d_m, k_m = ix.search(queries, k)
+    assert ix.stat("mma_queries") == B
+    assert_matches_oracle(d_m, keys_to_rows(k_m, KEY_BASE), queries, corpus, k, "cosine", "bf16",
+                          stored=stored_rows(ix), label=f"768-d B={B} k={k}")
+    np.testing.assert_allclose(d_m, d_s, rtol=0, atol=4e-6)
+    mism = k_m != k_s
+    if mism.any():
+        assert np.abs(d_m[mism] - d_s[mism]).max() <= 4e-6
+    if k >= 2:
+        assert keys_to_rows(k_m[0], KEY_BASE)[0] == 9 and keys_to_rows(k_m[0], KEY_BASE)[1] == 15000
+    if B > 2:
+        assert ix.stat("mma_rescanned_queries") >= 1
+        np.testing.assert_array_equal(keys_to_rows(k_m[2], KEY_BASE), dup_rows[:k])  # ties in insertion order
+    ix.set_path("auto")
+    d_a, k_a = ix.search(queries, k)
+    np.testing.assert_array_equal(k_a, k_m)
+    ix.close()
+
+
 def test_huge_batch_is_sliced(frb):
     """A batch above the 8192-query slice size is served slice by slice with bounded scratch and equals the
     per-slice answers."""
@@ -616,7 +652,7 @@ def test_mma_path_with_deletes_and_eligibility(frb):
     with pytest.raises(FrError):
         ix.search(queries, 101)
     ix.close()
-    for kw in ({"dtype": "f32"}, {"space": "l2"}, {"dim": 768}):
+    for kw in ({"dtype": "f32"}, {"space": "l2"}, {"dim": 128}):
         args = {"dim": 384, "space": "cosine", "dtype": "bf16"}
         args.update(kw)
         jx = frb.ShardIndex(**args)
