@@ -336,7 +336,7 @@ int search_stream(fr_index *ix, const float *q, int B, int k, float *d_out_dist,
 
 // K2 path: tensor-core selection of k' candidates per query, exact fp32-query rescoring with
 // certification, and a device-side re-scan of whatever could not be certified.
-int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, uint64_t *d_out_packed,
+int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_out_dist, uint64_t *d_out_packed,
                int64_t *d_out_keys, cudaStream_t s) {
     const int ksel = fr::scan_mma_ksel(k);
     const int group = fr::scan_mma_group(B);
@@ -353,18 +353,34 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     FR_CUDA(ix->sel.need(static_cast<size_t>(B) * ksel * sizeof(uint64_t)));
     FR_CUDA(ix->sel_keys.need(static_cast<size_t>(B) * ksel * sizeof(int64_t)));
     FR_CUDA(ix->flags.need(static_cast<size_t>(B)));
-    FR_CUDA(ix->fail.need(static_cast<size_t>(B + 1) * sizeof(int)));
+    FR_CUDA(ix->fail.need((4 + 2 * static_cast<size_t>(B)) * sizeof(int)));  // 3 counters | fail_list | fail_list2
     FR_CUDA(ix->tau.need(static_cast<size_t>(B) * ksel * sizeof(uint32_t)));
+    FR_CUDA(ix->q_prep.need(static_cast<size_t>(B) * ix->dim * sizeof(float)));
     if (!ix->stats.p) {
         FR_CUDA(ix->stats.need(64));
         FR_CUDA(cudaMemsetAsync(ix->stats.p, 0, 64, s));
     }
     ix->n_mma_queries += B;
-    FR_CUDA(cudaMemsetAsync(ix->tau.p, 0, static_cast<size_t>(B) * ksel * sizeof(uint32_t), s));
-    int *fail_count = static_cast<int *>(ix->fail.p);
-    int *fail_list = fail_count + 1;
-    FR_CUDA(cudaMemsetAsync(fail_count, 0, sizeof(int), s));
-    FR_CUDA(fr::launch_prep_queries(q, B, nq_pad, ix->dim, ix->q_bf16.p, static_cast<float *>(ix->err_bound.p), s));
+    int *counters = static_cast<int *>(ix->fail.p);
+    int *fail_count = counters, *retry_n = counters + 1, *fail_count2 = counters + 2;
+    int *fail_list = counters + 4, *fail_list2 = fail_list + B;
+    // one launch: cosine normalisation (K0's arithmetic), bf16 copy, error bounds, and the reset of this call's
+    // threshold slots and failure counters
+    fr::PrepArgs pa{};
+    pa.raw = d_raw_queries;
+    pa.nq = B;
+    pa.nq_pad = nq_pad;
+    pa.dim = ix->dim;
+    pa.q_prep = static_cast<float *>(ix->q_prep.p);
+    pa.qb = ix->q_bf16.p;
+    pa.err_bound = static_cast<float *>(ix->err_bound.p);
+    pa.tau_g = static_cast<uint32_t *>(ix->tau.p);
+    pa.ksel = ksel;
+    pa.counters = counters;
+    pa.n_counters = 3;
+    pa.stream = s;
+    FR_CUDA(fr::launch_prep_queries(pa));
+    const float *q = pa.q_prep;
 
     fr::MmaScanArgs ms{};
     ms.corpus = ix->corpus;
@@ -416,16 +432,12 @@ int search_mma(fr_index *ix, const float *q, int B, int k, float *d_out_dist, ui
     const fr::MmaPlan rplan = fr::scan_mma_plan(ix->sm_count, ix->rows, R, 1);
     FR_CUDA(ix->kth_exact.need(static_cast<size_t>(B) * sizeof(float)));
     FR_CUDA(ix->r_q.need(static_cast<size_t>(R) * ix->dim * 2));
-    FR_CUDA(ix->r_misc.need(static_cast<size_t>(R) * sizeof(float) + (static_cast<size_t>(B) + 2) * sizeof(int)));
+    FR_CUDA(ix->r_misc.need(static_cast<size_t>(R) * sizeof(float)));
     FR_CUDA(ix->r_tau.need(static_cast<size_t>(R) * ksel_r * sizeof(uint32_t)));
     FR_CUDA(ix->r_partials.need(static_cast<size_t>(rplan.lists_max) * R * ksel_r * sizeof(uint64_t)));
     FR_CUDA(ix->r_sel.need(static_cast<size_t>(R) * ksel_r * sizeof(uint64_t)));
     FR_CUDA(ix->r_sel_keys.need(static_cast<size_t>(R) * ksel_r * sizeof(int64_t)));
     float *tau0 = static_cast<float *>(ix->r_misc.p);
-    int *retry_n = reinterpret_cast<int *>(tau0 + R);
-    int *fail_count2 = retry_n + 1;
-    int *fail_list2 = fail_count2 + 1;
-    FR_CUDA(cudaMemsetAsync(retry_n, 0, 2 * sizeof(int), s));
     unsigned long long *stat_uncertified = static_cast<unsigned long long *>(ix->stats.p);
     unsigned long long *stat_rescanned = stat_uncertified + 1;
 
@@ -584,6 +596,7 @@ int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *
     const bool k2s = ix->mma_small_max > 0 && B <= ix->mma_small_max &&
                      fr::scan_mma_small_nq(B, fr::scan_mma_ksel(k), ix->dim) != 0;
     const bool use_mma = eligible && (ix->path == FR_PATH_MMA || (ix->path == FR_PATH_AUTO && (B >= ix->mma_min_batch || k2s)));
+    if (use_mma) return search_mma(ix, d_queries, B, k, d_out_dist, d_out_packed, d_out_keys, s);
     const size_t qbytes = static_cast<size_t>(B) * ix->dim * sizeof(float);
     const float *q = d_queries;
     if (ix->metric == FR_COSINE) {
@@ -601,8 +614,7 @@ int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *
         FR_CUDA(fr::launch_ingest(ia));
         q = static_cast<const float *>(ix->q_prep.p);
     }
-    return use_mma ? search_mma(ix, q, B, k, d_out_dist, d_out_packed, d_out_keys, s)
-                   : search_stream(ix, q, B, k, d_out_dist, d_out_packed, d_out_keys, s);
+    return search_stream(ix, q, B, k, d_out_dist, d_out_packed, d_out_keys, s);
 }
 
 int check_search_args(fr_index *ix, const void *q, int B, int k, const void *o1, const void *o2) {

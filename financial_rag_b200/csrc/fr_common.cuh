@@ -47,6 +47,43 @@ __device__ __forceinline__ uint4 ld_stream_u4(const void *p) {
     return r;
 }
 
+// ---- warp-wide bitonic networks on packed keys (one key per lane) -------------------------------
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t x, int m) {
+    const uint32_t lo = __shfl_xor_sync(FULL_MASK, static_cast<uint32_t>(x), m);
+    const uint32_t hi = __shfl_xor_sync(FULL_MASK, static_cast<uint32_t>(x >> 32), m);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint64_t umax64(uint64_t a, uint64_t b) { return a > b ? a : b; }
+__device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+// 32 keys in bitonic order -> descending (lane 0 holds the largest)
+__device__ __forceinline__ uint64_t bitonic_merge32_desc(uint64_t x, int lane) {
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const uint64_t y = shfl_xor_u64(x, j);
+        x = ((lane & j) == 0) ? umax64(x, y) : umin64(x, y);
+    }
+    return x;
+}
+// any 32 keys -> descending
+__device__ __forceinline__ uint64_t bitonic_sort32_desc(uint64_t x, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint64_t y = shfl_xor_u64(x, j);
+            const bool desc = (lane & k) == 0;  // k = 32: every lane sorts descending
+            const bool keep_max = ((lane & j) == 0) == desc;
+            x = keep_max ? umax64(x, y) : umin64(x, y);
+        }
+    }
+    return x;
+}
+__device__ __forceinline__ uint64_t reverse32(uint64_t x, int lane) {
+    const uint32_t lo = __shfl_sync(FULL_MASK, static_cast<uint32_t>(x), 31 - lane);
+    const uint32_t hi = __shfl_sync(FULL_MASK, static_cast<uint32_t>(x >> 32), 31 - lane);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
 // A top-K list held by one warp in registers: entry i lives in lane (i & 31), slot (i >> 5).
 // Entries are sorted descending by packed key.  KPL slots per lane => capacity 32*KPL.
 template <int KPL>

@@ -67,7 +67,19 @@ struct MmaScanArgs {
 };
 int scan_mma_ksel(int k);  // 0 = k not served by the tensor-core path
 int scan_mma_group(int nq_total);  // queries per corpus pass: 128 (one CTA per SM) or 256 (CTA pairs)
-cudaError_t launch_prep_queries(const float *q, int nq, int nq_pad, int dim, void *qb, float *err_bound, cudaStream_t s);
+struct PrepArgs {
+    const float *raw;   // [nq][dim] raw fp32 queries
+    int nq, nq_pad, dim;
+    float *q_prep;      // [nq][dim] out: cosine-normalised fp32 queries (same arithmetic as K0)
+    void *qb;           // [nq_pad][dim] out: bf16 copy, zero padded
+    float *err_bound;   // [nq] out: |q - bf16(q)|_2
+    uint32_t *tau_g;    // nq * ksel threshold slots, zeroed here
+    int ksel;
+    int *counters;      // n_counters ints zeroed here (failure counters of the call)
+    int n_counters;
+    cudaStream_t stream;
+};
+cudaError_t launch_prep_queries(const PrepArgs &a);
 cudaError_t launch_scan_mma(const MmaScanArgs &a);
 // K2s (scan_mma_small.cu): operands swapped for 2..64 queries, k' <= 64.  Uses plan.lists CTAs, one launch,
 // queries_bf16 padded to scan_mma_small_nq() rows; writes partials [plan.lists][nq_total][ksel].

@@ -77,6 +77,64 @@ merge_topk_kernel(const uint64_t *__restrict__ packed, int P, int64_t shard_stri
     }
 }
 
+// k <= 32: every partial list is one sorted 32-entry vector (zero padded), so folding a list into the running
+// top-32 is an elementwise max against the reversed list + one 5-stage bitonic merge -- no per-entry inserts.
+// 8 warps fold P/8 lists each (next list prefetched while the current one is merged), then a 3-level tree.
+template <bool SHARDS>
+__global__ void __launch_bounds__(256)
+merge_topk32_kernel(const uint64_t *__restrict__ packed, int P, int64_t shard_stride, int B, int k,
+                    const int64_t *__restrict__ row_keys, const int64_t *__restrict__ shard_keys, bool l2,
+                    float *__restrict__ out_dist, uint64_t *__restrict__ out_packed,
+                    int64_t *__restrict__ out_keys, const uint8_t *__restrict__ only_flagged,
+                    const int *__restrict__ limit) {
+    __shared__ uint64_t lists[8][32];
+    const int b = blockIdx.x;
+    if (only_flagged != nullptr && only_flagged[b] == 0) return;  // uniform per CTA
+    if (limit != nullptr && b >= *limit) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    auto load = [&](int p) -> uint64_t {
+        if (p >= P || lane >= k) return 0ull;
+        uint64_t key = packed[static_cast<int64_t>(p) * shard_stride + static_cast<int64_t>(b) * k + lane];
+        if (SHARDS && key != 0ull)
+            key = (key & 0xffffffff00000000ull) | static_cast<uint64_t>(0xffffffffu - static_cast<uint32_t>(p * k + lane));
+        return key;
+    };
+    uint64_t run = 0ull;
+    uint64_t next = load(warp);
+    for (int p = warp; p < P; p += 8) {
+        const uint64_t cur = next;
+        next = load(p + 8);
+        run = bitonic_merge32_desc(umax64(run, reverse32(cur, lane)), lane);
+    }
+    lists[warp][lane] = run;
+    for (int stride = 4; stride > 0; stride >>= 1) {
+        __syncthreads();
+        if (warp < stride) {
+            run = bitonic_merge32_desc(umax64(run, reverse32(lists[warp + stride][lane], lane)), lane);
+            lists[warp][lane] = run;
+        }
+    }
+    if (warp != 0 || lane >= k) return;
+    const int64_t o = static_cast<int64_t>(b) * k + lane;
+    if (run == 0ull) {
+        if (out_dist) out_dist[o] = INFINITY;
+        if (out_packed) out_packed[o] = 0ull;
+        out_keys[o] = -1;
+        return;
+    }
+    const uint32_t idx = key_row(run);
+    const float sc = key_score(run);
+    if (out_dist) out_dist[o] = l2 ? -sc : 1.0f - sc;
+    if (out_packed) out_packed[o] = run;
+    if (SHARDS) {
+        const int g = idx / k, jj = idx - g * k;
+        out_keys[o] = shard_keys[static_cast<int64_t>(g) * shard_stride + static_cast<int64_t>(b) * k + jj];
+    } else {
+        out_keys[o] = row_keys[idx];
+    }
+}
+
 cudaError_t launch_merge_topk(const MergeArgs &a) {
     if (a.B <= 0) return cudaSuccess;
     const dim3 grid(a.B), block(128);
@@ -85,7 +143,14 @@ cudaError_t launch_merge_topk(const MergeArgs &a) {
                                                              a.row_keys, a.shard_keys, a.l2, a.out_dist, \
                                                              a.out_packed, a.out_keys, a.only_flagged, a.limit)
     if (a.k <= 32) {
-        if (a.shards) FR_MERGE(1, true); else FR_MERGE(1, false);
+        if (a.shards)
+            merge_topk32_kernel<true><<<grid, 256, 0, a.stream>>>(a.packed, a.P, a.shard_stride, a.B, a.k, a.row_keys,
+                                                                 a.shard_keys, a.l2, a.out_dist, a.out_packed, a.out_keys,
+                                                                 a.only_flagged, a.limit);
+        else
+            merge_topk32_kernel<false><<<grid, 256, 0, a.stream>>>(a.packed, a.P, a.shard_stride, a.B, a.k, a.row_keys,
+                                                                  a.shard_keys, a.l2, a.out_dist, a.out_packed, a.out_keys,
+                                                                  a.only_flagged, a.limit);
     } else if (a.k <= 128) {
         if (a.shards) FR_MERGE(4, true); else FR_MERGE(4, false);
     } else if (a.k <= 256 && !a.shards) {

@@ -79,43 +79,6 @@ static_assert(SmemPlan<1>::ALLOC <= 232448 && SmemPlan<2>::ALLOC <= 232448 && Sm
                   SmemPlan<8>::ALLOC <= 232448,
               "exceeds 227 KB of shared memory");
 
-// ---- warp-wide bitonic networks on packed keys (one key per lane) -------------------------------
-__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t x, int m) {
-    const uint32_t lo = __shfl_xor_sync(FULL_MASK, static_cast<uint32_t>(x), m);
-    const uint32_t hi = __shfl_xor_sync(FULL_MASK, static_cast<uint32_t>(x >> 32), m);
-    return (static_cast<uint64_t>(hi) << 32) | lo;
-}
-__device__ __forceinline__ uint64_t umax64(uint64_t a, uint64_t b) { return a > b ? a : b; }
-__device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
-// 32 keys in bitonic order -> descending (lane 0 holds the largest)
-__device__ __forceinline__ uint64_t bitonic_merge32_desc(uint64_t x, int lane) {
-#pragma unroll
-    for (int j = 16; j > 0; j >>= 1) {
-        const uint64_t y = shfl_xor_u64(x, j);
-        x = ((lane & j) == 0) ? umax64(x, y) : umin64(x, y);
-    }
-    return x;
-}
-// any 32 keys -> descending
-__device__ __forceinline__ uint64_t bitonic_sort32_desc(uint64_t x, int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const uint64_t y = shfl_xor_u64(x, j);
-            const bool desc = (lane & k) == 0;  // k = 32: every lane sorts descending
-            const bool keep_max = ((lane & j) == 0) == desc;
-            x = keep_max ? umax64(x, y) : umin64(x, y);
-        }
-    }
-    return x;
-}
-__device__ __forceinline__ uint64_t reverse32(uint64_t x, int lane) {
-    const uint32_t lo = __shfl_sync(FULL_MASK, static_cast<uint32_t>(x), 31 - lane);
-    const uint32_t hi = __shfl_sync(FULL_MASK, static_cast<uint32_t>(x >> 32), 31 - lane);
-    return (static_cast<uint64_t>(hi) << 32) | lo;
-}
-
 // Fold the pending candidates of one query into its sorted list (all 32 lanes cooperate).
 //   list: [32*KPL] sorted descending (0 = empty), pend_w: this warp's pending block, n = pending count.
 // Returns the new k'-th key (0 while the list is not full).
@@ -468,23 +431,59 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
-// Query preparation for K2: bf16 copy (zero-padded to a multiple of 128 rows) and the per-query
-// selection error bound |q - q16|_2.
-__global__ void prep_queries_kernel(const float *__restrict__ q, int nq, int nq_pad, int dim,
-                                    __nv_bfloat16 *__restrict__ qb, float *__restrict__ err_bound) {
+// Query preparation for K2 / K2s, one launch: cosine normalisation of the raw queries (bit for bit the
+// arithmetic of K0's ingest_kernel, so K1 and K2 see the same prepared query), the bf16 copy the tensor cores
+// read (zero-padded to nq_pad rows), the per-query selection error bound |q - bf16(q)|_2, and the reset of the
+// call's scratch (threshold slots, failure counters) that would otherwise be three memsets.
+// One warp per query row.
+__global__ void prep_queries_kernel(const float *__restrict__ raw, int nq, int nq_pad, int dim, float *__restrict__ q_prep,
+                                    __nv_bfloat16 *__restrict__ qb, float *__restrict__ err_bound,
+                                    uint32_t *__restrict__ tau_g, int ksel, int *__restrict__ counters, int n_counters) {
     const int row = blockIdx.x;
     const int lane = threadIdx.x;  // 32 threads
+    if (row == 0 && lane < n_counters) counters[lane] = 0;
+    if (row < nq)
+        for (int j = lane; j < ksel; j += 32) tau_g[static_cast<size_t>(row) * ksel + j] = 0u;
+    const int c4 = dim >> 2;
+    uint2 *dst = reinterpret_cast<uint2 *>(qb + static_cast<size_t>(row) * dim);
+    if (row >= nq) {
+        for (int c = lane; c < c4; c += 32) dst[c] = make_uint2(0u, 0u);
+        return;
+    }
+    const float4 *s4 = reinterpret_cast<const float4 *>(raw + static_cast<size_t>(row) * dim);
     float ss = 0.0f;
-    for (int e = lane; e < dim; e += 32) {
-        const float x = row < nq ? q[static_cast<size_t>(row) * dim + e] : 0.0f;
-        const __nv_bfloat16 h = __float2bfloat16_rn(x);
-        qb[static_cast<size_t>(row) * dim + e] = h;
-        const float d = x - __bfloat162float(h);
-        ss = fmaf(d, d, ss);
+    for (int c = lane; c < c4; c += 32) {
+        const float4 v = s4[c];
+        ss = fmaf(v.x, v.x, ss);
+        ss = fmaf(v.y, v.y, ss);
+        ss = fmaf(v.z, v.z, ss);
+        ss = fmaf(v.w, v.w, ss);
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, s);
-    if (lane == 0 && row < nq) err_bound[row] = sqrtf(ss);
+    const float inv = 1.0f / (sqrtf(ss) + 1e-30f);
+    float4 *p4 = reinterpret_cast<float4 *>(q_prep + static_cast<size_t>(row) * dim);
+    float es = 0.0f;
+    for (int c = lane; c < c4; c += 32) {
+        float4 v = s4[c];
+        v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+        p4[c] = v;
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t *>(&lo);
+        o.y = *reinterpret_cast<const uint32_t *>(&hi);
+        dst[c] = o;
+        const float dx = v.x - __low2float(lo), dy = v.y - __high2float(lo);
+        const float dz = v.z - __low2float(hi), dw = v.w - __high2float(hi);
+        es = fmaf(dx, dx, es);
+        es = fmaf(dy, dy, es);
+        es = fmaf(dz, dz, es);
+        es = fmaf(dw, dw, es);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) es += __shfl_xor_sync(FULL_MASK, es, s);
+    if (lane == 0) err_bound[row] = sqrtf(es);
     (void)nq_pad;
 }
 
@@ -497,7 +496,7 @@ __global__ void prep_queries_kernel(const float *__restrict__ q, int nq, int nq_
 //                fixed threshold tau0[j].  A list that did not fill up holds EVERY row above tau0[j]; everything
 //                else scores at most tau0[j] + bound, so the query is certified iff its k-th exact score beats that.
 template <int KPL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restrict__ queries,
                const uint8_t *__restrict__ corpus, const int64_t *__restrict__ row_keys,
                const float *__restrict__ err_bound, int k, float *__restrict__ out_dist,
@@ -515,7 +514,8 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
     for (int i = threadIdx.x; i < 32 * KPL; i += blockDim.x) exact[i] = 0ull;
     __syncthreads();
     const uint64_t *s = sel + static_cast<size_t>(j_cta) * ksel;
-    for (int j = warp; j < ksel; j += 4) {
+    const int nwarps = blockDim.x >> 5;
+    for (int j = warp; j < ksel; j += nwarps) {
         const uint64_t key = s[j];
         if (key == 0ull) continue;  // warp-uniform
         const uint32_t row = key_row(key);
@@ -537,13 +537,19 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
     __syncthreads();
     if (warp != 0) return;
     WarpTopK<KPL> lst;
-    lst.clear();
     int n_valid = 0;
-    for (int j = 0; j < ksel; ++j) {
-        const uint64_t key = exact[j];
-        if (key == 0ull) continue;
-        ++n_valid;
-        lst.insert(key, 32 * KPL, lane);
+    if constexpr (KPL == 1) {  // 32 candidates: one key per lane, one bitonic sort
+        const uint64_t key = exact[lane];
+        n_valid = __popc(__ballot_sync(FULL_MASK, key != 0ull));
+        lst.e[0] = bitonic_sort32_desc(key, lane);
+    } else {
+        lst.clear();
+        for (int j = 0; j < ksel; ++j) {
+            const uint64_t key = exact[j];
+            if (key == 0ull) continue;
+            ++n_valid;
+            lst.insert(key, 32 * KPL, lane);
+        }
     }
     // certification: anything outside the candidate set scores at most (its selection-score ceiling + bound);
     // |c|_2 <= 1 + 2^-9 for a bf16-rounded unit row, 1e-5 (per 384 products) covers the fp32 accumulation
@@ -627,8 +633,11 @@ int scan_mma_ksel(int k) { return k <= 16 ? 32 : (k <= 32 ? 64 : (k <= 100 ? 128
 // queries served by one corpus pass: a single CTA per SM up to 128, CTA pairs (cta_group::2) above
 int scan_mma_group(int nq_total) { return nq_total <= mma::M_TILE ? mma::M_TILE : 2 * mma::M_TILE; }
 
-cudaError_t launch_prep_queries(const float *q, int nq, int nq_pad, int dim, void *qb, float *err_bound, cudaStream_t s) {
-    mma::prep_queries_kernel<<<nq_pad, 32, 0, s>>>(q, nq, nq_pad, dim, static_cast<__nv_bfloat16 *>(qb), err_bound);
+cudaError_t launch_prep_queries(const PrepArgs &a) {
+    if (a.dim % 4 != 0 || a.n_counters > 32) return cudaErrorInvalidValue;
+    mma::prep_queries_kernel<<<a.nq_pad, 32, 0, a.stream>>>(a.raw, a.nq, a.nq_pad, a.dim, a.q_prep,
+                                                           static_cast<__nv_bfloat16 *>(a.qb), a.err_bound, a.tau_g, a.ksel,
+                                                           a.counters, a.n_counters);
     count_launch();
     return cudaGetLastError();
 }
@@ -719,7 +728,7 @@ cudaError_t launch_rescore(const RescoreArgs &a) {
     if (a.B <= 0) return cudaSuccess;
     if (a.dim > mma::RESCORE_MAX_DIM || a.dim % 4 != 0) return cudaErrorInvalidValue;
 #define FR_RESCORE(KPL)                                                                                       \
-    mma::rescore_kernel<KPL><<<a.B, 128, 0, a.stream>>>(a.sel, a.ksel, a.queries, a.corpus, a.row_keys, a.err_bound, \
+    mma::rescore_kernel<KPL><<<a.B, 256, 0, a.stream>>>(a.sel, a.ksel, a.queries, a.corpus, a.row_keys, a.err_bound, \
                                                        a.k, a.out_dist, a.out_packed, a.out_keys, a.flags,       \
                                                        a.fail_count, a.fail_list, a.fail_total, a.kth_exact,     \
                                                        a.idx_list, a.limit, a.tau0, a.dim, a.fail_total2)
