@@ -7,7 +7,9 @@ loudly when the CUDA extension is missing.
 PARITY STATUS: **partially pinned**.  The arithmetic of the reference's path lives in the
 third-party wheel ``chromadb`` (``requirements.txt:21`` pins only ``chromadb>=0.5.4``; the shipped
 fixture was written by a 1.x Rust-core build) which is absent from ``/root/reference`` and from
-this image, and the reference has no test that asserts a search result.  What pins this oracle:
+this image, and the reference has no test that asserts a search result -- so for the ranked result
+list of the chromadb call itself this oracle is **parity unpinned** (neither a reference golden vector nor a
+runnable reference exists for it).  What IS pinned on the reference's own artefacts:
   * the 18 golden fp32 vectors in Chroma's WAL (``tests/golden/chroma_fixture.json``) and the
     known answers derived from them (SURVEY.md section 8c);
   * the 18 distinct fused scores in ``test_logs/query_trace_*.json`` (``tests/golden/rrf_traces.json``),

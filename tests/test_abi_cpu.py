@@ -113,3 +113,24 @@ def test_id_to_key_mapping():
 
     assert [canonical_space(x) for x in ("cos", "Cosine", "euclidean", "l2", "ip", "inner_product", None, "zzz")] == \
         ["cosine", "cosine", "l2", "l2", "ip", "ip", "cosine", "cosine"]
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours) needs no GPU and must print exactly
+    one JSON line on stdout with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--rows", "300000",
+                        "--batch", "4", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
