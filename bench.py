@@ -359,6 +359,8 @@ def run_ours(args, out=sys.stdout):
     lo, hi = shard_bounds(n, world, rank, align=CHUNK_ROWS)
     ix = frb.ShardIndex(dim=DIM, space="cosine", dtype=args.dtype, device=local_rank, reserve_rows=hi - lo)
     ix.set_path(args.path)
+    if os.environ.get("FR_MMA_CO_GROUPS"):  # tuning experiments only
+        ix.set_option("mma_co_groups", int(os.environ["FR_MMA_CO_GROUPS"]))
     t0 = time.time()
     for c in range(lo // CHUNK_ROWS, (hi + CHUNK_ROWS - 1) // CHUNK_ROWS):
         r0 = c * CHUNK_ROWS

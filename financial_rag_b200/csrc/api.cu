@@ -165,7 +165,9 @@ struct fr_index {
                             // too when the swapped-operand kernel K2s serves them (it out-streams K1: TMA ring)
     int mma_small_max = 64;  // K2s serves batches up to this size (0 = never)
     int mma_debug = 0;      // diagnostics (scripts/ablate_mma.py): results are wrong when non-zero
-    int mma_co_groups = 2;  // K2: query groups of 256 that share one corpus stream through L2
+    int mma_co_groups = 4;  // K2: query groups of 256 that share one corpus stream through L2 (measured at 100M rows,
+                            // batch 1024: 1 -> 2 groups +9 % QPS, 2 -> 4 another +1.5 %; the board is power-bound and
+                            // every HBM byte not fetched is clock for the tensor cores)
     DevBuf stats;           // [0] queries K2 could not certify (re-scanned by the stream kernel), cumulative
     int64_t n_searches = 0, n_queries = 0, n_mma_queries = 0;
     PinBuf pin;
