@@ -208,7 +208,8 @@ def roofline_of(batch, path, k, rows_local, elem, scan_ms, scan_launches, search
         "peak": tf_sustained if tensor_bound else hbm_peak,
         "unit": "TFLOP/s" if tensor_bound else "GB/s",
         "frac": (tfs / tf_sustained) if tensor_bound else (gbs / hbm_peak),
-        "traffic": ncu_traffic(kind + ("_co2" if kind == "mma_cg2" and q_per_launch > MMA_GROUP else ""), rows_local),
+        "traffic": ncu_traffic(kind + (f"_co{int(round(q_per_launch / MMA_GROUP))}"
+                                       if kind == "mma_cg2" and q_per_launch > MMA_GROUP else ""), rows_local),
         "peak_kind": (f"{peak_kind} (MEASURED_PEAKS.json bf16_tflops_sustained: the kernel runs inside a long step; "
                       f"burst {tf_burst})" if tensor_bound else f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)"),
         "kernel": kernel,

@@ -164,6 +164,8 @@ struct fr_index {
     int mma_min_batch = 2;  // FR_PATH_AUTO: batches at least this large go to the tensor-core scans; smaller ones
                             // too when the swapped-operand kernel K2s serves them (it out-streams K1: TMA ring)
     int mma_small_max = 64;  // K2s serves batches up to this size (0 = never)
+    int mma_split = -1;      // K2s reads the queries as two bf16 terms: 1 always, 0 never, -1 up to mma_split_max queries
+    int mma_split_max = 32;  // (measured: free up to 32 queries -- one MMA of N = 2 x 32 per K step; 64 do not fit an accumulator)
     int mma_debug = 0;      // diagnostics (scripts/ablate_mma.py): results are wrong when non-zero
     int mma_co_groups = 4;  // K2: query groups of 256 that share one corpus stream through L2 (measured at 100M rows,
                             // batch 1024: 1 -> 2 groups +9 % QPS, 2 -> 4 another +1.5 %; the board is power-bound and
@@ -285,12 +287,24 @@ struct ProfScope {
 
 // The tensor-core scans serve bf16 cosine collections: K2 and K2s at width 384, K2s alone (small batches, larger
 // ones in slices) at width 768 -- the multi-vector store's bert-base token vectors (multivector_store.py:70).
+// K2s reads the queries as ONE bf16 term (selection error up to |q - bf16(q)|, ~1e-3) or as TWO (hi + lo, error
+// ~1e-5: nearly every query certified at once even where thousands of rows score within 1e-2 of the best).
+int small_split(const fr_index *ix, int B, int ksel) {
+    // two terms while they fit one MMA per K step (measured: no cost at all, profiles/r01_sweep_split_10m.jsonl);
+    // always at widths without a second-chance pass (certify in the first)
+    const bool want = ix->dim != 384 || ix->mma_split == 1 || (ix->mma_split < 0 && B <= ix->mma_split_max);
+    return (want && fr::scan_mma_small_nq(B, ksel, ix->dim, 1) != 0) ? 1 : 0;
+}
+bool small_serves(const fr_index *ix, int B, int ksel) {
+    if (ix->mma_small_max <= 0 || B > ix->mma_small_max) return false;
+    return fr::scan_mma_small_nq(B, ksel, ix->dim, small_split(ix, B, ksel)) != 0;
+}
 int mma_slice(const fr_index *ix, int k) {  // 0 = not eligible, else the largest batch one pass may take
     const int ksel = fr::scan_mma_ksel(k);
     if (ix->dtype != FR_BF16 || ix->metric != FR_COSINE || ksel == 0 || ix->rows <= 0) return 0;
     if (ix->dim == 384) return 1 << 30;
     if (ix->dim != 768) return 0;  // the re-scan safety net exists for 384 and 768 only
-    const int m = fr::scan_mma_small_max_batch(ksel, ix->dim);
+    const int m = fr::scan_mma_small_max_batch(ksel, ix->dim, 1);
     return m < ix->mma_small_max ? m : ix->mma_small_max;
 }
 bool mma_eligible(const fr_index *ix, int k) { return mma_slice(ix, k) > 0; }
@@ -337,25 +351,31 @@ int search_stream(fr_index *ix, const float *q, int B, int k, float *d_out_dist,
 }
 
 // K2 path: tensor-core selection of k' candidates per query, exact fp32-query rescoring with
-// certification, and a device-side re-scan of whatever could not be certified.
+// certification, a second tensor-core pass for what could not be certified, and a device-side re-scan
+// of whatever is still open after that.
 int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_out_dist, uint64_t *d_out_packed,
                int64_t *d_out_keys, cudaStream_t s) {
     const int ksel = fr::scan_mma_ksel(k);
     const int group = fr::scan_mma_group(B);
     const int nq_pad = ((B + group - 1) / group) * group;
     // small batches take the swapped-operand kernel (tensor work proportional to the batch)
-    const bool small = ix->mma_small_max > 0 && B <= ix->mma_small_max && fr::scan_mma_small_nq(B, ksel, ix->dim) != 0;
+    const bool small = small_serves(ix, B, ksel);
+    const int split = small ? small_split(ix, B, ksel) : 0;
     if (!small && ix->dim != 384) return fail(FR_EUNSUP, "internal: width %d needs the small-batch kernel", ix->dim);
     const bool second_chance = ix->dim == 384;  // the second-chance pass runs on K2, which is 384-wide
     const fr::MmaPlan plan = fr::scan_mma_plan(ix->sm_count, ix->rows, B, ix->mma_co_groups);
     const int grid = plan.lists_max;  // partial lists per query (at most)
-    FR_CUDA(ix->q_bf16.need(static_cast<size_t>(nq_pad) * ix->dim * 2));
-    FR_CUDA(ix->err_bound.need(static_cast<size_t>(B) * sizeof(float)));
+    // second-chance blocks: R queries each, enough of them for every query of the call
+    const int R = fr::scan_mma_retry_max();
+    const int slices = second_chance ? (B + R - 1) / R : 0;
+    FR_CUDA(ix->q_bf16.need(static_cast<size_t>(nq_pad) * ix->dim * 2 * (1 + split)));
+    FR_CUDA(ix->err_bound.need(4 * static_cast<size_t>(B) * sizeof(float)));  // |e| one-term | two-term | |e.q| one-term | two-term
     FR_CUDA(ix->partials.need(static_cast<size_t>(grid) * B * ksel * sizeof(uint64_t)));
     FR_CUDA(ix->sel.need(static_cast<size_t>(B) * ksel * sizeof(uint64_t)));
     FR_CUDA(ix->sel_keys.need(static_cast<size_t>(B) * ksel * sizeof(int64_t)));
     FR_CUDA(ix->flags.need(static_cast<size_t>(B)));
-    FR_CUDA(ix->fail.need((4 + 2 * static_cast<size_t>(B)) * sizeof(int)));  // 3 counters | fail_list | fail_list2
+    // 2 counters (+2 pad) | fail_list [B] | fail_list2 [B] | retry_n [slices]
+    FR_CUDA(ix->fail.need((4 + 2 * static_cast<size_t>(B) + static_cast<size_t>(slices)) * sizeof(int)));
     FR_CUDA(ix->tau.need(static_cast<size_t>(B) * ksel * sizeof(uint32_t)));
     FR_CUDA(ix->q_prep.need(static_cast<size_t>(B) * ix->dim * sizeof(float)));
     if (!ix->stats.p) {
@@ -364,8 +384,9 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     }
     ix->n_mma_queries += B;
     int *counters = static_cast<int *>(ix->fail.p);
-    int *fail_count = counters, *retry_n = counters + 1, *fail_count2 = counters + 2;
-    int *fail_list = counters + 4, *fail_list2 = fail_list + B;
+    int *fail_count = counters, *fail_count2 = counters + 1;
+    int *fail_list = counters + 4, *fail_list2 = fail_list + B, *retry_n = fail_list2 + B;
+    float *eb_one = static_cast<float *>(ix->err_bound.p), *eb_two = eb_one + B, *ea_one = eb_two + B, *ea_two = ea_one + B;
     // one launch: cosine normalisation (K0's arithmetic), bf16 copy, error bounds, and the reset of this call's
     // threshold slots and failure counters
     fr::PrepArgs pa{};
@@ -375,11 +396,15 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     pa.dim = ix->dim;
     pa.q_prep = static_cast<float *>(ix->q_prep.p);
     pa.qb = ix->q_bf16.p;
-    pa.err_bound = static_cast<float *>(ix->err_bound.p);
+    pa.err_bound = eb_one;
+    pa.err_bound_split = eb_two;
+    pa.err_alpha = ea_one;
+    pa.err_alpha_split = ea_two;
+    pa.split = split;
     pa.tau_g = static_cast<uint32_t *>(ix->tau.p);
     pa.ksel = ksel;
     pa.counters = counters;
-    pa.n_counters = 3;
+    pa.n_counters = 2;
     pa.stream = s;
     FR_CUDA(fr::launch_prep_queries(pa));
     const float *q = pa.q_prep;
@@ -389,6 +414,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     ms.dim = ix->dim;
     ms.keys_or_null = ix->n_deleted > 0 ? ix->keys : nullptr;
     ms.queries_bf16 = ix->q_bf16.p;
+    ms.split = split;
     ms.nq_pad = nq_pad;
     ms.n_rows = ix->rows;
     ms.nq_total = B;
@@ -402,7 +428,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     int rc = prof.begin();
     if (rc != FR_OK) return rc;
     if (small)
-        FR_CUDA(fr::launch_scan_mma_small(ms));
+        FR_CUDA(fr::launch_scan_mma_small(ms, 0, B));
     else
         FR_CUDA(fr::launch_scan_mma(ms));
     rc = prof.end();
@@ -428,18 +454,6 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
         FR_CUDA(fr::launch_merge_topk(ma));
     }
 
-    // second-chance buffers: one more query block of RETRY_MAX queries
-    const int R = fr::scan_mma_retry_max();
-    const int ksel_r = fr::scan_mma_retry_ksel(ksel);
-    const fr::MmaPlan rplan = fr::scan_mma_plan(ix->sm_count, ix->rows, R, 1);
-    FR_CUDA(ix->kth_exact.need(static_cast<size_t>(B) * sizeof(float)));
-    FR_CUDA(ix->r_q.need(static_cast<size_t>(R) * ix->dim * 2));
-    FR_CUDA(ix->r_misc.need(static_cast<size_t>(R) * sizeof(float)));
-    FR_CUDA(ix->r_tau.need(static_cast<size_t>(R) * ksel_r * sizeof(uint32_t)));
-    FR_CUDA(ix->r_partials.need(static_cast<size_t>(rplan.lists_max) * R * ksel_r * sizeof(uint64_t)));
-    FR_CUDA(ix->r_sel.need(static_cast<size_t>(R) * ksel_r * sizeof(uint64_t)));
-    FR_CUDA(ix->r_sel_keys.need(static_cast<size_t>(R) * ksel_r * sizeof(int64_t)));
-    float *tau0 = static_cast<float *>(ix->r_misc.p);
     unsigned long long *stat_uncertified = static_cast<unsigned long long *>(ix->stats.p);
     unsigned long long *stat_rescanned = stat_uncertified + 1;
 
@@ -451,7 +465,9 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     ra.dim = ix->dim;
     ra.corpus = ix->corpus;
     ra.row_keys = ix->keys;
-    ra.err_bound = static_cast<const float *>(ix->err_bound.p);
+    ra.err_bound = split ? eb_two : eb_one;
+    ra.err_alpha = split ? ea_two : ea_one;
+    ra.split = split;
     ra.B = B;
     ra.k = k;
     ra.out_dist = d_out_dist;
@@ -462,71 +478,89 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     ra.fail_list = second_chance ? fail_list : fail_list2;
     ra.fail_total = stat_uncertified;
     ra.fail_total2 = second_chance ? nullptr : stat_rescanned;
+    FR_CUDA(ix->kth_exact.need(static_cast<size_t>(B) * sizeof(float)));
     ra.kth_exact = static_cast<float *>(ix->kth_exact.p);
     ra.stream = s;
     FR_CUDA(fr::launch_rescore(ra));
 
     if (second_chance) {
-        // second chance on the tensor cores for what could not be certified (all four launches return at once
-        // when nothing failed): gather -> scan above a fixed threshold -> merge -> rescore
+        // second chance on the tensor cores for what could not be certified: gather the failures into blocks of
+        // R queries, then per block scan above a fixed threshold -> merge -> rescore.  Everything is enqueued
+        // unconditionally; the launches of a block nobody failed into return at once (no host round trip).
+        const int ksel_r = fr::scan_mma_retry_ksel(ksel);
+        const fr::MmaPlan rplan = fr::scan_mma_plan(ix->sm_count, ix->rows, R, 1);
+        const size_t slots = static_cast<size_t>(slices) * R;
+        FR_CUDA(ix->r_q.need(slots * ix->dim * 2));
+        FR_CUDA(ix->r_misc.need(slots * sizeof(float)));
+        FR_CUDA(ix->r_tau.need(slots * ksel_r * sizeof(uint32_t)));
+        FR_CUDA(ix->r_partials.need(static_cast<size_t>(rplan.lists_max) * R * ksel_r * sizeof(uint64_t)));  // reused by every block
+        FR_CUDA(ix->r_sel.need(static_cast<size_t>(R) * ksel_r * sizeof(uint64_t)));
+        FR_CUDA(ix->r_sel_keys.need(static_cast<size_t>(R) * ksel_r * sizeof(int64_t)));
+        float *tau0 = static_cast<float *>(ix->r_misc.p);
+
         fr::RetryPrepArgs rp{};
         rp.queries = q;
-        rp.err_bound = ra.err_bound;
+        rp.err_bound = eb_one;  // the second-chance scan reads one-term bf16 queries
+        rp.err_alpha = ea_one;
         rp.kth_exact = ra.kth_exact;
         rp.fail_count = fail_count;
         rp.fail_list = fail_list;
+        rp.slices = slices;
         rp.qb_retry = ix->r_q.p;
         rp.tau0 = tau0;
         rp.retry_n = retry_n;
         rp.tau_g_retry = static_cast<uint32_t *>(ix->r_tau.p);
         rp.ksel = ksel_r;
-        rp.fail_count2 = fail_count2;
-        rp.fail_list2 = fail_list2;
         rp.flags = ra.flags;
-        rp.rescan_total = stat_rescanned;
         rp.stream = s;
         FR_CUDA(fr::launch_retry_prep(rp));
 
-        fr::MmaScanArgs rs = ms;
-        rs.queries_bf16 = ix->r_q.p;
-        rs.nq_pad = R;
-        rs.nq_total = R;
-        rs.ksel = ksel_r;
-        rs.partials = static_cast<uint64_t *>(ix->r_partials.p);
-        rs.plan = rplan;
-        rs.tau_g = rp.tau_g_retry;
-        rs.nq_dev = retry_n;
-        rs.tau0 = tau0;
-        FR_CUDA(fr::launch_scan_mma(rs));
+        for (int sl = 0; sl < slices; ++sl) {
+            fr::MmaScanArgs rs = ms;
+            rs.queries_bf16 = static_cast<const uint8_t *>(ix->r_q.p) + static_cast<size_t>(sl) * R * ix->dim * 2;
+            rs.split = 0;
+            rs.nq_pad = R;
+            rs.nq_total = R;
+            rs.ksel = ksel_r;
+            rs.partials = static_cast<uint64_t *>(ix->r_partials.p);
+            rs.plan = rplan;
+            rs.tau_g = rp.tau_g_retry + static_cast<size_t>(sl) * ksel_r * R;
+            rs.nq_dev = retry_n + sl;
+            rs.tau0 = tau0 + static_cast<size_t>(sl) * R;
+            FR_CUDA(fr::launch_scan_mma(rs));
 
-        fr::MergeArgs mr{};
-        mr.packed = rs.partials;
-        mr.P = rplan.lists;
-        mr.shard_stride = static_cast<int64_t>(R) * ksel_r;
-        mr.B = R;
-        mr.k = ksel_r;
-        mr.shards = false;
-        mr.row_keys = ix->keys;
-        mr.l2 = false;
-        mr.out_packed = static_cast<uint64_t *>(ix->r_sel.p);
-        mr.out_keys = static_cast<int64_t *>(ix->r_sel_keys.p);
-        mr.limit = retry_n;
-        mr.stream = s;
-        FR_CUDA(fr::launch_merge_topk(mr));
+            fr::MergeArgs mr{};
+            mr.packed = rs.partials;
+            mr.P = rplan.lists;
+            mr.shard_stride = static_cast<int64_t>(R) * ksel_r;
+            mr.B = R;
+            mr.k = ksel_r;
+            mr.shards = false;
+            mr.row_keys = ix->keys;
+            mr.l2 = false;
+            mr.out_packed = static_cast<uint64_t *>(ix->r_sel.p);
+            mr.out_keys = static_cast<int64_t *>(ix->r_sel_keys.p);
+            mr.limit = retry_n + sl;
+            mr.stream = s;
+            FR_CUDA(fr::launch_merge_topk(mr));
 
-        fr::RescoreArgs rr = ra;
-        rr.sel = static_cast<const uint64_t *>(ix->r_sel.p);
-        rr.ksel = ksel_r;
-        rr.B = R;
-        rr.fail_count = fail_count2;
-        rr.fail_list = fail_list2;
-        rr.fail_total = stat_rescanned;
-        rr.fail_total2 = nullptr;
-        rr.kth_exact = nullptr;
-        rr.idx_list = fail_list;
-        rr.limit = retry_n;
-        rr.tau0 = tau0;
-        FR_CUDA(fr::launch_rescore(rr));
+            fr::RescoreArgs rr = ra;
+            rr.sel = static_cast<const uint64_t *>(ix->r_sel.p);
+            rr.ksel = ksel_r;
+            rr.err_bound = eb_one;
+            rr.err_alpha = ea_one;
+            rr.split = 0;
+            rr.B = R;
+            rr.fail_count = fail_count2;
+            rr.fail_list = fail_list2;
+            rr.fail_total = stat_rescanned;
+            rr.fail_total2 = nullptr;
+            rr.kth_exact = nullptr;
+            rr.idx_list = fail_list + static_cast<size_t>(sl) * R;
+            rr.limit = retry_n + sl;
+            rr.tau0 = rs.tau0;
+            FR_CUDA(fr::launch_rescore(rr));
+        }
     }
 
     // safety net: both launches return immediately when every query was certified
@@ -595,8 +629,7 @@ int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *
                     "FR_PATH_MMA serves bf16 cosine collections of width 384 (k <= 100) or 768 (k <= 32) with at least one row "
                     "(this one: dtype %d, dim %d, metric %d, k %d, rows %lld)",
                     ix->dtype, ix->dim, ix->metric, k, (long long)ix->rows);
-    const bool k2s = ix->mma_small_max > 0 && B <= ix->mma_small_max &&
-                     fr::scan_mma_small_nq(B, fr::scan_mma_ksel(k), ix->dim) != 0;
+    const bool k2s = eligible && small_serves(ix, B, fr::scan_mma_ksel(k));
     const bool use_mma = eligible && (ix->path == FR_PATH_MMA || (ix->path == FR_PATH_AUTO && (B >= ix->mma_min_batch || k2s)));
     if (use_mma) return search_mma(ix, d_queries, B, k, d_out_dist, d_out_packed, d_out_keys, s);
     const size_t qbytes = static_cast<size_t>(B) * ix->dim * sizeof(float);
@@ -716,6 +749,16 @@ int fr_index_set_option(fr_index *ix, const char *name, int64_t value) {
     if (std::strcmp(name, "mma_co_groups") == 0) {
         if (value < 1 || value > 8) return fail(FR_EINVAL, "mma_co_groups must be in [1, 8]");
         ix->mma_co_groups = static_cast<int>(value);
+        return FR_OK;
+    }
+    if (std::strcmp(name, "mma_split") == 0) {
+        if (value < -1 || value > 1) return fail(FR_EINVAL, "mma_split must be -1 (auto), 0 or 1");
+        ix->mma_split = static_cast<int>(value);
+        return FR_OK;
+    }
+    if (std::strcmp(name, "mma_split_max") == 0) {
+        if (value < 0 || value > 64) return fail(FR_EINVAL, "mma_split_max must be in [0, 64]");
+        ix->mma_split_max = static_cast<int>(value);
         return FR_OK;
     }
     if (std::strcmp(name, "mma_small_max") == 0) {

@@ -50,7 +50,8 @@ struct MmaScanArgs {
     const void *corpus;         // [rows][dim] bf16
     int dim;                    // 384 for K2; K2s takes any multiple of 64 up to 1024
     const int64_t *keys_or_null;
-    const void *queries_bf16;   // [nq_pad][384] bf16, nq_pad multiple of scan_mma_group(), zero padded
+    const void *queries_bf16;   // [nq_pad][dim * (1 + split)] bf16, zero padded (K2: nq_pad multiple of scan_mma_group())
+    int split;                  // K2s only: every query row holds bf16(q) followed by bf16(q - bf16(q))
     int nq_pad;
     int64_t n_rows;
     int nq_total;
@@ -71,8 +72,12 @@ struct PrepArgs {
     const float *raw;   // [nq][dim] raw fp32 queries
     int nq, nq_pad, dim;
     float *q_prep;      // [nq][dim] out: cosine-normalised fp32 queries (same arithmetic as K0)
-    void *qb;           // [nq_pad][dim] out: bf16 copy, zero padded
+    void *qb;           // [nq_pad][dim * (1 + split)] out: bf16 copy, zero padded; split: followed by bf16(q - bf16(q))
     float *err_bound;   // [nq] out: |q - bf16(q)|_2
+    float *err_bound_split;  // [nq] out (split only): |q - bf16(q) - bf16(q - bf16(q))|_2
+    float *err_alpha;        // [nq] out: |(q - bf16(q)) . q|
+    float *err_alpha_split;  // [nq] out (split only): the same for the two-term residual
+    int split;
     uint32_t *tau_g;    // nq * ksel threshold slots, zeroed here
     int ksel;
     int *counters;      // n_counters ints zeroed here (failure counters of the call)
@@ -81,11 +86,11 @@ struct PrepArgs {
 };
 cudaError_t launch_prep_queries(const PrepArgs &a);
 cudaError_t launch_scan_mma(const MmaScanArgs &a);
-// K2s (scan_mma_small.cu): operands swapped for 2..64 queries, k' <= 64.  Uses plan.lists CTAs, one launch,
-// queries_bf16 padded to scan_mma_small_nq() rows; writes partials [plan.lists][nq_total][ksel].
-int scan_mma_small_nq(int nq_total, int ksel, int dim);  // padded query count (16/32/64), 0 = not served
-int scan_mma_small_max_batch(int ksel, int dim);         // largest batch one K2s launch serves (0 = none)
-cudaError_t launch_scan_mma_small(const MmaScanArgs &a);
+// K2s (scan_mma_small.cu): operands swapped for 1..64 queries, k' <= 64.  Uses plan.lists CTAs per launch;
+// writes partials [plan.lists][nq_total][ksel] for queries [q0, q0 + nq).
+int scan_mma_small_nq(int nq, int ksel, int dim, int split);  // padded query count (16/32/64), 0 = not served
+int scan_mma_small_max_batch(int ksel, int dim, int split);   // largest batch one K2s launch serves (0 = none)
+cudaError_t launch_scan_mma_small(const MmaScanArgs &a, int q0, int nq);
 
 struct RescoreArgs {
     const uint64_t *sel;  // [B][ksel] selection lists (K3 output, packed)
@@ -94,7 +99,9 @@ struct RescoreArgs {
     int dim;
     const uint8_t *corpus;
     const int64_t *row_keys;
-    const float *err_bound;  // [B] |q - bf16(q)|_2
+    const float *err_bound;  // [B] |e|_2, e = q - (what the scan read)
+    const float *err_alpha;  // [B] |e . q|
+    int split;               // the scan read two bf16 terms per query: twice the products in the accumulation slack
     int B, k;
     float *out_dist;       // [B][k] or null
     uint64_t *out_packed;  // [B][k] or null
@@ -112,22 +119,23 @@ struct RescoreArgs {
 };
 cudaError_t launch_rescore(const RescoreArgs &a);
 
-// Gathers the uncertified queries of the first pass into the second-chance query block (scan_mma.cu).
+// Gathers the uncertified queries of the first pass into second-chance query blocks of scan_mma_retry_max()
+// queries each (scan_mma.cu): `slices` blocks hold every query that can fail, block s serves the failures
+// [s * RETRY_MAX, (s + 1) * RETRY_MAX) and learns its live count from retry_n[s].
 struct RetryPrepArgs {
     const float *queries;     // [B][384] fp32 prepared queries
-    const float *err_bound;   // [B]
+    const float *err_bound;   // [B] |q - bf16(q)|_2 (the second-chance scan reads plain bf16 queries)
+    const float *err_alpha;   // [B] |(q - bf16(q)) . q|
     const float *kth_exact;   // [B]
     const int *fail_count;    // first-pass failures
     const int *fail_list;
-    void *qb_retry;           // [RETRY_MAX][384] bf16 out
-    float *tau0;              // [RETRY_MAX] out
-    int *retry_n;             // out: min(*fail_count, RETRY_MAX)
-    uint32_t *tau_g_retry;    // [ksel][RETRY_MAX] zeroed here
+    int slices;               // ceil(B / RETRY_MAX)
+    void *qb_retry;           // [slices * RETRY_MAX][384] bf16 out
+    float *tau0;              // [slices * RETRY_MAX] out
+    int *retry_n;             // [slices] out: live queries of each block
+    uint32_t *tau_g_retry;    // [slices][ksel][RETRY_MAX], the live slices zeroed here
     int ksel;
-    int *fail_count2;         // failures that did not fit the block are appended here (pre-zeroed by the caller)
-    int *fail_list2;
     uint8_t *flags;
-    unsigned long long *rescan_total;  // += failures that did not fit the block
     cudaStream_t stream;
 };
 int scan_mma_retry_max();

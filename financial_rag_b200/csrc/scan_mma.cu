@@ -216,7 +216,9 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             for (int64_t t = pair; t < num_tiles; t += npairs) {
-                const int row0 = static_cast<int>(t * TILE_ROWS) + static_cast<int>(rank) * N_TILE;
+                // diagnostics: dbg & 8 = every stream re-reads the same 64 tiles (L2-resident): no HBM traffic, same L2->SM traffic
+                const int64_t tt = (dbg & 8) ? (t & 63) : t;
+                const int row0 = static_cast<int>(tt * TILE_ROWS) + static_cast<int>(rank) * N_TILE;
 #pragma unroll 1
                 for (int kc = 0; kc < K_CHUNKS; ++kc) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -438,16 +440,20 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 // One warp per query row.
 __global__ void prep_queries_kernel(const float *__restrict__ raw, int nq, int nq_pad, int dim, float *__restrict__ q_prep,
                                     __nv_bfloat16 *__restrict__ qb, float *__restrict__ err_bound,
-                                    uint32_t *__restrict__ tau_g, int ksel, int *__restrict__ counters, int n_counters) {
+                                    float *__restrict__ err_bound_split, float *__restrict__ err_alpha,
+                                    float *__restrict__ err_alpha_split, int split, uint32_t *__restrict__ tau_g, int ksel,
+                                    int *__restrict__ counters, int n_counters) {
     const int row = blockIdx.x;
     const int lane = threadIdx.x;  // 32 threads
     if (row == 0 && lane < n_counters) counters[lane] = 0;
     if (row < nq)
         for (int j = lane; j < ksel; j += 32) tau_g[static_cast<size_t>(row) * ksel + j] = 0u;
     const int c4 = dim >> 2;
-    uint2 *dst = reinterpret_cast<uint2 *>(qb + static_cast<size_t>(row) * dim);
+    // split: the row holds bf16(q) in columns [0, dim) and bf16(q - bf16(q)) in [dim, 2 dim)
+    uint2 *dst = reinterpret_cast<uint2 *>(qb + static_cast<size_t>(row) * dim * (1 + split));
+    uint2 *dst_lo = dst + c4;
     if (row >= nq) {
-        for (int c = lane; c < c4; c += 32) dst[c] = make_uint2(0u, 0u);
+        for (int c = lane; c < c4 * (1 + split); c += 32) dst[c] = make_uint2(0u, 0u);
         return;
     }
     const float4 *s4 = reinterpret_cast<const float4 *>(raw + static_cast<size_t>(row) * dim);
@@ -463,7 +469,7 @@ __global__ void prep_queries_kernel(const float *__restrict__ raw, int nq, int n
     for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, s);
     const float inv = 1.0f / (sqrtf(ss) + 1e-30f);
     float4 *p4 = reinterpret_cast<float4 *>(q_prep + static_cast<size_t>(row) * dim);
-    float es = 0.0f;
+    float es = 0.0f, es2 = 0.0f, al = 0.0f, al2 = 0.0f;  // |e|^2 and e . q of the one-term / two-term residual e
     for (int c = lane; c < c4; c += 32) {
         float4 v = s4[c];
         v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
@@ -480,11 +486,60 @@ __global__ void prep_queries_kernel(const float *__restrict__ raw, int nq, int n
         es = fmaf(dy, dy, es);
         es = fmaf(dz, dz, es);
         es = fmaf(dw, dw, es);
+        al = fmaf(dx, v.x, al);
+        al = fmaf(dy, v.y, al);
+        al = fmaf(dz, v.z, al);
+        al = fmaf(dw, v.w, al);
+        if (split) {  // second bf16 term of the query: what the first one lost (exact differences above)
+            const __nv_bfloat162 lo2 = __floats2bfloat162_rn(dx, dy);
+            const __nv_bfloat162 hi2 = __floats2bfloat162_rn(dz, dw);
+            o.x = *reinterpret_cast<const uint32_t *>(&lo2);
+            o.y = *reinterpret_cast<const uint32_t *>(&hi2);
+            dst_lo[c] = o;
+            const float ex = dx - __low2float(lo2), ey = dy - __high2float(lo2);
+            const float ez = dz - __low2float(hi2), ew = dw - __high2float(hi2);
+            es2 = fmaf(ex, ex, es2);
+            es2 = fmaf(ey, ey, es2);
+            es2 = fmaf(ez, ez, es2);
+            es2 = fmaf(ew, ew, es2);
+            al2 = fmaf(ex, v.x, al2);
+            al2 = fmaf(ey, v.y, al2);
+            al2 = fmaf(ez, v.z, al2);
+            al2 = fmaf(ew, v.w, al2);
+        }
     }
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) es += __shfl_xor_sync(FULL_MASK, es, s);
-    if (lane == 0) err_bound[row] = sqrtf(es);
+    for (int s = 16; s > 0; s >>= 1) {
+        es += __shfl_xor_sync(FULL_MASK, es, s);
+        es2 += __shfl_xor_sync(FULL_MASK, es2, s);
+        al += __shfl_xor_sync(FULL_MASK, al, s);
+        al2 += __shfl_xor_sync(FULL_MASK, al2, s);
+    }
+    if (lane == 0) {
+        err_bound[row] = sqrtf(es);
+        err_alpha[row] = fabsf(al);
+        if (split) {
+            err_bound_split[row] = sqrtf(es2);
+            err_alpha_split[row] = fabsf(al2);
+        }
+    }
     (void)nq_pad;
+}
+
+// ---------------------------------------------------------------------------------------------
+// How far the selection score of a row (the score of the bf16 query terms the tensor cores read) can fall below
+// its exact fp32-query score s, for any stored row c (|c| <= L: a bf16-rounded unit vector) with s >= t.
+// With e = q - (what the scan read), |q| = 1 and c = s q + c_perp:   e . c = (e . q) s + e_perp . c_perp,
+// |c_perp|^2 = |c|^2 - s^2.  So  selection >= s - |e . q| s - |e| sqrt(L^2 - s^2)  as well as the plain
+// Cauchy-Schwarz  selection >= s - |e| L;  both right-hand sides grow with s, so every row whose exact score
+// reaches t > 0 has a selection score of at least  t - selection_error_bound(t).  For the high scores of real
+// embedding neighbourhoods (t ~ 0.6 ... 0.95) the second form is 0.8 ... 0.3 of the first.
+__device__ __forceinline__ float selection_error_bound(float t, float e_norm, float e_dot_q) {
+    constexpr float L = 1.004f;
+    const float plain = e_norm * L;
+    if (!(t > 0.0f)) return plain;
+    const float perp = sqrtf(fmaxf(L * L - t * t, 0.0f));
+    return fminf(plain, e_dot_q * 1.001f * t + e_norm * perp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -499,11 +554,11 @@ template <int KPL>
 __global__ void __launch_bounds__(256)
 rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restrict__ queries,
                const uint8_t *__restrict__ corpus, const int64_t *__restrict__ row_keys,
-               const float *__restrict__ err_bound, int k, float *__restrict__ out_dist,
+               const float *__restrict__ err_bound, const float *__restrict__ err_alpha, int k, float *__restrict__ out_dist,
                uint64_t *__restrict__ out_packed, int64_t *__restrict__ out_keys, uint8_t *__restrict__ flags,
                int *__restrict__ fail_count, int *__restrict__ fail_list, unsigned long long *__restrict__ fail_total,
                float *__restrict__ kth_exact_out, const int *__restrict__ idx_list, const int *__restrict__ limit,
-               const float *__restrict__ tau0, int dim, unsigned long long *__restrict__ fail_total2) {
+               const float *__restrict__ tau0, int dim, unsigned long long *__restrict__ fail_total2, float acc_slack) {
     __shared__ float sq[RESCORE_MAX_DIM];
     __shared__ uint64_t exact[32 * KPL];
     const int j_cta = blockIdx.x;
@@ -551,16 +606,18 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
             lst.insert(key, 32 * KPL, lane);
         }
     }
-    // certification: anything outside the candidate set scores at most (its selection-score ceiling + bound);
-    // |c|_2 <= 1 + 2^-9 for a bf16-rounded unit row, 1e-5 (per 384 products) covers the fp32 accumulation
-    const float bound = err_bound[b] * 1.004f + 1e-5f * static_cast<float>((dim + 383) / 384);
+    // certification: a row outside the candidate set has a selection score <= ceiling (the k'-th selection score of
+    // a full list, or the fixed threshold of a second-chance list); had its exact score reached the k-th exact score
+    // found here, its selection score would be above (k-th exact) - selection_error_bound.  acc_slack (1e-5 per 384
+    // products) covers the fp32 accumulation orders of the two kernels.
     const uint64_t last_sel = s[ksel - 1];
     const float kth_exact = n_valid >= k ? key_score(lst.kth(k)) : -INFINITY;
+    const float floor_sel = kth_exact - selection_error_bound(kth_exact, err_bound[b], err_alpha[b]) - acc_slack;
     bool certified = true;
     if (last_sel != 0ull) {                       // list full: ceiling = the k'-th selection score
-        certified = n_valid >= k && kth_exact > key_score(last_sel) + bound;
+        certified = n_valid >= k && floor_sel > key_score(last_sel);
     } else if (tau0 != nullptr) {                 // not full, but only rows above tau0 were collected
-        certified = n_valid >= k && kth_exact > tau0[j_cta] + bound;
+        certified = n_valid >= k && floor_sel > tau0[j_cta];
     }                                             // not full and no threshold: every live row is a candidate
 #pragma unroll
     for (int j = 0; j < KPL; ++j) {
@@ -597,29 +654,30 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
 // one more query block and scanned again by the same tensor-core kernel with the threshold FIXED at T from
 // the first tile on and a longer list (scan_mma_retry_ksel): the list then holds every row above T unless it
 // overflows, which is exactly what the second rescore pass certifies.  Only what still fails (or did not fit the block) goes to the stream kernel.
-// One CTA per retry slot.
+// One CTA per retry slot; slot j belongs to slice j / RETRY_MAX, which is one more launch of the scan kernel
+// (its own query block, thresholds and live count retry_n[slice]; an empty slice's launches exit at once).
 __global__ void retry_prep_kernel(const float *__restrict__ queries, const float *__restrict__ err_bound,
-                                  const float *__restrict__ kth_exact, const int *__restrict__ fail_count,
+                                  const float *__restrict__ err_alpha, const float *__restrict__ kth_exact, const int *__restrict__ fail_count,
                                   const int *__restrict__ fail_list, __nv_bfloat16 *__restrict__ qb_retry,
                                   float *__restrict__ tau0, int *__restrict__ retry_n, uint32_t *__restrict__ tau_g_retry,
-                                  int ksel, int *__restrict__ fail_count2, int *__restrict__ fail_list2,
-                                  uint8_t *__restrict__ flags, unsigned long long *__restrict__ rescan_total) {
-    const int j = blockIdx.x;  // retry slot, < RETRY_MAX
+                                  int ksel, uint8_t *__restrict__ flags) {
+    const int j = blockIdx.x;  // retry slot
+    const int slice = j / RETRY_MAX, jj = j % RETRY_MAX;
     const int lane = threadIdx.x;
     const int nf = *fail_count;
-    const int n = nf < RETRY_MAX ? nf : RETRY_MAX;
-    if (j == 0 && lane == 0) {
-        *retry_n = n;
-        for (int f = RETRY_MAX; f < nf; ++f) fail_list2[atomicAdd(fail_count2, 1)] = fail_list[f];  // no room: stream kernel
-        if (nf > RETRY_MAX && rescan_total) atomicAdd(rescan_total, static_cast<unsigned long long>(nf - RETRY_MAX));
+    if (jj == 0 && lane == 0) {
+        const int left = nf - slice * RETRY_MAX;
+        retry_n[slice] = left < 0 ? 0 : (left < RETRY_MAX ? left : RETRY_MAX);
     }
-    for (int g = lane; g < ksel; g += 32) tau_g_retry[static_cast<size_t>(g) * RETRY_MAX + j] = 0u;
-    const bool on = j < n;
+    if (slice * RETRY_MAX >= nf) return;  // nothing of this slice will be read
+    uint32_t *tg = tau_g_retry + static_cast<size_t>(slice) * ksel * RETRY_MAX;  // [ksel][RETRY_MAX] per slice
+    for (int g = lane; g < ksel; g += 32) tg[static_cast<size_t>(g) * RETRY_MAX + jj] = 0u;
+    const bool on = j < nf;
     const int b = on ? fail_list[j] : 0;
     for (int e = lane; e < DIM; e += 32)
         qb_retry[static_cast<size_t>(j) * DIM + e] = __float2bfloat16_rn(on ? queries[static_cast<size_t>(b) * DIM + e] : 0.0f);
     if (lane == 0) {
-        tau0[j] = on ? kth_exact[b] - (err_bound[b] * 1.004f + 1e-5f) - 1e-5f : INFINITY;
+        tau0[j] = on ? kth_exact[b] - selection_error_bound(kth_exact[b], err_bound[b], err_alpha[b]) - 2e-5f : INFINITY;
         if (on) flags[b] = 1;  // stays flagged until the second rescore pass certifies it
     }
 }
@@ -636,7 +694,8 @@ int scan_mma_group(int nq_total) { return nq_total <= mma::M_TILE ? mma::M_TILE 
 cudaError_t launch_prep_queries(const PrepArgs &a) {
     if (a.dim % 4 != 0 || a.n_counters > 32) return cudaErrorInvalidValue;
     mma::prep_queries_kernel<<<a.nq_pad, 32, 0, a.stream>>>(a.raw, a.nq, a.nq_pad, a.dim, a.q_prep,
-                                                           static_cast<__nv_bfloat16 *>(a.qb), a.err_bound, a.tau_g, a.ksel,
+                                                           static_cast<__nv_bfloat16 *>(a.qb), a.err_bound, a.err_bound_split,
+                                                           a.err_alpha, a.err_alpha_split, a.split, a.tau_g, a.ksel,
                                                            a.counters, a.n_counters);
     count_launch();
     return cudaGetLastError();
@@ -729,9 +788,10 @@ cudaError_t launch_rescore(const RescoreArgs &a) {
     if (a.dim > mma::RESCORE_MAX_DIM || a.dim % 4 != 0) return cudaErrorInvalidValue;
 #define FR_RESCORE(KPL)                                                                                       \
     mma::rescore_kernel<KPL><<<a.B, 256, 0, a.stream>>>(a.sel, a.ksel, a.queries, a.corpus, a.row_keys, a.err_bound, \
-                                                       a.k, a.out_dist, a.out_packed, a.out_keys, a.flags,       \
+                                                       a.err_alpha, a.k, a.out_dist, a.out_packed, a.out_keys, a.flags, \
                                                        a.fail_count, a.fail_list, a.fail_total, a.kth_exact,     \
-                                                       a.idx_list, a.limit, a.tau0, a.dim, a.fail_total2)
+                                                       a.idx_list, a.limit, a.tau0, a.dim, a.fail_total2,        \
+                                                       1e-5f * static_cast<float>(((a.dim + 383) / 384) * (1 + a.split)))
     if (a.ksel <= 32) FR_RESCORE(1);
     else if (a.ksel <= 64) FR_RESCORE(2);
     else if (a.ksel <= 128) FR_RESCORE(4);
@@ -747,10 +807,10 @@ int scan_mma_retry_max() { return mma::RETRY_MAX; }
 int scan_mma_retry_ksel(int ksel) { return ksel >= 128 ? 256 : 128; }
 
 cudaError_t launch_retry_prep(const RetryPrepArgs &a) {
-    mma::retry_prep_kernel<<<mma::RETRY_MAX, 32, 0, a.stream>>>(a.queries, a.err_bound, a.kth_exact, a.fail_count,
-                                                              a.fail_list, static_cast<__nv_bfloat16 *>(a.qb_retry),
-                                                              a.tau0, a.retry_n, a.tau_g_retry, a.ksel, a.fail_count2,
-                                                              a.fail_list2, a.flags, a.rescan_total);
+    if (a.slices <= 0) return cudaSuccess;
+    mma::retry_prep_kernel<<<a.slices * mma::RETRY_MAX, 32, 0, a.stream>>>(a.queries, a.err_bound, a.err_alpha, a.kth_exact, a.fail_count,
+                                                                         a.fail_list, static_cast<__nv_bfloat16 *>(a.qb_retry),
+                                                                         a.tau0, a.retry_n, a.tau_g_retry, a.ksel, a.flags);
     count_launch();
     return cudaGetLastError();
 }

@@ -35,10 +35,12 @@ constexpr int S_TMEM_BUFS = 4;
 // bge-small / gte-small embeddings, 12 for 768-d bert-base token vectors of the multi-vector store), so the
 // offsets are computed, identically, on the host (launch size) and in the kernel.
 constexpr int S_MAX_STAGES = 8;
-template <int NQ, int KPL>
+template <int NQ, int KPL, int SPLIT>
 struct SmallPlan {
     static constexpr int CAP = 32 * KPL;
-    static constexpr size_t Q_CHUNK = size_t(NQ) * K_CHUNK * 2;                  // [NQ x 64] bf16
+    static constexpr int N_MMA = NQ * (1 + SPLIT);                               // operand rows: hi terms, then lo terms
+    static_assert(N_MMA <= 64, "an accumulator is 64 TMEM columns");
+    static constexpr size_t Q_CHUNK = size_t(N_MMA) * K_CHUNK * 2;               // [N_MMA x 64] bf16
     static constexpr size_t LIST_BYTES = size_t(4) * NQ * CAP * 8;               // [4 warps][NQ][CAP]
     static constexpr size_t STASH_BYTES = size_t(4) * NQ * 32 * 4;               // [4 warps][NQ][32 rows] fp32
     static_assert(Q_CHUNK % 1024 == 0, "query chunks must keep the 1024-byte swizzle alignment");
@@ -70,12 +72,24 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *r) {
 
 // grid = P CTAs (P = partial lists per query); CTA p takes corpus tiles p, p + P, ... of 128 rows.
 // partials: [P][nq_total][ksel].
-template <int NQ, int KPL>
+// SPLIT: the queries are read as TWO bf16 terms, q ~ hi + lo with lo = bf16(q - bf16(q)): the operand holds the NQ
+// hi rows followed by the NQ lo rows (one MMA of N = 2 NQ per K step, not two of N = NQ: the cost of an MMA here is
+// mostly per instruction), and the epilogue adds the two columns of a query.  Selection error ~1e-5 instead of ~1e-3.
+template <int NQ, int KPL, int SPLIT>
 __global__ void __launch_bounds__(S_THREADS, 1)
 scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                       const int64_t *__restrict__ keys_or_null, int64_t n_rows, int nq, int ksel,
-                      uint64_t *__restrict__ partials, int nq_total, uint32_t *__restrict__ tau_g, int k_chunks) {
-    using Plan = SmallPlan<NQ, KPL>;
+                      uint64_t *__restrict__ partials, int nq_total, uint32_t *__restrict__ tau_g, int k_chunks,
+                      int q0, const int *__restrict__ nq_dev) {
+    // q0: first query (row of the query block, index into partials / tau_g) this launch serves; with nq_dev the
+    // live count comes from the device (retry slices: *nq_dev queries in all, this slice takes [q0, q0 + nq))
+    if (nq_dev != nullptr) {
+        const int left = *nq_dev - q0;
+        nq = left < nq ? left : nq;
+        if (nq <= 0) return;  // every thread of every CTA takes the same branch
+    }
+    using Plan = SmallPlan<NQ, KPL, SPLIT>;
+    constexpr int N_MMA = Plan::N_MMA;
     const Plan plan(k_chunks);
     const int STAGES = plan.stages;
     constexpr int CAP = Plan::CAP;
@@ -129,8 +143,12 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         // ===================== TMA producer =====================
         if (lane == 0) {
             mbar_expect_tx(bar_qfull, static_cast<uint32_t>(plan.q_bytes));
-            for (int kc = 0; kc < k_chunks; ++kc)
-                tma_load_2d<1>(smem_u32(smem_q + kc * Plan::Q_CHUNK), &tmap_q, bar_qfull, kc * K_CHUNK, 0);
+            for (int kc = 0; kc < k_chunks; ++kc) {  // a query row: columns [0, dim) = bf16(q), [dim, 2 dim) = the lo term
+                tma_load_2d<1>(smem_u32(smem_q + kc * Plan::Q_CHUNK), &tmap_q, bar_qfull, kc * K_CHUNK, q0);
+                if (SPLIT)  // rows NQ .. 2 NQ - 1 of the operand (NQ * 128 B is a multiple of the 1024-byte swizzle atom)
+                    tma_load_2d<1>(smem_u32(smem_q + kc * Plan::Q_CHUNK + NQ * K_CHUNK * 2), &tmap_q, bar_qfull,
+                                   (k_chunks + kc) * K_CHUNK, q0);
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int64_t t = cta; t < num_tiles; t += ncta) {
@@ -150,7 +168,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     } else if (warp == 1) {
         // ===================== MMA issuer: D[128 rows x NQ] += corpus chunk * queries^T =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(TILE_ROWS_CTA, NQ);
+            constexpr uint32_t idesc = make_idesc_bf16(TILE_ROWS_CTA, N_MMA);
             mbar_wait(bar_qfull, 0);
             tc_fence_after();
             int stage = 0;
@@ -192,21 +210,23 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
         for (int q = 0; q < NQ; ++q) tau[q] = q < nq ? -INFINITY : INFINITY;  // padded queries never pass
         // shared thresholds (see scan_mma.cu): this CTA raises slot cta % k' of a query to the best score it holds
-        uint32_t *my_slots = tau_g + (cta % ksel);  // + q * ksel
+        uint32_t *my_slots = tau_g + static_cast<size_t>(q0) * ksel + (cta % ksel);  // + q * ksel
         uint32_t it = 0;
         for (int64_t t = cta; t < num_tiles; t += ncta, ++it) {
             const uint32_t buf = it % S_TMEM_BUFS;
             const uint32_t bphase = (it / S_TMEM_BUFS) & 1;
             // refresh from the other CTAs.  tau_g is laid out [query][k' slots] here, so the k' slots of a query
             // are one or two coalesced 128-byte reads for the warp (lane j reads slot j) and a warp min: one L2
-            // request per query instead of k' (the requests of all CTAs meet on the same few lines)
+            // request per query instead of k' (the requests of all CTAs meet on the same few lines).
+            // (Tried: a seventh warp polling the slots every 1.5 us and handing the thresholds over through shared
+            // memory -- 5-8 % slower at every batch size: the polling traffic costs more than the refresh.)
             if (it < 8u || (it & 7u) == 0u) {
                 uint32_t x[NQ];
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
                     x[q] = 0u;
                     if (q < nq) {  // warp-uniform
-                        const uint32_t *sp = tau_g + static_cast<size_t>(q) * ksel + lane;
+                        const uint32_t *sp = tau_g + static_cast<size_t>(q0 + q) * ksel + lane;
                         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(x[q]) : "l"(sp));
                         if (KPL == 2) {
                             uint32_t y;
@@ -225,10 +245,10 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             }
             mbar_wait(bar_tfull + 8 * buf, bphase);
             tc_fence_after();
-            uint32_t r[NQ];
+            uint32_t r[N_MMA];
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * S_ACC_STRIDE;
 #pragma unroll
-            for (int c = 0; c < NQ / 16; ++c) tmem_ld16_nowait(taddr + c * 16, r + c * 16);
+            for (int c = 0; c < N_MMA / 16; ++c) tmem_ld16_nowait(taddr + c * 16, r + c * 16);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             // the scores are in registers: hand the accumulator back before looking at them
             tc_fence_before();
@@ -236,16 +256,60 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
             float v[NQ];
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) v[q] = __uint_as_float(r[q]);
-            float m0 = v[0] - tau[0], m1 = v[1] - tau[1];
+            for (int q = 0; q < NQ; ++q) v[q] = SPLIT ? __uint_as_float(r[q]) + __uint_as_float(r[NQ + q]) : __uint_as_float(r[q]);
+            if (it == 0u) {
+                // first tile of this warp: every list is empty and every row would pass one by one (32 x NQ sorted
+                // inserts).  Load the lists in bulk instead: per query one 32-key bitonic sort of the tile's scores.
+                const uint32_t row = static_cast<uint32_t>(t * TILE_ROWS_CTA) + quarter * 32 + lane;
+                bool valid = row < n_rows;
+                if (valid && keys_or_null != nullptr) valid = keys_or_null[row] != KEY_TOMBSTONE;
 #pragma unroll
-            for (int q = 2; q < NQ; q += 2) {
-                m0 = fmaxf(m0, v[q] - tau[q]);
-                m1 = fmaxf(m1, v[q + 1] - tau[q + 1]);
+                for (int q = 0; q < NQ; ++q) my_stash[q * 32 + lane] = v[q];
+                __syncwarp();
+                for (int q = 0; q < nq; ++q) {
+                    uint64_t key = valid ? pack_key(my_stash[q * 32 + lane], row) : 0ull;
+                    key = bitonic_sort32_desc(key, lane);
+                    my_lists[q * CAP + lane] = key;  // entries 32 .. CAP-1 stay empty
+                    const uint32_t best = __shfl_sync(FULL_MASK, static_cast<uint32_t>(key >> 32), 0);
+                    if (KPL == 1) {  // a full list already gates
+                        const uint32_t last = __shfl_sync(FULL_MASK, static_cast<uint32_t>(key >> 32), 31);
+                        const float nt = last != 0u ? unorder_bits(last) : -INFINITY;
+                        switch (q) {
+#define FR_TAU_CASE(i) case i: tau[(i) < NQ ? (i) : 0] = fmaxf(tau[(i) < NQ ? (i) : 0], nt); break;
+#define FR_TAU_CASE8(b) FR_TAU_CASE(b) FR_TAU_CASE(b + 1) FR_TAU_CASE(b + 2) FR_TAU_CASE(b + 3) \
+                        FR_TAU_CASE(b + 4) FR_TAU_CASE(b + 5) FR_TAU_CASE(b + 6) FR_TAU_CASE(b + 7)
+                            FR_TAU_CASE8(0) FR_TAU_CASE8(8)
+                            FR_TAU_CASE8(16) FR_TAU_CASE8(24)
+                            FR_TAU_CASE8(32) FR_TAU_CASE8(40) FR_TAU_CASE8(48) FR_TAU_CASE8(56)
+#undef FR_TAU_CASE8
+#undef FR_TAU_CASE
+                            default: break;
+                        }
+                    }
+                    if (lane == 0 && best != 0u) atomicMax(my_slots + static_cast<size_t>(q) * ksel, best);
+                }
+                __syncwarp();
+                continue;
             }
-            if (!__any_sync(FULL_MASK, fmaxf(m0, m1) > 0.0f)) continue;  // the common case
+            // gate: per group of 16 queries, max_q (score_q - tau_q); two chains per group
+            constexpr int NG = NQ / 16;
+            float gm[NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                float m0 = v[g * 16] - tau[g * 16], m1 = v[g * 16 + 1] - tau[g * 16 + 1];
+#pragma unroll
+                for (int i = 2; i < 16; i += 2) {
+                    m0 = fmaxf(m0, v[g * 16 + i] - tau[g * 16 + i]);
+                    m1 = fmaxf(m1, v[g * 16 + i + 1] - tau[g * 16 + i + 1]);
+                }
+                gm[g] = fmaxf(m0, m1);
+            }
+            float mall = gm[0];
+#pragma unroll
+            for (int g = 1; g < NG; ++g) mall = fmaxf(mall, gm[g]);
+            if (!__any_sync(FULL_MASK, mall > 0.0f)) continue;  // the common case
             // ---- candidate path (one copy of the insert code whatever NQ: the queries with a passing row are
-            //      walked with a run-time index, so the scores go through shared memory) ----
+            //      walked with a run-time index, so the scores of the groups that hold one go through shared memory) ----
             const uint32_t row = static_cast<uint32_t>(t * TILE_ROWS_CTA) + quarter * 32 + lane;
             bool valid = row < n_rows;  // rows past the end arrive as zeros from TMA
             if (valid && keys_or_null != nullptr) valid = keys_or_null[row] != KEY_TOMBSTONE;
@@ -253,9 +317,14 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
             for (int h = 0; h < (NQ + 31) / 32; ++h) pm[h] = 0u;
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                my_stash[q * 32 + lane] = v[q];
-                pm[q / 32] |= (valid && v[q] > tau[q]) ? (1u << (q & 31)) : 0u;
+            for (int g = 0; g < NG; ++g) {
+                if (!__any_sync(FULL_MASK, gm[g] > 0.0f)) continue;  // warp-uniform: no row of the warp passes here
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int q = g * 16 + i;
+                    my_stash[q * 32 + lane] = v[q];
+                    pm[q / 32] |= (valid && v[q] > tau[q]) ? (1u << (q & 31)) : 0u;
+                }
             }
             __syncwarp();
 #pragma unroll
@@ -283,9 +352,18 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
                     for (int j = 0; j < KPL; ++j) lp[j * 32 + lane] = lst.e[j];
                     const float nt = key_threshold(lst.kth(CAP));
-#pragma unroll
-                    for (int qq = 0; qq < NQ; ++qq)  // tau lives in registers: predicated update of entry q
-                        tau[qq] = (qq == q) ? fmaxf(tau[qq], nt) : tau[qq];
+                    // tau lives in registers: a jump table of NQ one-line cases instead of NQ predicated updates
+                    switch (q) {
+#define FR_TAU_CASE(i) case i: tau[(i) < NQ ? (i) : 0] = fmaxf(tau[(i) < NQ ? (i) : 0], nt); break;
+#define FR_TAU_CASE8(b) FR_TAU_CASE(b) FR_TAU_CASE(b + 1) FR_TAU_CASE(b + 2) FR_TAU_CASE(b + 3) \
+                        FR_TAU_CASE(b + 4) FR_TAU_CASE(b + 5) FR_TAU_CASE(b + 6) FR_TAU_CASE(b + 7)
+                        FR_TAU_CASE8(0) FR_TAU_CASE8(8)
+                        FR_TAU_CASE8(16) FR_TAU_CASE8(24)
+                        FR_TAU_CASE8(32) FR_TAU_CASE8(40) FR_TAU_CASE8(48) FR_TAU_CASE8(56)
+#undef FR_TAU_CASE8
+#undef FR_TAU_CASE
+                        default: break;
+                    }
                     if (lane == 0) atomicMax(my_slots + static_cast<size_t>(q) * ksel, best);
                 }
             }
@@ -298,7 +376,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
             for (int j = 0; j < KPL; ++j) lst.e[j] = lists[static_cast<size_t>(q) * CAP + j * 32 + lane];
             for (int w = 1; w < 4; ++w) lst.merge_sorted(lists + (static_cast<size_t>(w) * NQ + q) * CAP, CAP, CAP, lane);
-            uint64_t *dst = partials + (static_cast<size_t>(cta) * nq_total + q) * ksel;
+            uint64_t *dst = partials + (static_cast<size_t>(cta) * nq_total + q0 + q) * ksel;
 #pragma unroll
             for (int j = 0; j < KPL; ++j) dst[j * 32 + lane] = lst.e[j];
         }
@@ -315,62 +393,76 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 }  // namespace mma
 
 namespace {
-template <int NQ, int KPL>
-cudaError_t launch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CUtensorMap &tc, int k_chunks, size_t *alloc_out) {
-    const mma::SmallPlan<NQ, KPL> plan(k_chunks);
+template <int NQ, int KPL, int SPLIT>
+cudaError_t launch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CUtensorMap &tc, int k_chunks, int nq, int q0,
+                         size_t *alloc_out) {
+    const mma::SmallPlan<NQ, KPL, SPLIT> plan(k_chunks);
     if (alloc_out) {  // planning only: does this instance fit, and with how deep a ring?
         *alloc_out = plan.stages >= mma::S_MIN_STAGES ? plan.alloc : 0;
         return cudaSuccess;
     }
     if (plan.stages < mma::S_MIN_STAGES) return cudaErrorInvalidValue;
-    auto kern = mma::scan_mma_small_kernel<NQ, KPL>;
+    auto kern = mma::scan_mma_small_kernel<NQ, KPL, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.alloc));
     if (e != cudaSuccess) return e;
-    kern<<<a.plan.lists, mma::S_THREADS, plan.alloc, a.stream>>>(tq, tc, a.keys_or_null, a.n_rows, a.nq_total, a.ksel,
-                                                                a.partials, a.nq_total, a.tau_g, k_chunks);
+    kern<<<a.plan.lists, mma::S_THREADS, plan.alloc, a.stream>>>(tq, tc, a.keys_or_null, a.n_rows, nq, a.ksel, a.partials,
+                                                                a.nq_total, a.tau_g, k_chunks, q0, a.nq_dev);
     count_launch();
     return cudaGetLastError();
 }
 
 cudaError_t dispatch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CUtensorMap &tc, int nq_pad, int ksel,
-                           int k_chunks, size_t *alloc_out) {
+                           int k_chunks, int split, int nq, int q0, size_t *alloc_out) {
     const bool k1 = ksel <= 32;
+#define FR_SMALL(NQ, KPL, SPLIT) launch_small<NQ, KPL, SPLIT>(a, tq, tc, k_chunks, nq, q0, alloc_out)
+    if (split) {
+        switch (nq_pad) {
+            case 16: return k1 ? FR_SMALL(16, 1, 1) : FR_SMALL(16, 2, 1);
+            case 32: return k1 ? FR_SMALL(32, 1, 1) : FR_SMALL(32, 2, 1);
+            default: return cudaErrorInvalidValue;  // 2 x 64 operand rows exceed an accumulator
+        }
+    }
     switch (nq_pad) {
-        case 16: return k1 ? launch_small<16, 1>(a, tq, tc, k_chunks, alloc_out) : launch_small<16, 2>(a, tq, tc, k_chunks, alloc_out);
-        case 32: return k1 ? launch_small<32, 1>(a, tq, tc, k_chunks, alloc_out) : launch_small<32, 2>(a, tq, tc, k_chunks, alloc_out);
-        case 64: return k1 ? launch_small<64, 1>(a, tq, tc, k_chunks, alloc_out) : launch_small<64, 2>(a, tq, tc, k_chunks, alloc_out);
+        case 16: return k1 ? FR_SMALL(16, 1, 0) : FR_SMALL(16, 2, 0);
+        case 32: return k1 ? FR_SMALL(32, 1, 0) : FR_SMALL(32, 2, 0);
+        case 64: return k1 ? FR_SMALL(64, 1, 0) : FR_SMALL(64, 2, 0);
         default: return cudaErrorInvalidValue;
     }
+#undef FR_SMALL
 }
 }  // namespace
 
-// Padded query count (16 / 32 / 64) of the instance that serves `nq_total` queries of width `dim` with k' = ksel,
-// 0 when none fits (too many queries for the shared memory left beside a ring of at least S_MIN_STAGES stages).
-int scan_mma_small_nq(int nq_total, int ksel, int dim) {
-    if (nq_total < 1 || nq_total > 64 || ksel > 64 || dim < 64 || dim % 64 != 0 || dim > 1024) return 0;
-    const int nq_pad = nq_total <= 16 ? 16 : (nq_total <= 32 ? 32 : 64);
+// Padded query count (16 / 32 / 64) of the instance that serves `nq` queries of width `dim` with k' = ksel
+// (`split`: bf16 hi + lo halves of every query, twice the query block), 0 when none fits (too many queries for
+// the shared memory left beside a ring of at least S_MIN_STAGES stages).
+int scan_mma_small_nq(int nq, int ksel, int dim, int split) {
+    if (nq < 1 || nq > (split ? 32 : 64) || ksel > 64 || dim < 64 || dim % 64 != 0 || dim > 1024) return 0;
+    const int nq_pad = nq <= 16 ? 16 : (nq <= 32 ? 32 : 64);
     size_t alloc = 0;
     MmaScanArgs dummy{};
     CUtensorMap none{};
-    if (dispatch_small(dummy, none, none, nq_pad, ksel, dim / mma::K_CHUNK, &alloc) != cudaSuccess || alloc == 0) return 0;
+    if (dispatch_small(dummy, none, none, nq_pad, ksel, dim / mma::K_CHUNK, split, nq, 0, &alloc) != cudaSuccess || alloc == 0)
+        return 0;
     return nq_pad;
 }
 
-// largest batch one K2s launch can serve for this width and k' (0 = none)
-int scan_mma_small_max_batch(int ksel, int dim) {
+// largest batch one K2s launch can serve for this width, k' and query precision (0 = none)
+int scan_mma_small_max_batch(int ksel, int dim, int split) {
     for (int nq : {64, 32, 16})
-        if (scan_mma_small_nq(nq, ksel, dim) != 0) return nq;
+        if (scan_mma_small_nq(nq, ksel, dim, split) != 0) return nq;
     return 0;
 }
 
-cudaError_t launch_scan_mma_small(const MmaScanArgs &a) {
-    const int nq_pad = scan_mma_small_nq(a.nq_total, a.ksel, a.dim);
-    if (nq_pad == 0 || a.nq_pad < nq_pad) return cudaErrorInvalidValue;
+// One launch: queries [q0, q0 + nq) of the query block (a.nq_dev: of the *a.nq_dev live ones).  a.queries_bf16 is
+// [a.nq_pad rows][dim * (1 + a.split)] bf16.
+cudaError_t launch_scan_mma_small(const MmaScanArgs &a, int q0, int nq) {
+    const int nq_pad = scan_mma_small_nq(nq, a.ksel, a.dim, a.split);
+    if (nq_pad == 0 || a.nq_pad < q0 + nq_pad) return cudaErrorInvalidValue;
     CUtensorMap tq, tc;
-    if (!mma::make_row_major_map(&tq, a.queries_bf16, a.nq_pad, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, nq_pad, a.dim) ||
+    if (!mma::make_row_major_map(&tq, a.queries_bf16, a.nq_pad, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, nq_pad, a.dim * (1 + a.split)) ||
         !mma::make_row_major_map(&tc, a.corpus, a.n_rows, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, mma::TILE_ROWS_CTA, a.dim))
         return cudaErrorNotSupported;
-    return dispatch_small(a, tq, tc, nq_pad, a.ksel, a.dim / mma::K_CHUNK, nullptr);
+    return dispatch_small(a, tq, tc, nq_pad, a.ksel, a.dim / mma::K_CHUNK, a.split, nq, q0, nullptr);
 }
 
 }  // namespace fr

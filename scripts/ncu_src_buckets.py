@@ -1,13 +1,14 @@
 #!/usr/bin/env python3
 """Bucket the warp-stall samples of an ncu source page by basic block (runs of equal execution count).
 
-    python scripts/ncu_src_buckets.py gpurun_out/prof.ncu-rep [min_fraction]
+    python scripts/ncu_src_buckets.py gpurun_out/prof.ncu-rep [min_fraction] [launch_index]
 """
 import csv, subprocess, sys
 
 rep = sys.argv[1]
 thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.004
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+skip = ["--launch-skip", sys.argv[3], "--launch-count", "1"] if len(sys.argv) > 3 else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", *skip], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 h = next(i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r)
 hdr = rows[h]

@@ -606,9 +606,18 @@ def test_mma_second_chance_pass_resolves_crowded_neighbourhoods(frb):
     ix.set_path("stream")
     d_s, k_s = ix.search(queries, k)
     ix.set_path("mma")
+    ix.set_option("mma_split", 0)  # one-term bf16 queries: selection scores are off by up to ~1e-3
     d_m, k_m = ix.search(queries, k)
     assert ix.stat("mma_uncertified_queries") >= 2, "the crowd must defeat the first pass"
     assert ix.stat("mma_rescanned_queries") == 0, "the second-chance pass must certify it without a stream re-scan"
+    # two-term queries (hi + lo) rank the crowd almost exactly: certified in the first pass, same answer
+    before = ix.stat("mma_uncertified_queries")
+    ix.set_option("mma_split", 1)
+    d_2, k_2 = ix.search(queries, k)
+    assert ix.stat("mma_uncertified_queries") == before, "two-term selection must certify the crowd at once"
+    np.testing.assert_array_equal(k_2, k_m)
+    np.testing.assert_array_equal(d_2, d_m)
+    ix.set_option("mma_split", 0)
     assert_matches_oracle(d_m, keys_to_rows(k_m, KEY_BASE), queries, corpus, k, "cosine", "bf16",
                           stored=stored_rows(ix), label="mma second chance")
     np.testing.assert_allclose(d_m, d_s, rtol=0, atol=2e-6)
@@ -622,6 +631,78 @@ def test_mma_second_chance_pass_resolves_crowded_neighbourhoods(frb):
     assert_matches_oracle(d_m, keys_to_rows(k_m, KEY_BASE), queries, corpus, 100, "cosine", "bf16",
                           stored=stored_rows(ix), label="mma second chance k=100")
     np.testing.assert_allclose(d_m, d_s, rtol=0, atol=2e-6)
+    ix.close()
+
+
+def make_clustered(n, centres, spread, seed):
+    """Rows = centre + spread * noise: hundreds of rows score within 1e-2 of a query's best hits, like the chunks of
+    one document family in a real collection (isotropic Gaussian rows never do)."""
+    rng = np.random.default_rng(seed)
+    c = rng.standard_normal((centres, 384), dtype=np.float32)
+    c /= np.linalg.norm(c, axis=1, keepdims=True)
+    which = rng.integers(0, centres, n)
+    rows = c[which] + spread / np.sqrt(384.0) * rng.standard_normal((n, 384), dtype=np.float32)
+    return rows.astype(np.float32), c
+
+
+@pytest.mark.parametrize("B", [1, 8, 16])
+def test_two_term_queries_certify_a_clustered_corpus_in_one_pass(frb, B):
+    """One tight cluster (cosine 0.99 to its centre) puts the k-th and k'-th scores of a query 1e-4 apart, less than
+    the one-term selection error even with the score-aware bound (|q - bf16(q)| sqrt(1 - t^2) ~ 1.7e-4): most
+    queries fail the first certification.  With the queries read as two bf16 terms (auto for small batches) the
+    selection error is ~1e-5 and every query is certified at once; both give the stream kernel's answer."""
+    n, k = 200000, 10
+    corpus, centres = make_clustered(n, 1, 0.1, seed=3100)
+    rng = np.random.default_rng(3101 + B)
+    queries = centres[rng.integers(0, 1, B)] + 0.1 / np.sqrt(384.0) * rng.standard_normal((B, 384), dtype=np.float32)
+    queries = queries.astype(np.float32)
+    ix = build_index(frb, corpus, "cosine", "bf16")
+    ix.set_path("stream")
+    d_s, k_s = ix.search(queries, k)
+    ix.set_path("mma")
+    ix.set_option("mma_split", 0)
+    d_1, k_1 = ix.search(queries, k)
+    fails_one_term = ix.stat("mma_uncertified_queries")
+    rescans_one_term = ix.stat("mma_rescanned_queries")  # a crowd this dense can overflow the 128 second-chance slots
+    ix.set_option("mma_split", -1)  # auto: two terms at these batch sizes
+    d_2, k_2 = ix.search(queries, k)
+    assert ix.stat("mma_uncertified_queries") == fails_one_term, "two-term selection left queries uncertified"
+    assert ix.stat("mma_rescanned_queries") == rescans_one_term
+    if B >= 8:
+        assert fails_one_term >= 1, "the corpus is meant to defeat the one-term certification"
+    np.testing.assert_array_equal(k_1, k_2)
+    np.testing.assert_allclose(d_1, d_2, rtol=0, atol=2e-6)  # re-scanned queries: the stream kernel's summation order
+    np.testing.assert_allclose(d_2, d_s, rtol=0, atol=2e-6)
+    mism = k_2 != k_s
+    if mism.any():
+        assert np.abs(d_2[mism] - d_s[mism]).max() <= 2e-6
+    assert_matches_oracle(d_2, keys_to_rows(k_2, KEY_BASE), queries, corpus, k, "cosine", "bf16", strict=False,
+                          stored=stored_rows(ix), label=f"clustered two-term B={B}")
+    ix.close()
+
+
+def test_second_chance_blocks_cover_every_failed_query(frb):
+    """A large batch on a clustered corpus fails the first certification for hundreds of queries -- more than one
+    second-chance block of 128 holds.  Every failure gets its tensor-core second chance (block after block); none
+    is left to the stream re-scan, and the answers equal the stream kernel's."""
+    n, B, k = 120000, 700, 10
+    corpus, centres = make_clustered(n, 40, 0.3, seed=3200)
+    rng = np.random.default_rng(3201)
+    queries = centres[rng.integers(0, 40, B)] + 0.3 / np.sqrt(384.0) * rng.standard_normal((B, 384), dtype=np.float32)
+    queries = queries.astype(np.float32)
+    ix = build_index(frb, corpus, "cosine", "bf16")
+    ix.set_path("stream")
+    d_s, k_s = ix.search(queries, k)
+    ix.set_path("mma")
+    d_m, k_m = ix.search(queries, k)
+    assert ix.stat("mma_uncertified_queries") > 128, "need more failures than one second-chance block holds"
+    assert ix.stat("mma_rescanned_queries") == 0
+    np.testing.assert_allclose(d_m, d_s, rtol=0, atol=2e-6)
+    mism = k_m != k_s
+    if mism.any():
+        assert np.abs(d_m[mism] - d_s[mism]).max() <= 2e-6
+    assert_matches_oracle(d_m[:40], keys_to_rows(k_m[:40], KEY_BASE), queries[:40], corpus, k, "cosine", "bf16",
+                          strict=False, stored=stored_rows(ix), label="second-chance blocks")
     ix.close()
 
 
