@@ -1,4 +1,4 @@
-// K2s scan_topk_mma_small -- the tensor-core scan for SMALL query batches (2 ... 64 queries), operands swapped.
+// K2s scan_topk_mma_small -- the tensor-core scan for SMALL query batches (1 ... 64 queries), operands swapped.
 //
 // Replaces the arithmetic behind chromadb Collection.query (parent_child/chroma_child_store.py:63,
 // parent_child/multivector_store.py:151) in the HBM-bound regime, where the scan must cost nothing but the
@@ -10,11 +10,13 @@
 // and the tensor work (and its energy) shrinks with the batch: 1/8 of K2's at 16 queries.
 //   * A = corpus tiles, streamed by TMA exactly as in K2 ([64 x 128] boxes, SWIZZLE_128B, K-major) through
 //     an mbarrier ring;  B = the query block, loaded once ([64 x NQ] boxes, six K-chunks);
-//   * accumulators: 4 x NQ TMEM columns; one TMEM lane = one corpus ROW, one column = one query;
+//   * accumulators: 4 x NQ TMEM columns; one TMEM lane = one corpus ROW, one column = one query
+//     (SPLIT: two columns, the bf16 hi and lo terms of the query, added in the epilogue -- see the kernel);
 //   * epilogue (4 warps, a thread per row): tcgen05.ld its NQ scores, release the accumulator at once, then
 //     max_q (score_q - tau_q) > 0 ?  -- NQ FADDs + NQ/2 FMNMX per row; only then the insert path: the queries
 //     with a passing row are walked one by one, a ballot over the 32 rows, warp-cooperative sorted insert into
-//     that warp's list for the query (shared memory), new threshold.  No score ever goes to HBM;
+//     that warp's list for the query (shared memory), new threshold.  A warp's first tile is loaded in bulk
+//     (one bitonic sort per query) instead of 32 x NQ single inserts.  No score ever goes to HBM;
 //   * thresholds are shared between CTAs through tau_g slots as in K2 (slot = stream % k'), laid out
 //     [query][slot] so a warp refreshes a query with one coalesced read and a warp-min;
 //   * at the end the four warps' lists of each query are merged and written to `partials` in K2's format, so

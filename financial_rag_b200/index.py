@@ -80,11 +80,12 @@ class ShardIndex:
         check(self._lib.fr_index_set_option(self._handle(), b"path", _PATHS[path]))
 
     def set_option(self, name: str, value: int) -> None:
-        """Tuning knobs of the C ABI: 'mma_min_batch', 'mma_co_groups', 'path', 'profile'."""
+        """Tuning knobs of the C ABI: 'mma_min_batch', 'mma_small_max', 'mma_co_groups', 'mma_split' (-1 auto, 0, 1),
+        'mma_split_max', 'path', 'profile'."""
         check(self._lib.fr_index_set_option(self._handle(), name.encode(), int(value)))
 
     def stat(self, name: str) -> int:
-        """'searches' | 'queries' | 'mma_queries' | 'mma_uncertified_queries' since creation."""
+        """'searches' | 'queries' | 'mma_queries' | 'mma_uncertified_queries' | 'mma_rescanned_queries' since creation."""
         out = ctypes.c_int64()
         check(self._lib.fr_index_get_stat(self._handle(), name.encode(), ctypes.byref(out)))
         return int(out.value)

@@ -73,9 +73,13 @@ int fr_index_reserve(fr_index *idx, int64_t rows);
 int fr_index_set_option(fr_index *idx, const char *name, int64_t value);
 
 /* Counters since creation (bench.py and tests report them): "searches", "queries", "mma_queries"
- * (queries served by the tensor-core scan) and "mma_uncertified_queries" (of those, the ones whose
- * bf16-query selection could not be certified against the fp32-query order and were re-scanned by
- * the streaming kernel inside the same call). */
+ * (queries served by the tensor-core scan), "mma_uncertified_queries" (of those, the ones whose
+ * bf16-query selection could not be certified against the fp32-query order in the first pass and took
+ * the second tensor-core pass) and "mma_rescanned_queries" (the ones still open after that, re-scanned
+ * by the streaming kernel inside the same call).
+ * Options (fr_index_set_option): "path" (FR_PATH_*), "profile", "mma_min_batch", "mma_small_max",
+ * "mma_co_groups", "mma_split" (-1 auto | 0 | 1: small batches read the queries as two bf16 terms),
+ * "mma_split_max". */
 int fr_index_get_stat(fr_index *idx, const char *name, int64_t *out);
 
 /* Replaces Collection.count()                     parent_child/chroma_child_store.py:76-80

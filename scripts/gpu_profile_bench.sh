@@ -15,7 +15,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'scan_|merge_
     --csv --log-file $OUT/launches_$TAG.csv $SHORT > $OUT/ncu_launch_$TAG.log 2>&1
 echo "launch list rc=$?"
 $SHORT > $OUT/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:scan_mma_kernel -s 6 -c 2 -o $OUT/prof_mma_bench_$TAG -f \
+# (the second-chance launches share the function name: select the CTA-pair instance of the first pass by its template arguments)
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'scan_mma_kernel<.int.1, .int.2' -s 6 -c 2 -o $OUT/prof_mma_bench_$TAG -f \
     $SHORT > $OUT/ncu_full_$TAG.log 2>&1
 echo "full capture rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:scan_mma_small -s 6 -c 2 -o $OUT/prof_mma_small_bench_$TAG -f \

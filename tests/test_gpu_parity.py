@@ -670,8 +670,10 @@ def test_two_term_queries_certify_a_clustered_corpus_in_one_pass(frb, B):
     assert ix.stat("mma_rescanned_queries") == rescans_one_term
     if B >= 8:
         assert fails_one_term >= 1, "the corpus is meant to defeat the one-term certification"
-    np.testing.assert_array_equal(k_1, k_2)
     np.testing.assert_allclose(d_1, d_2, rtol=0, atol=2e-6)  # re-scanned queries: the stream kernel's summation order
+    mism = k_1 != k_2
+    if mism.any():  # ... which may order two rows 1e-7 apart the other way round
+        assert np.abs(d_1[mism] - d_2[mism]).max() <= 2e-6 and mism.mean() < 0.05
     np.testing.assert_allclose(d_2, d_s, rtol=0, atol=2e-6)
     mism = k_2 != k_s
     if mism.any():
