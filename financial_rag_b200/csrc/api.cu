@@ -166,6 +166,8 @@ struct fr_index {
     int mma_small_max = 64;  // K2s serves batches up to this size (0 = never)
     int mma_split = -1;      // K2s reads the queries as two bf16 terms: 1 always, 0 never, -1 up to mma_split_max queries
     int mma_split_max = 32;  // (measured: free up to 32 queries -- one MMA of N = 2 x 32 per K step; 64 do not fit an accumulator)
+    int64_t small_rows_b1 = 2000000, small_rows_b4 = 200000;  // FR_PATH_AUTO: below these sizes batch 1 / batch <= 4 take K1
+    int mma_bound_scale_pct = 100;  // diagnostics / tests: certification error bounds x this / 100 (>= 100: stricter, still exact)
     int mma_debug = 0;      // diagnostics (scripts/ablate_mma.py): results are wrong when non-zero
     int mma_co_groups = 4;  // K2: query groups of 256 that share one corpus stream through L2 (measured at 100M rows,
                             // batch 1024: 1 -> 2 groups +9 % QPS, 2 -> 4 another +1.5 %; the board is power-bound and
@@ -178,6 +180,19 @@ struct fr_index {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // one pair per profiled search
     std::vector<cudaEvent_t> prof_pool;
     int64_t prof_launches = 0;
+    // host-path search graphs (small collections: the search is a chain of ~3-12 short kernels whose launch gaps,
+    // not their run time, set the latency): one captured graph per (B, k), replayed while nothing it baked in changed
+    struct SearchGraph {
+        cudaGraphExec_t exec = nullptr;
+        uint64_t state = 0;      // state_hash() the graph was captured under
+        uint64_t seen = 0;       // state_hash() after the last eager run of this shape (capture on the second stable call)
+        int64_t launches = 0, d_searches = 0, d_queries = 0, d_mma_queries = 0;
+        bool failed = false;     // capture did not work for this shape: stay eager
+    };
+    std::unordered_map<uint64_t, SearchGraph> graphs;
+    int use_graphs = 1;
+    int64_t graph_max_bytes = int64_t(2) << 30;  // corpora above this are bandwidth-bound: launch gaps do not matter
+    int64_t n_graph_replays = 0;
     std::unordered_map<int64_t, int64_t> keymap;  // key -> row (live rows only)
     bool keymap_valid = true;
 
@@ -401,6 +416,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     pa.err_alpha = ea_one;
     pa.err_alpha_split = ea_two;
     pa.split = split;
+    pa.bound_scale = static_cast<float>(ix->mma_bound_scale_pct) / 100.0f;
     pa.tau_g = static_cast<uint32_t *>(ix->tau.p);
     pa.ksel = ksel;
     pa.counters = counters;
@@ -630,7 +646,11 @@ int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *
                     "(this one: dtype %d, dim %d, metric %d, k %d, rows %lld)",
                     ix->dtype, ix->dim, ix->metric, k, (long long)ix->rows);
     const bool k2s = eligible && small_serves(ix, B, fr::scan_mma_ksel(k));
-    const bool use_mma = eligible && (ix->path == FR_PATH_MMA || (ix->path == FR_PATH_AUTO && (B >= ix->mma_min_batch || k2s)));
+    // small collections are launch-bound, not bandwidth-bound: K1 is 3 launches, the tensor-core path 11+
+    // (scripts/latency_small.py: batch 1 over 1M rows 148 vs 165 us, over 10k rows 25 vs 53 us)
+    const bool launch_bound = (B == 1 && ix->rows <= ix->small_rows_b1) || (B <= 4 && ix->rows <= ix->small_rows_b4);
+    const bool use_mma = eligible && (ix->path == FR_PATH_MMA ||
+                                      (ix->path == FR_PATH_AUTO && !launch_bound && (B >= ix->mma_min_batch || k2s)));
     if (use_mma) return search_mma(ix, d_queries, B, k, d_out_dist, d_out_packed, d_out_keys, s);
     const size_t qbytes = static_cast<size_t>(B) * ix->dim * sizeof(float);
     const float *q = d_queries;
@@ -650,6 +670,37 @@ int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *
         q = static_cast<const float *>(ix->q_prep.p);
     }
     return search_stream(ix, q, B, k, d_out_dist, d_out_packed, d_out_keys, s);
+}
+
+// Everything a captured search graph bakes in: array addresses, row counts, routing options.
+uint64_t state_hash(const fr_index *ix) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&h](uint64_t v) {
+        h ^= v;
+        h *= 1099511628211ull;
+    };
+    const DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist, &ix->out_keys, &ix->q_bf16,
+                            &ix->err_bound, &ix->sel, &ix->sel_keys, &ix->flags, &ix->fail, &ix->fb_partials, &ix->tau,
+                            &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau, &ix->r_partials, &ix->r_sel,
+                            &ix->r_sel_keys};
+    for (const DevBuf *b : bufs) mix(reinterpret_cast<uintptr_t>(b->p));
+    mix(reinterpret_cast<uintptr_t>(ix->pin.p));
+    mix(reinterpret_cast<uintptr_t>(ix->corpus));
+    mix(reinterpret_cast<uintptr_t>(ix->keys));
+    mix(static_cast<uint64_t>(ix->rows));
+    mix(ix->n_deleted > 0 ? 1u : 0u);
+    for (int v : {ix->path, ix->mma_min_batch, ix->mma_small_max, ix->mma_co_groups, ix->mma_split, ix->mma_split_max,
+                  ix->mma_debug, ix->mma_bound_scale_pct})
+        mix(static_cast<uint64_t>(static_cast<int64_t>(v)));
+    mix(static_cast<uint64_t>(ix->small_rows_b1));
+    mix(static_cast<uint64_t>(ix->small_rows_b4));
+    return h;
+}
+
+void drop_graphs(fr_index *ix) {
+    for (auto &kv : ix->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    ix->graphs.clear();
 }
 
 int check_search_args(fr_index *ix, const void *q, int B, int k, const void *o1, const void *o2) {
@@ -710,6 +761,7 @@ int fr_index_destroy(fr_index *ix) {
     {
         DeviceGuard g(ix->device);
         cudaDeviceSynchronize();
+        drop_graphs(ix);
         if (ix->corpus) cudaFree(ix->corpus);
         if (ix->keys) cudaFree(ix->keys);
         DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist,
@@ -749,6 +801,27 @@ int fr_index_set_option(fr_index *ix, const char *name, int64_t value) {
     if (std::strcmp(name, "mma_co_groups") == 0) {
         if (value < 1 || value > 8) return fail(FR_EINVAL, "mma_co_groups must be in [1, 8]");
         ix->mma_co_groups = static_cast<int>(value);
+        return FR_OK;
+    }
+    if (std::strcmp(name, "mma_bound_scale_pct") == 0) {
+        if (value < 100 || value > 100000) return fail(FR_EINVAL, "mma_bound_scale_pct must be in [100, 100000]");
+        ix->mma_bound_scale_pct = static_cast<int>(value);
+        return FR_OK;
+    }
+    if (std::strcmp(name, "use_graphs") == 0) {
+        ix->use_graphs = value != 0;
+        return FR_OK;
+    }
+    if (std::strcmp(name, "graph_max_bytes") == 0) {
+        ix->graph_max_bytes = value;
+        return FR_OK;
+    }
+    if (std::strcmp(name, "small_rows_b1") == 0) {
+        ix->small_rows_b1 = value;
+        return FR_OK;
+    }
+    if (std::strcmp(name, "small_rows_b4") == 0) {
+        ix->small_rows_b4 = value;
         return FR_OK;
     }
     if (std::strcmp(name, "mma_split") == 0) {
@@ -816,6 +889,10 @@ int fr_index_get_stat(fr_index *ix, const char *name, int64_t *out) {
     }
     if (std::strcmp(name, "mma_queries") == 0) {
         *out = ix->n_mma_queries;
+        return FR_OK;
+    }
+    if (std::strcmp(name, "graph_replays") == 0) {
+        *out = ix->n_graph_replays;
         return FR_OK;
     }
     const bool unc = std::strcmp(name, "mma_uncertified_queries") == 0;
@@ -1089,23 +1166,88 @@ int fr_index_search(fr_index *ix, const float *queries, int B, int k, float *out
     const size_t qb = static_cast<size_t>(B) * ix->dim * sizeof(float);
     const size_t db = static_cast<size_t>(B) * k * sizeof(float);
     const size_t kb = static_cast<size_t>(B) * k * sizeof(int64_t);
-    const size_t db_al = (db + 15) & ~static_cast<size_t>(15);
-    FR_CUDA(ix->pin.need(qb + db_al + kb));
+    const size_t db_al = (db + 15) & ~static_cast<size_t>(15), kb_al = (kb + 15) & ~static_cast<size_t>(15);
+    FR_CUDA(ix->pin.need(qb + db_al + kb_al));
     FR_CUDA(ix->q_raw.need(qb));
     FR_CUDA(ix->out_dist.need(db));
     FR_CUDA(ix->out_keys.need(kb));
+    uint8_t *pin = static_cast<uint8_t *>(ix->pin.p);
+    // every block 16-byte aligned: the kernels may read the queries as float4 straight from the pinned block
+    uint8_t *pin_keys = pin, *pin_dist = pin + kb_al, *pin_q = pin + kb_al + db_al;
+    // the whole call as it is enqueued on `s`: H2D of the queries, the search, D2H of the results
+    // Small batches of a cosine collection skip the three copy operations: the query-preparation kernel reads the
+    // pinned block directly (the only reader of the raw queries) and the last kernel of the chain writes its
+    // B x k results straight into it -- each copy node costs more than the kernels around it at this size.
+    const bool zero_copy = ix->metric == FR_COSINE && B <= 64;
+    auto enqueue = [&]() -> int {
+        if (zero_copy)
+            return search_on_stream(ix, reinterpret_cast<const float *>(pin_q), B, k, reinterpret_cast<float *>(pin_dist),
+                                    nullptr, reinterpret_cast<int64_t *>(pin_keys), s);
+        FR_CUDA(cudaMemcpyAsync(ix->q_raw.p, pin_q, qb, cudaMemcpyHostToDevice, s));
+        int r = search_on_stream(ix, static_cast<const float *>(ix->q_raw.p), B, k, static_cast<float *>(ix->out_dist.p),
+                                 nullptr, static_cast<int64_t *>(ix->out_keys.p), s);
+        if (r != FR_OK) return r;
+        FR_CUDA(cudaMemcpyAsync(pin_dist, ix->out_dist.p, db, cudaMemcpyDeviceToHost, s));
+        FR_CUDA(cudaMemcpyAsync(pin_keys, ix->out_keys.p, kb, cudaMemcpyDeviceToHost, s));
+        return FR_OK;
+    };
+    // Small collections: replay a captured graph of the call (same shape, nothing it baked in changed).  The first
+    // call of a shape runs eagerly (it sizes the scratch), the second is captured, later ones are replays.
+    const bool graphable = ix->use_graphs && !ix->profile && B <= 8192 &&
+                           static_cast<int64_t>(ix->rows) * static_cast<int64_t>(ix->row_bytes()) <= ix->graph_max_bytes;
+    fr_index::SearchGraph *sg = nullptr;
+    if (graphable) {
+        if (ix->graphs.size() > 64) drop_graphs(ix);
+        sg = &ix->graphs[(static_cast<uint64_t>(static_cast<uint32_t>(B)) << 32) | static_cast<uint32_t>(k)];
+        const uint64_t h = state_hash(ix);
+        if (sg->exec && sg->state != h) {
+            cudaGraphExecDestroy(sg->exec);
+            sg->exec = nullptr;
+        }
+        if (!sg->exec && !sg->failed && sg->seen == h) {  // second stable call of this shape: capture it
+            const int64_t l0 = fr_launch_count(), s0 = ix->n_searches, q0 = ix->n_queries, m0 = ix->n_mma_queries;
+            cudaGraph_t graph = nullptr;
+            bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+            if (ok) {
+                const int r = enqueue();
+                ok = cudaStreamEndCapture(s, &graph) == cudaSuccess && r == FR_OK && graph != nullptr;
+            }
+            // capture enqueues nothing: take back what the bookkeeping counted
+            sg->launches = fr_launch_count() - l0;
+            sg->d_searches = ix->n_searches - s0;
+            sg->d_queries = ix->n_queries - q0;
+            sg->d_mma_queries = ix->n_mma_queries - m0;
+            g_launches.fetch_sub(sg->launches, std::memory_order_relaxed);
+            ix->n_searches = s0;
+            ix->n_queries = q0;
+            ix->n_mma_queries = m0;
+            if (ok) ok = state_hash(ix) == h;  // the capture must not have moved any scratch
+            if (ok) ok = cudaGraphInstantiate(&sg->exec, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            if (!ok) {
+                cudaGetLastError();
+                sg->exec = nullptr;
+                sg->failed = true;
+            } else {
+                sg->state = h;
+            }
+        }
+    }
     rc = begin_use(ix, s);
     if (rc != FR_OK) return rc;
-    uint8_t *pin = static_cast<uint8_t *>(ix->pin.p);
-    // results first so the int64 block stays 8-byte aligned
-    uint8_t *pin_keys = pin, *pin_dist = pin + kb, *pin_q = pin + kb + db_al;
     std::memcpy(pin_q, queries, qb);
-    FR_CUDA(cudaMemcpyAsync(ix->q_raw.p, pin_q, qb, cudaMemcpyHostToDevice, s));
-    rc = search_on_stream(ix, static_cast<const float *>(ix->q_raw.p), B, k, static_cast<float *>(ix->out_dist.p),
-                          nullptr, static_cast<int64_t *>(ix->out_keys.p), s);
-    if (rc != FR_OK) return rc;
-    FR_CUDA(cudaMemcpyAsync(pin_dist, ix->out_dist.p, db, cudaMemcpyDeviceToHost, s));
-    FR_CUDA(cudaMemcpyAsync(pin_keys, ix->out_keys.p, kb, cudaMemcpyDeviceToHost, s));
+    if (sg && sg->exec) {
+        FR_CUDA(cudaGraphLaunch(sg->exec, s));
+        g_launches.fetch_add(sg->launches, std::memory_order_relaxed);
+        ix->n_searches += sg->d_searches;
+        ix->n_queries += sg->d_queries;
+        ix->n_mma_queries += sg->d_mma_queries;
+        ix->n_graph_replays += 1;
+    } else {
+        rc = enqueue();
+        if (rc != FR_OK) return rc;
+        if (sg) sg->seen = state_hash(ix);
+    }
     rc = end_use(ix, s);
     if (rc != FR_OK) return rc;
     FR_CUDA(cudaStreamSynchronize(s));
@@ -1113,7 +1255,6 @@ int fr_index_search(fr_index *ix, const float *queries, int B, int k, float *out
     std::memcpy(out_keys, pin_keys, kb);
     return FR_OK;
 }
-
 int fr_index_search_device(fr_index *ix, const float *d_queries, int B, int k, float *d_out_dist, int64_t *d_out_keys,
                            void *stream) {
     int rc = check_search_args(ix, d_queries, B, k, d_out_dist, d_out_keys);

@@ -80,6 +80,7 @@ struct PrepArgs {
     int split;
     uint32_t *tau_g;    // nq * ksel threshold slots, zeroed here
     int ksel;
+    float bound_scale;  // >= 1: inflates the error bounds (diagnostics: forces second-chance passes; never unsafe)
     int *counters;      // n_counters ints zeroed here (failure counters of the call)
     int n_counters;
     cudaStream_t stream;

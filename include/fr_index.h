@@ -79,7 +79,10 @@ int fr_index_set_option(fr_index *idx, const char *name, int64_t value);
  * by the streaming kernel inside the same call).
  * Options (fr_index_set_option): "path" (FR_PATH_*), "profile", "mma_min_batch", "mma_small_max",
  * "mma_co_groups", "mma_split" (-1 auto | 0 | 1: small batches read the queries as two bf16 terms),
- * "mma_split_max". */
+ * "mma_split_max", "use_graphs" (host search replays a captured CUDA graph on small collections; default 1),
+ * "graph_max_bytes", "small_rows_b1" / "small_rows_b4" (FR_PATH_AUTO: collections up to this many rows send
+ * batch 1 / batch <= 4 to the 3-launch streaming kernel), "mma_bound_scale_pct" (diagnostics: inflate the
+ * certification bounds).  Further stat: "graph_replays". */
 int fr_index_get_stat(fr_index *idx, const char *name, int64_t *out);
 
 /* Replaces Collection.count()                     parent_child/chroma_child_store.py:76-80
