@@ -28,7 +28,11 @@
 namespace fr {
 namespace mma {
 
-constexpr int S_THREADS = 192;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
+// warp 0 TMA, warp 1 MMA + TMEM alloc, then EW epilogue warps: 4 (one per TMEM lane quarter, all NQ queries each) for
+// 16 queries, 8 (two per quarter, NQ/2 queries each) above -- an epilogue warp is a serial, latency-bound instruction
+// stream (tcgen05.ld -> wait -> gate -> rare inserts) whose length grows with the queries it serves; at 32 and 64
+// queries four of them could not keep up with the corpus stream.
+__host__ __device__ constexpr int small_epilogue_warps(int nq) { return nq <= 16 ? 4 : 8; }
 constexpr int S_TMEM_COLS = 256; // 4 accumulators at a 64-column stride
 constexpr int S_ACC_STRIDE = 64;
 constexpr int S_TMEM_BUFS = 4;
@@ -43,8 +47,11 @@ struct SmallPlan {
     static constexpr int N_MMA = NQ * (1 + SPLIT);                               // operand rows: hi terms, then lo terms
     static_assert(N_MMA <= 64, "an accumulator is 64 TMEM columns");
     static constexpr size_t Q_CHUNK = size_t(N_MMA) * K_CHUNK * 2;               // [N_MMA x 64] bf16
-    static constexpr size_t LIST_BYTES = size_t(4) * NQ * CAP * 8;               // [4 warps][NQ][CAP]
-    static constexpr size_t STASH_BYTES = size_t(4) * NQ * 32 * 4;               // [4 warps][NQ][32 rows] fp32
+    static constexpr int EW = small_epilogue_warps(NQ);                          // epilogue warps
+    static constexpr int NQH = NQ * 4 / EW;                                      // queries per epilogue warp
+    static constexpr int THREADS = 64 + 32 * EW;
+    static constexpr size_t LIST_BYTES = size_t(EW) * NQH * CAP * 8;             // [EW warps][NQH][CAP]
+    static constexpr size_t STASH_BYTES = size_t(EW) * NQH * 32 * 4;             // [EW warps][NQH][32 rows] fp32
     static_assert(Q_CHUNK % 1024 == 0, "query chunks must keep the 1024-byte swizzle alignment");
     size_t q_bytes, ring_off, list_off, stash_off, bar_off, alloc;
     int stages;
@@ -78,7 +85,7 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *r) {
 // hi rows followed by the NQ lo rows (one MMA of N = 2 NQ per K step, not two of N = NQ: the cost of an MMA here is
 // mostly per instruction), and the epilogue adds the two columns of a query.  Selection error ~1e-5 instead of ~1e-3.
 template <int NQ, int KPL, int SPLIT>
-__global__ void __launch_bounds__(S_THREADS, 1)
+__global__ void __launch_bounds__(64 + 32 * small_epilogue_warps(NQ), 1)
 scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                       const int64_t *__restrict__ keys_or_null, int64_t n_rows, int nq, int ksel,
                       uint64_t *__restrict__ partials, int nq_total, uint32_t *__restrict__ tau_g, int k_chunks,
@@ -92,6 +99,8 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     }
     using Plan = SmallPlan<NQ, KPL, SPLIT>;
     constexpr int N_MMA = Plan::N_MMA;
+    constexpr int EW = Plan::EW;
+    constexpr int NQH = Plan::NQH;
     const Plan plan(k_chunks);
     const int STAGES = plan.stages;
     constexpr int CAP = Plan::CAP;
@@ -121,7 +130,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         }
         for (int b = 0; b < S_TMEM_BUFS; ++b) {
             mbar_init(bar_tfull + 8 * b, 1);
-            mbar_init(bar_tempty + 8 * b, 4);  // one arrival per epilogue warp
+            mbar_init(bar_tempty + 8 * b, EW);  // one arrival per epilogue warp
         }
         mbar_init(bar_qfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -133,7 +142,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < 4 * NQ * CAP; i += 128) lists[i] = 0ull;
+        for (int i = threadIdx.x - 64; i < EW * NQH * CAP; i += 32 * EW) lists[i] = 0ull;
     }
     tc_fence_before();
     __syncthreads();
@@ -206,13 +215,16 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     } else {
         // ===================== epilogue: one TMEM lane = one corpus row =====================
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access = rows [32 quarter, +32) of the tile
-        uint64_t *my_lists = lists + static_cast<size_t>(warp - 2) * NQ * CAP;  // [NQ][CAP], sorted descending
-        float *my_stash = reinterpret_cast<float *>(smem + plan.stash_off) + static_cast<size_t>(warp - 2) * NQ * 32;
-        float tau[NQ];
+        const int ew = warp - 2;       // epilogue warp index; warps ew and ew + 4 share a quarter and split the queries
+        const int qbase = (ew >> 2) * NQH;  // first query (of the launch's block) this warp serves
+        const int nqw = max(0, min(NQH, nq - qbase));  // live queries of this warp
+        uint64_t *my_lists = lists + static_cast<size_t>(ew) * NQH * CAP;  // [NQH][CAP], sorted descending
+        float *my_stash = reinterpret_cast<float *>(smem + plan.stash_off) + static_cast<size_t>(ew) * NQH * 32;
+        float tau[NQH];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) tau[q] = q < nq ? -INFINITY : INFINITY;  // padded queries never pass
+        for (int q = 0; q < NQH; ++q) tau[q] = q < nqw ? -INFINITY : INFINITY;  // padded queries never pass
         // shared thresholds (see scan_mma.cu): this CTA raises slot cta % k' of a query to the best score it holds
-        uint32_t *my_slots = tau_g + static_cast<size_t>(q0) * ksel + (cta % ksel);  // + q * ksel
+        uint32_t *my_slots = tau_g + static_cast<size_t>(q0 + qbase) * ksel + (cta % ksel);  // + q * ksel
         uint32_t it = 0;
         for (int64_t t = cta; t < num_tiles; t += ncta, ++it) {
             const uint32_t buf = it % S_TMEM_BUFS;
@@ -223,12 +235,12 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             // (Tried: a seventh warp polling the slots every 1.5 us and handing the thresholds over through shared
             // memory -- 5-8 % slower at every batch size: the polling traffic costs more than the refresh.)
             if (it < 8u || (it & 7u) == 0u) {
-                uint32_t x[NQ];
+                uint32_t x[NQH];
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) {
+                for (int q = 0; q < NQH; ++q) {
                     x[q] = 0u;
-                    if (q < nq) {  // warp-uniform
-                        const uint32_t *sp = tau_g + static_cast<size_t>(q0 + q) * ksel + lane;
+                    if (q < nqw) {  // warp-uniform
+                        const uint32_t *sp = tau_g + static_cast<size_t>(q0 + qbase + q) * ksel + lane;
                         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(x[q]) : "l"(sp));
                         if (KPL == 2) {
                             uint32_t y;
@@ -238,8 +250,8 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    if (q < nq) {
+                for (int q = 0; q < NQH; ++q) {
+                    if (q < nqw) {
                         const uint32_t m = __reduce_min_sync(FULL_MASK, x[q]);
                         if (m != 0u) tau[q] = fmaxf(tau[q], unorder_bits(m));
                     }
@@ -247,18 +259,22 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             }
             mbar_wait(bar_tfull + 8 * buf, bphase);
             tc_fence_after();
-            uint32_t r[N_MMA];
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * S_ACC_STRIDE;
+            uint32_t r[NQH * (1 + SPLIT)];  // this warp's queries: hi columns [qbase, +NQH), lo columns NQ further on
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * S_ACC_STRIDE + qbase;
 #pragma unroll
-            for (int c = 0; c < N_MMA / 16; ++c) tmem_ld16_nowait(taddr + c * 16, r + c * 16);
+            for (int c = 0; c < NQH / 16; ++c) tmem_ld16_nowait(taddr + c * 16, r + c * 16);
+            if (SPLIT) {
+#pragma unroll
+                for (int c = 0; c < NQH / 16; ++c) tmem_ld16_nowait(taddr + NQ + c * 16, r + NQH + c * 16);
+            }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             // the scores are in registers: hand the accumulator back before looking at them
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-            float v[NQ];
+            float v[NQH];
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) v[q] = SPLIT ? __uint_as_float(r[q]) + __uint_as_float(r[NQ + q]) : __uint_as_float(r[q]);
+            for (int q = 0; q < NQH; ++q) v[q] = SPLIT ? __uint_as_float(r[q]) + __uint_as_float(r[NQH + q]) : __uint_as_float(r[q]);
             if (it == 0u) {
                 // first tile of this warp: every list is empty and every row would pass one by one (32 x NQ sorted
                 // inserts).  Load the lists in bulk instead: per query one 32-key bitonic sort of the tile's scores.
@@ -266,9 +282,9 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 bool valid = row < n_rows;
                 if (valid && keys_or_null != nullptr) valid = keys_or_null[row] != KEY_TOMBSTONE;
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) my_stash[q * 32 + lane] = v[q];
+                for (int q = 0; q < NQH; ++q) my_stash[q * 32 + lane] = v[q];
                 __syncwarp();
-                for (int q = 0; q < nq; ++q) {
+                for (int q = 0; q < nqw; ++q) {
                     uint64_t key = valid ? pack_key(my_stash[q * 32 + lane], row) : 0ull;
                     key = bitonic_sort32_desc(key, lane);
                     my_lists[q * CAP + lane] = key;  // entries 32 .. CAP-1 stay empty
@@ -277,12 +293,11 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                         const uint32_t last = __shfl_sync(FULL_MASK, static_cast<uint32_t>(key >> 32), 31);
                         const float nt = last != 0u ? unorder_bits(last) : -INFINITY;
                         switch (q) {
-#define FR_TAU_CASE(i) case i: tau[(i) < NQ ? (i) : 0] = fmaxf(tau[(i) < NQ ? (i) : 0], nt); break;
+#define FR_TAU_CASE(i) case i: tau[(i) < NQH ? (i) : 0] = fmaxf(tau[(i) < NQH ? (i) : 0], nt); break;
 #define FR_TAU_CASE8(b) FR_TAU_CASE(b) FR_TAU_CASE(b + 1) FR_TAU_CASE(b + 2) FR_TAU_CASE(b + 3) \
                         FR_TAU_CASE(b + 4) FR_TAU_CASE(b + 5) FR_TAU_CASE(b + 6) FR_TAU_CASE(b + 7)
                             FR_TAU_CASE8(0) FR_TAU_CASE8(8)
                             FR_TAU_CASE8(16) FR_TAU_CASE8(24)
-                            FR_TAU_CASE8(32) FR_TAU_CASE8(40) FR_TAU_CASE8(48) FR_TAU_CASE8(56)
 #undef FR_TAU_CASE8
 #undef FR_TAU_CASE
                             default: break;
@@ -294,7 +309,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 continue;
             }
             // gate: per group of 16 queries, max_q (score_q - tau_q); two chains per group
-            constexpr int NG = NQ / 16;
+            constexpr int NG = NQH / 16;
             float gm[NG];
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
@@ -315,9 +330,8 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             const uint32_t row = static_cast<uint32_t>(t * TILE_ROWS_CTA) + quarter * 32 + lane;
             bool valid = row < n_rows;  // rows past the end arrive as zeros from TMA
             if (valid && keys_or_null != nullptr) valid = keys_or_null[row] != KEY_TOMBSTONE;
-            uint32_t pm[(NQ + 31) / 32];  // this row's passing queries
-#pragma unroll
-            for (int h = 0; h < (NQ + 31) / 32; ++h) pm[h] = 0u;
+            static_assert(NQH <= 32, "one mask word per epilogue warp");
+            uint32_t pm[1] = {0u};  // this row's passing queries
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
                 if (!__any_sync(FULL_MASK, gm[g] > 0.0f)) continue;  // warp-uniform: no row of the warp passes here
@@ -330,7 +344,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             }
             __syncwarp();
 #pragma unroll
-            for (int h = 0; h < (NQ + 31) / 32; ++h) {
+            for (int h = 0; h < 1; ++h) {
                 uint32_t qm = __reduce_or_sync(FULL_MASK, pm[h]);  // queries with at least one passing row
                 while (qm != 0u) {
                     const int qb = __ffs(qm) - 1;
@@ -356,12 +370,11 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     const float nt = key_threshold(lst.kth(CAP));
                     // tau lives in registers: a jump table of NQ one-line cases instead of NQ predicated updates
                     switch (q) {
-#define FR_TAU_CASE(i) case i: tau[(i) < NQ ? (i) : 0] = fmaxf(tau[(i) < NQ ? (i) : 0], nt); break;
+#define FR_TAU_CASE(i) case i: tau[(i) < NQH ? (i) : 0] = fmaxf(tau[(i) < NQH ? (i) : 0], nt); break;
 #define FR_TAU_CASE8(b) FR_TAU_CASE(b) FR_TAU_CASE(b + 1) FR_TAU_CASE(b + 2) FR_TAU_CASE(b + 3) \
                         FR_TAU_CASE(b + 4) FR_TAU_CASE(b + 5) FR_TAU_CASE(b + 6) FR_TAU_CASE(b + 7)
                         FR_TAU_CASE8(0) FR_TAU_CASE8(8)
                         FR_TAU_CASE8(16) FR_TAU_CASE8(24)
-                        FR_TAU_CASE8(32) FR_TAU_CASE8(40) FR_TAU_CASE8(48) FR_TAU_CASE8(56)
 #undef FR_TAU_CASE8
 #undef FR_TAU_CASE
                         default: break;
@@ -372,12 +385,13 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             __syncwarp();
         }
         // ---- merge the four warps' lists of each query, write the CTA's partial lists ----
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
-        for (int q = warp - 2; q < nq; q += 4) {
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");  // epilogue warps only
+        for (int q = ew; q < nq; q += EW) {
+            const int first = (q / NQH) * 4, ql = q % NQH;  // the four warps (one per lane quarter) that served query q
             WarpTopK<KPL> lst;
 #pragma unroll
-            for (int j = 0; j < KPL; ++j) lst.e[j] = lists[static_cast<size_t>(q) * CAP + j * 32 + lane];
-            for (int w = 1; w < 4; ++w) lst.merge_sorted(lists + (static_cast<size_t>(w) * NQ + q) * CAP, CAP, CAP, lane);
+            for (int j = 0; j < KPL; ++j) lst.e[j] = lists[(static_cast<size_t>(first) * NQH + ql) * CAP + j * 32 + lane];
+            for (int w = 1; w < 4; ++w) lst.merge_sorted(lists + (static_cast<size_t>(first + w) * NQH + ql) * CAP, CAP, CAP, lane);
             uint64_t *dst = partials + (static_cast<size_t>(cta) * nq_total + q0 + q) * ksel;
 #pragma unroll
             for (int j = 0; j < KPL; ++j) dst[j * 32 + lane] = lst.e[j];
@@ -407,7 +421,7 @@ cudaError_t launch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CUte
     auto kern = mma::scan_mma_small_kernel<NQ, KPL, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.alloc));
     if (e != cudaSuccess) return e;
-    kern<<<a.plan.lists, mma::S_THREADS, plan.alloc, a.stream>>>(tq, tc, a.keys_or_null, a.n_rows, nq, a.ksel, a.partials,
+    kern<<<a.plan.lists, mma::SmallPlan<NQ, KPL, SPLIT>::THREADS, plan.alloc, a.stream>>>(tq, tc, a.keys_or_null, a.n_rows, nq, a.ksel, a.partials,
                                                                 a.nq_total, a.tau_g, k_chunks, q0, a.nq_dev);
     count_launch();
     return cudaGetLastError();
