@@ -159,7 +159,7 @@ struct fr_index {
     cudaStream_t stream = nullptr;   // host-path stream
     cudaEvent_t last_use = nullptr;  // orders scratch reuse across caller streams
     DevBuf q_raw, q_prep, q_keys, partials, out_dist, out_keys, stage_vecs, stage_keys, stage_rows;
-    DevBuf q_bf16, err_bound, sel, sel_keys, flags, fail, fb_partials, tau;  // K2 path
+    DevBuf q_bf16, err_bound, sel, sel_keys, flags, fail, fb_partials, tau, progress;  // K2 path
     DevBuf kth_exact, r_q, r_misc, r_tau, r_partials, r_sel, r_sel_keys;     // K2 second-chance pass
     int mma_min_batch = 2;  // FR_PATH_AUTO: batches at least this large go to the tensor-core scans; smaller ones
                             // too when the swapped-operand kernel K2s serves them (it out-streams K1: TMA ring)
@@ -169,6 +169,7 @@ struct fr_index {
     int64_t small_rows_b1 = 2000000, small_rows_b4 = 200000;  // FR_PATH_AUTO: below these sizes batch 1 / batch <= 4 take K1
     int mma_bound_scale_pct = 100;  // diagnostics / tests: certification error bounds x this / 100 (>= 100: stricter, still exact)
     int mma_debug = 0;      // diagnostics (scripts/ablate_mma.py): results are wrong when non-zero
+    int mma_max_lead = 6;   // K2 co-resident groups: tiles a group may run ahead of the slowest group of its stream (0 = unthrottled)
     int mma_co_groups = 4;  // K2: query groups of 256 that share one corpus stream through L2 (measured at 100M rows,
                             // batch 1024: 1 -> 2 groups +9 % QPS, 2 -> 4 another +1.5 %; the board is power-bound and
                             // every HBM byte not fetched is clock for the tensor cores)
@@ -438,6 +439,11 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     ms.partials = static_cast<uint64_t *>(ix->partials.p);
     ms.plan = plan;
     ms.dbg = ix->mma_debug;
+    if (!small && plan.co > 1 && ix->mma_max_lead > 0) {
+        FR_CUDA(ix->progress.need(static_cast<size_t>(plan.lists_max) * plan.co * sizeof(uint32_t)));
+        ms.progress = static_cast<uint32_t *>(ix->progress.p);
+        ms.max_lead = ix->mma_max_lead;
+    }
     ms.tau_g = static_cast<uint32_t *>(ix->tau.p);
     ms.stream = s;
     ProfScope prof{ix, s};
@@ -681,7 +687,7 @@ uint64_t state_hash(const fr_index *ix) {
     };
     const DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist, &ix->out_keys, &ix->q_bf16,
                             &ix->err_bound, &ix->sel, &ix->sel_keys, &ix->flags, &ix->fail, &ix->fb_partials, &ix->tau,
-                            &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau, &ix->r_partials, &ix->r_sel,
+                            &ix->progress, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau, &ix->r_partials, &ix->r_sel,
                             &ix->r_sel_keys};
     for (const DevBuf *b : bufs) mix(reinterpret_cast<uintptr_t>(b->p));
     mix(reinterpret_cast<uintptr_t>(ix->pin.p));
@@ -690,7 +696,7 @@ uint64_t state_hash(const fr_index *ix) {
     mix(static_cast<uint64_t>(ix->rows));
     mix(ix->n_deleted > 0 ? 1u : 0u);
     for (int v : {ix->path, ix->mma_min_batch, ix->mma_small_max, ix->mma_co_groups, ix->mma_split, ix->mma_split_max,
-                  ix->mma_debug, ix->mma_bound_scale_pct})
+                  ix->mma_debug, ix->mma_bound_scale_pct, ix->mma_max_lead})
         mix(static_cast<uint64_t>(static_cast<int64_t>(v)));
     mix(static_cast<uint64_t>(ix->small_rows_b1));
     mix(static_cast<uint64_t>(ix->small_rows_b4));
@@ -767,7 +773,7 @@ int fr_index_destroy(fr_index *ix) {
         DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist,
                           &ix->out_keys, &ix->stage_vecs, &ix->stage_keys, &ix->stage_rows,
                           &ix->q_bf16, &ix->err_bound, &ix->sel, &ix->sel_keys, &ix->flags, &ix->fail,
-                          &ix->fb_partials, &ix->tau, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau,
+                          &ix->fb_partials, &ix->tau, &ix->progress, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau,
                           &ix->r_partials, &ix->r_sel, &ix->r_sel_keys};
         for (DevBuf *b : bufs) b->release();
         ix->pin.release();
@@ -801,6 +807,11 @@ int fr_index_set_option(fr_index *ix, const char *name, int64_t value) {
     if (std::strcmp(name, "mma_co_groups") == 0) {
         if (value < 1 || value > 8) return fail(FR_EINVAL, "mma_co_groups must be in [1, 8]");
         ix->mma_co_groups = static_cast<int>(value);
+        return FR_OK;
+    }
+    if (std::strcmp(name, "mma_max_lead") == 0) {
+        if (value < 0 || value > 1024) return fail(FR_EINVAL, "mma_max_lead must be in [0, 1024]");
+        ix->mma_max_lead = static_cast<int>(value);
         return FR_OK;
     }
     if (std::strcmp(name, "mma_bound_scale_pct") == 0) {

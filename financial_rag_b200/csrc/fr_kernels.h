@@ -61,6 +61,9 @@ struct MmaScanArgs {
     MmaPlan plan;
     const int *nq_dev;          // optional: the launch serves *nq_dev queries (second-chance pass), 0 = exit at once
     const float *tau0;          // optional [nq_total]: fixed initial threshold per query (second-chance pass)
+    uint32_t *progress;         // optional [plan.lists_max * plan.co]: tiles requested per (stream, co-resident group); lets the
+                                // groups of a stream stay within max_lead tiles of each other (zeroed by the launcher)
+    int max_lead;
     int dbg;                    // diagnostics only (option "mma_debug"): 1 = no corpus loads, 2 = no accumulator reads
     uint32_t *tau_g;            // ksel * nq_total shared threshold slots (order_bits of a score), zeroed before the launches;
                                 // K2 lays them out [ksel][nq_total], K2s [nq_total][ksel]

@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                 const int64_t *__restrict__ keys_or_null, int64_t n_rows, int nq_launch, int q_row0_launch, int ksel,
                 uint64_t *__restrict__ partials, int nq_total, int co, uint32_t *__restrict__ tau_g, int dbg,
-                const int *__restrict__ nq_dev, const float *__restrict__ tau0) {
+                const int *__restrict__ nq_dev, const float *__restrict__ tau0, uint32_t *__restrict__ progress,
+                int max_lead) {
     using Plan = SmemPlan<KPL>;
     constexpr int STAGES = Plan::STAGES;
     constexpr int CAP = Plan::CAP;
@@ -215,7 +216,41 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                                 q_row0 + static_cast<int>(rank) * M_TILE);
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t t = pair; t < num_tiles; t += npairs) {
+            // Co-resident groups of one stream only share its tiles through L2 while they stay within a few tiles of
+            // each other, and nothing keeps them there: their epilogues do different amounts of insert work, the
+            // distances random-walk, and once a pair trails by more than L2 retains (~30 us of streaming) it re-reads
+            // the corpus from HBM for the rest of the scan (measured with 4 groups over 100M rows: 233 GB of DRAM reads
+            // per launch against 76.8 GB of corpus).  So every pair publishes how many tiles it has requested, and a
+            // pair that is more than max_lead tiles ahead of the slowest sibling waits for it.  The wait is bounded:
+            // should a sibling not be resident (or the budget run out) the pair stops waiting for good -- sharing is
+            // an optimisation, never a dependency.
+            bool throttle = progress != nullptr && co > 1 && rank == 0;
+            int budget = 3000;
+            uint32_t *my_progress = throttle ? progress + static_cast<size_t>(pair) * co + grp : nullptr;
+            const uint32_t *siblings = throttle ? progress + static_cast<size_t>(pair) * co : nullptr;
+            uint32_t issued = 0;
+            uint32_t slowest = 0;  // last known progress of the slowest sibling: polled only when the lead may be used up
+            for (int64_t t = pair; t < num_tiles; t += npairs, ++issued) {
+                if (throttle && issued > slowest + static_cast<uint32_t>(max_lead)) {
+                    while (true) {
+                        slowest = 0xffffffffu;
+                        for (int g = 0; g < co; ++g) {
+                            uint32_t x;
+                            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(x) : "l"(siblings + g));
+                            slowest = min(slowest, x);
+                        }
+                        if (slowest == 0xffffffffu) {  // every sibling is done
+                            throttle = false;
+                            break;
+                        }
+                        if (slowest + static_cast<uint32_t>(max_lead) >= issued) break;
+                        if (--budget <= 0) {
+                            throttle = false;
+                            break;
+                        }
+                        __nanosleep(64);
+                    }
+                }
                 // diagnostics: dbg & 8 = every stream re-reads the same 64 tiles (L2-resident): no HBM traffic, same L2->SM traffic
                 const int64_t tt = (dbg & 8) ? (t & 63) : t;
                 const int row0 = static_cast<int>(tt * TILE_ROWS) + static_cast<int>(rank) * N_TILE;
@@ -233,7 +268,11 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                         phase ^= 1;
                     }
                 }
+                if (my_progress != nullptr)
+                    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(my_progress), "r"(issued + 1u) : "memory");
             }
+            if (my_progress != nullptr)  // done: nobody waits for this pair any more
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(my_progress), "r"(0xffffffffu) : "memory");
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
@@ -707,6 +746,10 @@ template <int KPL, int CG>
 cudaError_t launch_one(const MmaScanArgs &a, const CUtensorMap &tq, const CUtensorMap &tc, int nq, int q0, int co,
                        int lists) {
     auto kern = mma::scan_mma_kernel<KPL, CG>;
+    if (co > 1 && a.progress != nullptr) {  // progress counters of the co-resident groups, [lists][co]
+        cudaError_t em = cudaMemsetAsync(a.progress, 0, static_cast<size_t>(lists) * co * sizeof(uint32_t), a.stream);
+        if (em != cudaSuccess) return em;
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(mma::SmemPlan<KPL>::ALLOC));
     if (e != cudaSuccess) return e;
@@ -723,7 +766,7 @@ cudaError_t launch_one(const MmaScanArgs &a, const CUtensorMap &tq, const CUtens
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     e = cudaLaunchKernelEx(&cfg, kern, tq, tc, a.keys_or_null, a.n_rows, nq, q0, a.ksel, a.partials, a.nq_total, co,
-                           a.tau_g, a.dbg, a.nq_dev, a.tau0);
+                           a.tau_g, a.dbg, a.nq_dev, a.tau0, co > 1 ? a.progress : nullptr, a.max_lead);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }
