@@ -46,13 +46,20 @@ class ShardedSearcher:
             device = torch.device("cuda", local_index.device)
         self.device = torch.device(device)
         n = self.max_batch * self.k
-        # [packed | keys] per rank, gathered into [G][2][B*k]
-        self.local = torch.zeros((2, n), dtype=torch.int64, device=self.device)
-        self.gathered = torch.zeros((self.world, 2, n), dtype=torch.int64, device=self.device)
+        # [packed | keys] per rank, gathered into [G][2][B*k]; `local` / `gathered` are views sized for the batch of
+        # the current call, so a batch of 1 exchanges 160 bytes per rank, not max_batch times that
+        self._local_flat = torch.zeros((2 * n,), dtype=torch.int64, device=self.device)
+        self._gathered_flat = torch.zeros((self.world * 2 * n,), dtype=torch.int64, device=self.device)
+        self._views(self.max_batch)
         self.out_dist = torch.empty((self.max_batch, self.k), dtype=torch.float32, device=self.device)
         self.out_keys = torch.empty((self.max_batch, self.k), dtype=torch.int64, device=self.device)
         self._local_search = local_search or self._cuda_local_search
         self._merge = merge or self._cuda_merge
+
+    def _views(self, b: int) -> None:
+        m = b * self.k
+        self.local = self._local_flat[: 2 * m].view(2, m)
+        self.gathered = self._gathered_flat[: self.world * 2 * m].view(self.world, 2, m)
 
     # -- default (product) compute steps: CUDA through the C ABI -----------------------------------
     def _cuda_local_search(self, queries, b: int) -> None:
@@ -61,8 +68,7 @@ class ShardedSearcher:
     def _cuda_merge(self, b: int) -> None:
         from .index import merge_shards_device
 
-        n = self.max_batch * self.k
-        merge_shards_device(self.device.index, self.space, self.gathered[:, 0], self.gathered[:, 1], 2 * n,
+        merge_shards_device(self.device.index, self.space, self.gathered[:, 0], self.gathered[:, 1], 2 * b * self.k,
                             self.world, b, self.k, self.out_dist, self.out_keys)
 
     # -- the search -----------------------------------------------------------------------------------
@@ -72,6 +78,7 @@ class ShardedSearcher:
         b = int(queries.shape[0])
         if b > self.max_batch:
             raise ValueError(f"batch {b} exceeds max_batch {self.max_batch}")
+        self._views(b)
         self._local_search(queries, b)
         if self.world > 1:
             self.dist.all_gather_into_tensor(self.gathered.view(-1), self.local.view(-1), group=self.group)
