@@ -334,12 +334,21 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         uint32_t best = 0, published = 0;          // order bits of the best score appended / published
         const uint32_t l_tempty = (CG == 2) ? map_to_cta(bar_tempty, 0) : bar_tempty;
         uint32_t it = 0;
+        uint32_t next_refresh = 0;
+        const uint32_t refresh_cap = (dbg & 16) ? 8u : 64u;  // diagnostics: dbg & 16 = the old dense schedule
         for (int64_t t = pair; t < num_tiles; t += npairs, ++it) {
             const uint32_t buf = it % TMEM_BUFS;
             const uint32_t bphase = (it / TMEM_BUFS) & 1;
             // min over the k' group slots = a score k' distinct rows reach (monotone hints: relaxed loads)
             uint32_t g = 0;
-            if (live && (it < 8u || (it & 7u) == 0u)) {
+            // Refresh schedule: every tile at first, then at geometrically growing distances (the k'-th best of
+            // everything scanned so far moves like 1/rows: a threshold read at 2/3 of the current progress lets at most
+            // 1.5 x the candidates through), at least every `refresh_cap` tiles.  k' relaxed loads per lane and refresh are
+            // latency the accumulator hand-back waits for: at k' = 128 the fixed every-8-tiles schedule kept the
+            // epilogue in the refresh for half of its time.
+            const bool refresh_now = it >= next_refresh;
+            if (refresh_now) next_refresh = it + 1u + min(it >> 1, refresh_cap - 1u);
+            if (live && refresh_now) {
                 g = 0xffffffffu;
 #pragma unroll 8
                 for (int j = 0; j < ksel; ++j) {

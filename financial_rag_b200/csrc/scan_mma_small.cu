@@ -226,6 +226,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         // shared thresholds (see scan_mma.cu): this CTA raises slot cta % k' of a query to the best score it holds
         uint32_t *my_slots = tau_g + static_cast<size_t>(q0 + qbase) * ksel + (cta % ksel);  // + q * ksel
         uint32_t it = 0;
+        uint32_t next_refresh = 0;
         for (int64_t t = cta; t < num_tiles; t += ncta, ++it) {
             const uint32_t buf = it % S_TMEM_BUFS;
             const uint32_t bphase = (it / S_TMEM_BUFS) & 1;
@@ -234,7 +235,10 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             // request per query instead of k' (the requests of all CTAs meet on the same few lines).
             // (Tried: a seventh warp polling the slots every 1.5 us and handing the thresholds over through shared
             // memory -- 5-8 % slower at every batch size: the polling traffic costs more than the refresh.)
-            if (it < 8u || (it & 7u) == 0u) {
+            // (schedule as in K2: every tile at first, then geometrically thinning out to every 64th tile)
+            const bool refresh_now = it >= next_refresh;
+            if (refresh_now) next_refresh = it + 1u + min(it >> 1, 63u);
+            if (refresh_now) {
                 uint32_t x[NQH];
 #pragma unroll
                 for (int q = 0; q < NQH; ++q) {
