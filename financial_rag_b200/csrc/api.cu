@@ -169,6 +169,7 @@ struct fr_index {
     int64_t small_rows_b1 = 2000000, small_rows_b4 = 200000;  // FR_PATH_AUTO: below these sizes batch 1 / batch <= 4 take K1
     int mma_bound_scale_pct = 100;  // diagnostics / tests: certification error bounds x this / 100 (>= 100: stricter, still exact)
     int mma_debug = 0;      // diagnostics (scripts/ablate_mma.py): results are wrong when non-zero
+    int mma_wide_lists = 1; // k in (64, 100]: keep 256 candidates per query instead of 128
     int mma_max_lead = 6;   // K2 co-resident groups: tiles a group may run ahead of the slowest group of its stream (0 = unthrottled)
     int mma_co_groups = 4;  // K2: query groups of 256 that share one corpus stream through L2 (measured at 100M rows,
                             // batch 1024: 1 -> 2 groups +9 % QPS, 2 -> 4 another +1.5 %; the board is power-bound and
@@ -316,7 +317,7 @@ bool small_serves(const fr_index *ix, int B, int ksel) {
     return fr::scan_mma_small_nq(B, ksel, ix->dim, small_split(ix, B, ksel)) != 0;
 }
 int mma_slice(const fr_index *ix, int k) {  // 0 = not eligible, else the largest batch one pass may take
-    const int ksel = fr::scan_mma_ksel(k);
+    const int ksel = fr::scan_mma_ksel(k, ix->mma_wide_lists);
     if (ix->dtype != FR_BF16 || ix->metric != FR_COSINE || ksel == 0 || ix->rows <= 0) return 0;
     if (ix->dim == 384) return 1 << 30;
     if (ix->dim != 768) return 0;  // the re-scan safety net exists for 384 and 768 only
@@ -371,7 +372,7 @@ int search_stream(fr_index *ix, const float *q, int B, int k, float *d_out_dist,
 // of whatever is still open after that.
 int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_out_dist, uint64_t *d_out_packed,
                int64_t *d_out_keys, cudaStream_t s) {
-    const int ksel = fr::scan_mma_ksel(k);
+    const int ksel = fr::scan_mma_ksel(k, ix->mma_wide_lists);
     const int group = fr::scan_mma_group(B);
     const int nq_pad = ((B + group - 1) / group) * group;
     // small batches take the swapped-operand kernel (tensor work proportional to the batch)
@@ -651,7 +652,7 @@ int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *
                     "FR_PATH_MMA serves bf16 cosine collections of width 384 (k <= 100) or 768 (k <= 32) with at least one row "
                     "(this one: dtype %d, dim %d, metric %d, k %d, rows %lld)",
                     ix->dtype, ix->dim, ix->metric, k, (long long)ix->rows);
-    const bool k2s = eligible && small_serves(ix, B, fr::scan_mma_ksel(k));
+    const bool k2s = eligible && small_serves(ix, B, fr::scan_mma_ksel(k, ix->mma_wide_lists));
     // small collections are launch-bound, not bandwidth-bound: K1 is 3 launches, the tensor-core path 11+
     // (scripts/latency_small.py: batch 1 over 1M rows 148 vs 165 us, over 10k rows 25 vs 53 us)
     const bool launch_bound = (B == 1 && ix->rows <= ix->small_rows_b1) || (B <= 4 && ix->rows <= ix->small_rows_b4);
@@ -696,7 +697,7 @@ uint64_t state_hash(const fr_index *ix) {
     mix(static_cast<uint64_t>(ix->rows));
     mix(ix->n_deleted > 0 ? 1u : 0u);
     for (int v : {ix->path, ix->mma_min_batch, ix->mma_small_max, ix->mma_co_groups, ix->mma_split, ix->mma_split_max,
-                  ix->mma_debug, ix->mma_bound_scale_pct, ix->mma_max_lead})
+                  ix->mma_debug, ix->mma_bound_scale_pct, ix->mma_max_lead, ix->mma_wide_lists})
         mix(static_cast<uint64_t>(static_cast<int64_t>(v)));
     mix(static_cast<uint64_t>(ix->small_rows_b1));
     mix(static_cast<uint64_t>(ix->small_rows_b4));
@@ -807,6 +808,10 @@ int fr_index_set_option(fr_index *ix, const char *name, int64_t value) {
     if (std::strcmp(name, "mma_co_groups") == 0) {
         if (value < 1 || value > 8) return fail(FR_EINVAL, "mma_co_groups must be in [1, 8]");
         ix->mma_co_groups = static_cast<int>(value);
+        return FR_OK;
+    }
+    if (std::strcmp(name, "mma_wide_lists") == 0) {
+        ix->mma_wide_lists = value != 0;
         return FR_OK;
     }
     if (std::strcmp(name, "mma_max_lead") == 0) {

@@ -69,7 +69,7 @@ struct MmaScanArgs {
                                 // K2 lays them out [ksel][nq_total], K2s [nq_total][ksel]
     cudaStream_t stream;
 };
-int scan_mma_ksel(int k);  // 0 = k not served by the tensor-core path
+int scan_mma_ksel(int k, int wide = 1);  // candidates kept per query (0 = k not served by the tensor-core path); wide: 256 for k > 64
 int scan_mma_group(int nq_total);  // queries per corpus pass: 128 (one CTA per SM) or 256 (CTA pairs)
 struct PrepArgs {
     const float *raw;   // [nq][dim] raw fp32 queries

@@ -54,7 +54,9 @@ constexpr int CHUNK_BYTES = STAGE_BYTES;       // 16 KB: one [128 x 64] bf16 box
 constexpr int TMEM_COLS = 512;                 // the whole tensor memory: 4 x 128 or 2 x 256 columns
 constexpr int THREADS = 192;                   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
 
-constexpr int PEND = 16;                       // unsorted pending candidates per query between compactions
+// unsorted pending candidates per query between compactions: 16 beside shared-memory lists, 32 (a full warp sort per
+// compaction, half as many compactions against L2) where the lists live in global memory and shared memory has room
+__host__ __device__ constexpr int pend_slots(int kpl) { return kpl >= 4 ? 32 : 16; }
 constexpr int RETRY_MAX = M_TILE;              // uncertified queries that get a second tensor-core pass
 constexpr int RESCORE_MAX_DIM = 1024;          // widest vectors the rescoring kernel stages in shared memory
 
@@ -71,6 +73,7 @@ struct SmemPlan {
     static constexpr size_t B_OFF = A_OFF + size_t(K_CHUNKS) * CHUNK_BYTES;
     static constexpr size_t LIST_OFF = B_OFF + size_t(STAGES) * CHUNK_BYTES;   // [128 queries][CAP] sorted
     static constexpr size_t PEND_OFF = LIST_OFF + (LISTS_IN_SMEM ? size_t(M_TILE) * CAP * 8 : 0);  // [4 warps][PEND][32] swizzled
+    static constexpr int PEND = pend_slots(KPL);
     static constexpr size_t BAR_OFF = PEND_OFF + size_t(M_TILE) * PEND * 8;
     static constexpr size_t TOTAL = BAR_OFF + 256;
     static constexpr size_t ALLOC = TOTAL + 1024;  // slack to align the base to 1024 B
@@ -316,6 +319,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int quarter = warp & 3;              // TMEM lane quarter this warp may access
         const int my_q = quarter * 32 + lane;      // query index inside this CTA's block of 128
         uint64_t *my_lists = lists + static_cast<size_t>(quarter) * 32 * CAP;
+        constexpr int PEND = Plan::PEND;
         uint64_t *pend_w = pend_all + static_cast<size_t>(warp - 2) * PEND * 32;  // entry j of lane q: [j][(q + j) & 31]
         const bool live = my_q < nq_local;
         // padded query rows never pass the gate; a second-chance query starts at its fixed threshold
@@ -735,7 +739,11 @@ __global__ void retry_prep_kernel(const float *__restrict__ queries, const float
 
 // ---- host launchers ---------------------------------------------------------------------------
 // candidates kept per query: k' > k leaves the certification a margin (k' - k rows may overtake)
-int scan_mma_ksel(int k) { return k <= 16 ? 32 : (k <= 32 ? 64 : (k <= 100 ? 128 : 0)); }
+// (k' = 128 for k = 100 left 28 rows of margin: 1.4 % of the queries of a Gaussian corpus and nearly all of a
+// clustered one failed the first certification, and every block of failures costs a whole extra corpus pass)
+int scan_mma_ksel(int k, int wide) {
+    return k <= 16 ? 32 : (k <= 32 ? 64 : (k <= 64 ? 128 : (k <= 100 ? (wide ? 256 : 128) : 0)));
+}
 
 // queries served by one corpus pass: a single CTA per SM up to 128, CTA pairs (cta_group::2) above
 int scan_mma_group(int nq_total) { return nq_total <= mma::M_TILE ? mma::M_TILE : 2 * mma::M_TILE; }
@@ -825,12 +833,11 @@ cudaError_t launch_scan_mma(const MmaScanArgs &a) {
                 : a.ksel <= 64  ? launch_one<2, 1>(a, tq, tc, nq, q0, co, lists)
                 : a.ksel <= 128 ? launch_one<4, 1>(a, tq, tc, nq, q0, co, lists)
                                 : launch_one<8, 1>(a, tq, tc, nq, q0, co, lists);  // second-chance pass of k' = 128
-        else if (a.ksel > 128)
-            e = cudaErrorNotSupported;
         else
-            e = a.ksel <= 32   ? launch_one<1, 2>(a, tq, tc, nq, q0, co, lists)
-                : a.ksel <= 64 ? launch_one<2, 2>(a, tq, tc, nq, q0, co, lists)
-                               : launch_one<4, 2>(a, tq, tc, nq, q0, co, lists);
+            e = a.ksel <= 32    ? launch_one<1, 2>(a, tq, tc, nq, q0, co, lists)
+                : a.ksel <= 64  ? launch_one<2, 2>(a, tq, tc, nq, q0, co, lists)
+                : a.ksel <= 128 ? launch_one<4, 2>(a, tq, tc, nq, q0, co, lists)
+                                : launch_one<8, 2>(a, tq, tc, nq, q0, co, lists);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
