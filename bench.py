@@ -171,11 +171,14 @@ def ncu_traffic(path_kind, rows_local):
         return None
 
 
-def scan_kernel_of(batch, path, k, dtype="bf16"):
+def scan_kernel_of(batch, path, k, dtype="bf16", rows_local=None):
     """Which scan kernel a batch runs on (mirrors search_on_stream in csrc/api.cu) and the queries
     one launch of it serves."""
     mma_ok = k <= 100 and dtype == "bf16"
     use_mma = mma_ok and path in ("mma", "auto")
+    if use_mma and path == "auto" and rows_local is not None:  # small shards are launch-bound: K1 is 3 launches
+        if (batch == 1 and rows_local <= 2_000_000) or (batch <= 4 and rows_local <= 200_000):
+            use_mma = False
     if not use_mma:
         return "scan_stream_kernel", "stream", min(batch, 4)
     if batch <= 64 and k <= 32 and not (batch > 32 and k > 16):
@@ -193,7 +196,7 @@ def roofline_of(batch, path, k, rows_local, elem, scan_ms, scan_launches, search
     read once per launch whatever the number of queries; flops = 2 * rows_per_gpu * 384 * queries the
     launch serves.  The bound is whichever of bytes/hbm_peak and flops/tensor_peak is the longer."""
     hbm_peak, tf_sustained, tf_burst, peak_kind = measured_peaks()
-    kernel, kind, _ = scan_kernel_of(batch, path, k, dtype)
+    kernel, kind, _ = scan_kernel_of(batch, path, k, dtype, rows_local)
     avg_launch_s = (scan_ms / max(scan_launches, 1)) / 1e3
     q_per_launch = batch * max(searches, 1) / max(scan_launches, 1)
     bytes_per_launch = rows_local * DIM * elem
