@@ -224,17 +224,17 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             // distances random-walk, and once a pair trails by more than L2 retains (~30 us of streaming) it re-reads
             // the corpus from HBM for the rest of the scan (measured with 4 groups over 100M rows: 233 GB of DRAM reads
             // per launch against 76.8 GB of corpus).  So every pair publishes how many tiles it has requested, and a
-            // pair that is more than max_lead tiles ahead of the slowest sibling waits for it.  The wait is bounded:
-            // should a sibling not be resident (or the budget run out) the pair stops waiting for good -- sharing is
-            // an optimisation, never a dependency.
+            // pair that is more than max_lead tiles ahead of the slowest sibling waits for it.  One wait is bounded
+            // (~20 ms of polling): a sibling that makes no progress for that long is not resident, and the pair stops
+            // waiting for good -- sharing is an optimisation, never a dependency.
             bool throttle = progress != nullptr && co > 1 && rank == 0;
-            int budget = 3000;
             uint32_t *my_progress = throttle ? progress + static_cast<size_t>(pair) * co + grp : nullptr;
             const uint32_t *siblings = throttle ? progress + static_cast<size_t>(pair) * co : nullptr;
             uint32_t issued = 0;
             uint32_t slowest = 0;  // last known progress of the slowest sibling: polled only when the lead may be used up
             for (int64_t t = pair; t < num_tiles; t += npairs, ++issued) {
                 if (throttle && issued > slowest + static_cast<uint32_t>(max_lead)) {
+                    int spins = 0;
                     while (true) {
                         slowest = 0xffffffffu;
                         for (int g = 0; g < co; ++g) {
@@ -247,7 +247,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                             break;
                         }
                         if (slowest + static_cast<uint32_t>(max_lead) >= issued) break;
-                        if (--budget <= 0) {
+                        if (++spins > 20000) {
                             throttle = false;
                             break;
                         }
