@@ -634,6 +634,37 @@ def test_mma_second_chance_pass_resolves_crowded_neighbourhoods(frb):
     ix.close()
 
 
+def test_scheduling_options_do_not_change_results(frb):
+    """Lead throttle between co-resident groups, candidate-list width for k in (64, 100] and the threshold refresh
+    schedule only decide WHEN and HOW MUCH is kept, never what the answer is: ids and distances are bit-identical
+    across every setting (the exact rescoring sees a superset of the true top-k in all of them)."""
+    n, B = 60000, 1100
+    corpus = make_corpus(n, 384, seed=6100, dup_pairs=[(17, 41000)])
+    queries = make_queries(B, corpus, seed=6101)
+    queries[3] = corpus[17]
+    ix = build_index(frb, corpus, "cosine", "bf16")
+    ix.set_path("mma")
+    for k in (10, 100):
+        ref = None
+        for opts in ({}, {"mma_max_lead": 0}, {"mma_max_lead": 1}, {"mma_co_groups": 2, "mma_max_lead": 2},
+                     {"mma_wide_lists": 0}, {"mma_debug": 16}):
+            defaults = {"mma_max_lead": 6, "mma_co_groups": 4, "mma_wide_lists": 1, "mma_debug": 0}
+            defaults.update(opts)
+            for name, value in defaults.items():
+                ix.set_option(name, value)
+            d, kk = ix.search(queries, k)
+            if ref is None:
+                ref = (d, kk)
+                assert_matches_oracle(d[:24], keys_to_rows(kk[:24], KEY_BASE), queries[:24], corpus, k, "cosine", "bf16",
+                                      stored=stored_rows(ix), label=f"scheduling options k={k}")
+                assert keys_to_rows(kk[3], KEY_BASE)[0] == 17 and keys_to_rows(kk[3], KEY_BASE)[1] == 41000
+            else:
+                np.testing.assert_array_equal(kk, ref[1], err_msg=f"k={k} {opts}")
+                np.testing.assert_array_equal(d, ref[0], err_msg=f"k={k} {opts}")
+    assert ix.stat("mma_rescanned_queries") == 0
+    ix.close()
+
+
 def make_clustered(n, centres, spread, seed):
     """Rows = centre + spread * noise: hundreds of rows score within 1e-2 of a query's best hits, like the chunks of
     one document family in a real collection (isotropic Gaussian rows never do)."""
