@@ -292,21 +292,44 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 mbar_wait(bar_tempty + 8 * buf, bphase ^ 1);  // both epilogues have drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
+                // Two K-chunks per barrier round trip: the issuing thread waits for two stages, then issues their
+                // eight MMAs back to back.  One chunk per wait left ~0.3 us of wait + fence latency exposed between
+                // every four MMAs (+2 ... +4 % at every batch size; three chunks per wait starve the 5-stage ring).
+                static_assert(K_CHUNKS % 2 == 0, "the MMA loop takes K-chunks in pairs");
 #pragma unroll 1
-                for (int kc = 0; kc < K_CHUNKS; ++kc) {
-                    mbar_wait(bar_full + 8 * stage, phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem_a + kc * CHUNK_BYTES);
-                    const uint32_t b_addr = smem_u32(smem_b + stage * CHUNK_BYTES);
-#pragma unroll
-                    for (int k4 = 0; k4 < K_CHUNK / UMMA_K; ++k4) {
-                        const uint64_t adesc = make_kmajor_sw128_desc(a_addr + k4 * UMMA_K * 2);
-                        const uint64_t bdesc = make_kmajor_sw128_desc(b_addr + k4 * UMMA_K * 2);
-                        if (!(dbg & 4))  // diagnostics: dbg & 4 = no MMAs at all
-                            tc_mma_bf16<CG>(d_tmem, adesc, bdesc, idesc, (kc | k4) != 0 ? 1u : 0u);
+                for (int kc = 0; kc < K_CHUNKS; kc += 2) {
+                    const int s0 = stage;
+                    const uint32_t p0 = phase;
+                    int s1 = stage + 1;
+                    uint32_t p1 = phase;
+                    if (s1 == STAGES) {
+                        s1 = 0;
+                        p1 ^= 1;
                     }
-                    tc_commit<CG>(bar_empty + 8 * stage);  // smem stage reusable once these MMAs have read it
-                    if (++stage == STAGES) {
+                    mbar_wait(bar_full + 8 * s0, p0);
+                    if (!(dbg & 32)) mbar_wait(bar_full + 8 * s1, p1);  // diagnostics: dbg & 32 = one chunk per wait
+                    tc_fence_after();
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int sh = h == 0 ? s0 : s1;
+                        if (h == 1 && (dbg & 32)) {
+                            mbar_wait(bar_full + 8 * s1, p1);
+                            tc_fence_after();
+                        }
+                        const uint32_t a_addr = smem_u32(smem_a + (kc + h) * CHUNK_BYTES);
+                        const uint32_t b_addr = smem_u32(smem_b + sh * CHUNK_BYTES);
+#pragma unroll
+                        for (int k4 = 0; k4 < K_CHUNK / UMMA_K; ++k4) {
+                            const uint64_t adesc = make_kmajor_sw128_desc(a_addr + k4 * UMMA_K * 2);
+                            const uint64_t bdesc = make_kmajor_sw128_desc(b_addr + k4 * UMMA_K * 2);
+                            if (!(dbg & 4))  // diagnostics: dbg & 4 = no MMAs at all
+                                tc_mma_bf16<CG>(d_tmem, adesc, bdesc, idesc, ((kc + h) | k4) != 0 ? 1u : 0u);
+                        }
+                        tc_commit<CG>(bar_empty + 8 * sh);  // smem stage reusable once these MMAs have read it
+                    }
+                    stage = s1 + 1;
+                    phase = p1;
+                    if (stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }

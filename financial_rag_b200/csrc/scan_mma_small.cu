@@ -191,19 +191,37 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 mbar_wait(bar_tempty + 8 * buf, bphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * S_ACC_STRIDE;
+                // K-chunks in pairs per barrier round trip (see scan_mma.cu); an odd width ends with a single chunk
 #pragma unroll 1
-                for (int kc = 0; kc < k_chunks; ++kc) {
-                    mbar_wait(bar_full + 8 * stage, phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem_ring + stage * STAGE_BYTES);
-                    const uint32_t b_addr = smem_u32(smem_q + kc * Plan::Q_CHUNK);
-#pragma unroll
-                    for (int k4 = 0; k4 < K_CHUNK / UMMA_K; ++k4) {
-                        const uint64_t adesc = make_kmajor_sw128_desc(a_addr + k4 * UMMA_K * 2);
-                        const uint64_t bdesc = make_kmajor_sw128_desc(b_addr + k4 * UMMA_K * 2);
-                        tc_mma_bf16<1>(d_tmem, adesc, bdesc, idesc, (kc | k4) != 0 ? 1u : 0u);
+                for (int kc = 0; kc < k_chunks; kc += 2) {
+                    const int n_here = (kc + 1 < k_chunks) ? 2 : 1;
+                    const int s0 = stage;
+                    const uint32_t p0 = phase;
+                    int s1 = stage + 1;
+                    uint32_t p1 = phase;
+                    if (s1 == STAGES) {
+                        s1 = 0;
+                        p1 ^= 1;
                     }
-                    tc_commit<1>(bar_empty + 8 * stage);
+                    mbar_wait(bar_full + 8 * s0, p0);
+                    if (n_here == 2) mbar_wait(bar_full + 8 * s1, p1);
+                    tc_fence_after();
+                    for (int h = 0; h < n_here; ++h) {
+                        const int sh = h == 0 ? s0 : s1;
+                        const uint32_t a_addr = smem_u32(smem_ring + sh * STAGE_BYTES);
+                        const uint32_t b_addr = smem_u32(smem_q + (kc + h) * Plan::Q_CHUNK);
+#pragma unroll
+                        for (int k4 = 0; k4 < K_CHUNK / UMMA_K; ++k4) {
+                            const uint64_t adesc = make_kmajor_sw128_desc(a_addr + k4 * UMMA_K * 2);
+                            const uint64_t bdesc = make_kmajor_sw128_desc(b_addr + k4 * UMMA_K * 2);
+                            tc_mma_bf16<1>(d_tmem, adesc, bdesc, idesc, ((kc + h) | k4) != 0 ? 1u : 0u);
+                        }
+                        tc_commit<1>(bar_empty + 8 * sh);
+                    }
+                    if (n_here == 2) {
+                        stage = s1;
+                        phase = p1;
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
