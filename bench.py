@@ -40,9 +40,10 @@ if ROOT not in sys.path:
 DIM = 384
 CHUNK_ROWS = 500_000          # global generation chunk; seed = 1234 + chunk index
 DEFAULT_ROWS = 100_000_000    # BASELINE.json: "exact top-10 over 100M x 384"
-DEFAULT_BATCH = 1024          # cfg4 spans batch 1-4096; QPS is quoted in the batched (tensor-core) regime,
+DEFAULT_BATCH = 4096          # cfg4 spans batch 1-4096; QPS is quoted at its top (8 co-resident groups of 256 queries
+                              # per corpus pass: the corpus crosses HBM once per 2048 queries),
                               # the HBM-streaming regime (batch 1 ... 128) is in "sweep" of the same line
-DEFAULT_SWEEP = "1,1s,8,64,128,256,4096"   # "1s" = batch 1 through the K1 streaming kernel (path stream)
+DEFAULT_SWEEP = "1,1s,8,64,128,256,1024"   # "1s" = batch 1 through the K1 streaming kernel (path stream)
 MMA_GROUP = 256               # queries per K2 corpus pass above 128 (CTA pairs)
 METRIC = "QPS exact top-10 over 100Mx384 bf16 (cosine), row-sharded"
 

@@ -171,9 +171,10 @@ struct fr_index {
     int mma_debug = 0;      // diagnostics (scripts/ablate_mma.py): results are wrong when non-zero
     int mma_wide_lists = 1; // k in (64, 100]: keep 256 candidates per query instead of 128
     int mma_max_lead = 6;   // K2 co-resident groups: tiles a group may run ahead of the slowest group of its stream (0 = unthrottled)
-    int mma_co_groups = 4;  // K2: query groups of 256 that share one corpus stream through L2 (measured at 100M rows,
-                            // batch 1024: 1 -> 2 groups +9 % QPS, 2 -> 4 another +1.5 %; the board is power-bound and
-                            // every HBM byte not fetched is clock for the tensor cores)
+    int mma_co_groups = 8;  // K2: at most this many query groups of 256 share one corpus stream through L2, kept together
+                            // by the lead throttle (100M rows: batch 1024 = 4 groups, one HBM pass per 1024 queries,
+                            // 14.4k -> 17.0k QPS; batch 4096 with 8 groups another +2 % over 4: the board is power-bound
+                            // and every HBM byte not fetched is clock for the tensor cores)
     DevBuf stats;           // [0] queries K2 could not certify (re-scanned by the stream kernel), cumulative
     int64_t n_searches = 0, n_queries = 0, n_mma_queries = 0;
     PinBuf pin;
