@@ -175,7 +175,7 @@ def ncu_traffic(path_kind, rows_local):
 def scan_kernel_of(batch, path, k, dtype="bf16", rows_local=None):
     """Which scan kernel a batch runs on (mirrors search_on_stream in csrc/api.cu) and the queries
     one launch of it serves."""
-    mma_ok = k <= 100 and dtype == "bf16"
+    mma_ok = k <= 100  # fp32 collections select on a bf16 copy of their rows
     use_mma = mma_ok and path in ("mma", "auto")
     if use_mma and path == "auto" and rows_local is not None:  # small shards are launch-bound: K1 is 3 launches
         if (batch == 1 and rows_local <= 2_000_000) or (batch <= 4 and rows_local <= 200_000):

@@ -156,6 +156,13 @@ struct fr_index {
     int64_t n_deleted = 0;
     uint8_t *corpus = nullptr;
     int64_t *keys = nullptr;
+    // fp32 collections (cosine, width 384): bf16 copy of the rows that the tensor-core scans SELECT from (the exact
+    // scores always come from the fp32 rows).  Built lazily on the first batched search, extended after appends,
+    // rebuilt after an in-place overwrite.
+    uint8_t *shadow = nullptr;
+    int64_t shadow_cap = 0, shadow_rows = 0;
+    bool shadow_dirty = false;
+    int mma_f32_shadow = 1;
     cudaStream_t stream = nullptr;   // host-path stream
     cudaEvent_t last_use = nullptr;  // orders scratch reuse across caller streams
     DevBuf q_raw, q_prep, q_keys, partials, out_dist, out_keys, stage_vecs, stage_keys, stage_rows;
@@ -244,6 +251,9 @@ int grow(fr_index *ix, int64_t need_rows, bool exact) {
     FR_CUDA(cudaStreamSynchronize(ix->stream));
     if (ix->corpus) cudaFree(ix->corpus);
     if (ix->keys) cudaFree(ix->keys);
+    if (ix->shadow) cudaFree(ix->shadow);  // sized for the old capacity: rebuilt on the next batched search
+    ix->shadow = nullptr;
+    ix->shadow_cap = ix->shadow_rows = 0;
     ix->corpus = nc;
     ix->keys = nk;
     ix->cap_rows = new_cap;
@@ -307,6 +317,43 @@ struct ProfScope {
 // ones in slices) at width 768 -- the multi-vector store's bert-base token vectors (multivector_store.py:70).
 // K2s reads the queries as ONE bf16 term (selection error up to |q - bf16(q)|, ~1e-3) or as TWO (hi + lo, error
 // ~1e-5: nearly every query certified at once even where thousands of rows score within 1e-2 of the best).
+bool shadow_serves(const fr_index *ix) {
+    return ix->dtype == FR_F32 && ix->mma_f32_shadow && ix->metric == FR_COSINE && ix->dim == 384;
+}
+
+// bring the bf16 selection copy of an fp32 collection up to date (stream-ordered on `s`)
+int ensure_shadow(fr_index *ix, cudaStream_t s) {
+    const size_t rb16 = static_cast<size_t>(ix->dim) * 2;
+    if (ix->shadow == nullptr || ix->shadow_cap < ix->cap_rows) {
+        if (ix->shadow) {
+            FR_CUDA(cudaStreamSynchronize(s));
+            cudaFree(ix->shadow);
+            ix->shadow = nullptr;
+        }
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ix->shadow), static_cast<size_t>(ix->cap_rows + PAD_ROWS) * rb16);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            ix->shadow_cap = ix->shadow_rows = 0;
+            return fail(FR_ENOMEM, "cannot allocate the bf16 selection copy of %lld fp32 rows: %s", (long long)ix->cap_rows,
+                        cudaGetErrorString(e));
+        }
+        ix->shadow_cap = ix->cap_rows;
+        ix->shadow_rows = 0;
+        FR_CUDA(cudaMemsetAsync(ix->shadow, 0, static_cast<size_t>(ix->cap_rows + PAD_ROWS) * rb16, s));
+    }
+    if (ix->shadow_dirty) {
+        ix->shadow_rows = 0;
+        ix->shadow_dirty = false;
+    }
+    if (ix->shadow_rows < ix->rows) {
+        const int64_t first = ix->shadow_rows;
+        FR_CUDA(fr::launch_shadow_convert(reinterpret_cast<const float *>(ix->corpus) + first * ix->dim,
+                                          ix->shadow + static_cast<size_t>(first) * rb16, (ix->rows - first) * ix->dim, s));
+        ix->shadow_rows = ix->rows;
+    }
+    return FR_OK;
+}
+
 int small_split(const fr_index *ix, int B, int ksel) {
     // two terms while they fit one MMA per K step (measured: no cost at all, profiles/r01_sweep_split_10m.jsonl);
     // always at widths without a second-chance pass (certify in the first)
@@ -319,7 +366,8 @@ bool small_serves(const fr_index *ix, int B, int ksel) {
 }
 int mma_slice(const fr_index *ix, int k) {  // 0 = not eligible, else the largest batch one pass may take
     const int ksel = fr::scan_mma_ksel(k, ix->mma_wide_lists);
-    if (ix->dtype != FR_BF16 || ix->metric != FR_COSINE || ksel == 0 || ix->rows <= 0) return 0;
+    if (ix->metric != FR_COSINE || ksel == 0 || ix->rows <= 0) return 0;
+    if (ix->dtype != FR_BF16) return shadow_serves(ix) ? 1 << 30 : 0;  // fp32 rows: selection on a bf16 copy
     if (ix->dim == 384) return 1 << 30;
     if (ix->dim != 768) return 0;  // the re-scan safety net exists for 384 and 768 only
     const int m = fr::scan_mma_small_max_batch(ksel, ix->dim, 1);
@@ -373,6 +421,7 @@ int search_stream(fr_index *ix, const float *q, int B, int k, float *d_out_dist,
 // of whatever is still open after that.
 int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_out_dist, uint64_t *d_out_packed,
                int64_t *d_out_keys, cudaStream_t s) {
+    int rc0 = FR_OK;
     const int ksel = fr::scan_mma_ksel(k, ix->mma_wide_lists);
     const int group = fr::scan_mma_group(B);
     const int nq_pad = ((B + group - 1) / group) * group;
@@ -428,8 +477,15 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     FR_CUDA(fr::launch_prep_queries(pa));
     const float *q = pa.q_prep;
 
+    const bool f32_rows = ix->dtype == FR_F32;
+    if (f32_rows) {
+        rc0 = ensure_shadow(ix, s);
+        if (rc0 != FR_OK) return rc0;
+    }
+    // |q . (c - bf16(c))| <= 2^-9 sum|q_i c_i| <= 2^-9 |q||c| for an fp32 unit row c
+    const float extra_bound = f32_rows ? 0.001953125f * 1.001f : 0.0f;
     fr::MmaScanArgs ms{};
-    ms.corpus = ix->corpus;
+    ms.corpus = f32_rows ? ix->shadow : ix->corpus;
     ms.dim = ix->dim;
     ms.keys_or_null = ix->n_deleted > 0 ? ix->keys : nullptr;
     ms.queries_bf16 = ix->q_bf16.p;
@@ -488,6 +544,8 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     ra.queries = q;
     ra.dim = ix->dim;
     ra.corpus = ix->corpus;
+    ra.f32_rows = f32_rows ? 1 : 0;
+    ra.extra_bound = extra_bound;
     ra.row_keys = ix->keys;
     ra.err_bound = split ? eb_two : eb_one;
     ra.err_alpha = split ? ea_two : ea_one;
@@ -526,6 +584,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
         rp.queries = q;
         rp.err_bound = eb_one;  // the second-chance scan reads one-term bf16 queries
         rp.err_alpha = ea_one;
+        rp.extra_bound = extra_bound;
         rp.kth_exact = ra.kth_exact;
         rp.fail_count = fail_count;
         rp.fail_list = fail_list;
@@ -594,7 +653,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     sa.queries = q;
     sa.n_rows = ix->rows;
     sa.dim = ix->dim;
-    sa.bf16 = true;
+    sa.bf16 = !f32_rows;  // the re-scan reads the rows the collection stores
     sa.l2 = false;
     sa.k = k;
     sa.nq_total = B;
@@ -650,7 +709,7 @@ int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *
     const bool eligible = mma_eligible(ix, k);
     if (ix->path == FR_PATH_MMA && !eligible)
         return fail(FR_EUNSUP,
-                    "FR_PATH_MMA serves bf16 cosine collections of width 384 (k <= 100) or 768 (k <= 32) with at least one row "
+                    "FR_PATH_MMA serves cosine collections of width 384 (bf16 or fp32 rows, k <= 100) or 768 (bf16, k <= 32) with at least one row "
                     "(this one: dtype %d, dim %d, metric %d, k %d, rows %lld)",
                     ix->dtype, ix->dim, ix->metric, k, (long long)ix->rows);
     const bool k2s = eligible && small_serves(ix, B, fr::scan_mma_ksel(k, ix->mma_wide_lists));
@@ -694,11 +753,13 @@ uint64_t state_hash(const fr_index *ix) {
     for (const DevBuf *b : bufs) mix(reinterpret_cast<uintptr_t>(b->p));
     mix(reinterpret_cast<uintptr_t>(ix->pin.p));
     mix(reinterpret_cast<uintptr_t>(ix->corpus));
+    mix(reinterpret_cast<uintptr_t>(ix->shadow));
+    mix(static_cast<uint64_t>(ix->shadow_rows) * 2u + (ix->shadow_dirty ? 1u : 0u));
     mix(reinterpret_cast<uintptr_t>(ix->keys));
     mix(static_cast<uint64_t>(ix->rows));
     mix(ix->n_deleted > 0 ? 1u : 0u);
     for (int v : {ix->path, ix->mma_min_batch, ix->mma_small_max, ix->mma_co_groups, ix->mma_split, ix->mma_split_max,
-                  ix->mma_debug, ix->mma_bound_scale_pct, ix->mma_max_lead, ix->mma_wide_lists})
+                  ix->mma_debug, ix->mma_bound_scale_pct, ix->mma_max_lead, ix->mma_wide_lists, ix->mma_f32_shadow})
         mix(static_cast<uint64_t>(static_cast<int64_t>(v)));
     mix(static_cast<uint64_t>(ix->small_rows_b1));
     mix(static_cast<uint64_t>(ix->small_rows_b4));
@@ -770,6 +831,7 @@ int fr_index_destroy(fr_index *ix) {
         DeviceGuard g(ix->device);
         cudaDeviceSynchronize();
         drop_graphs(ix);
+        if (ix->shadow) cudaFree(ix->shadow);
         if (ix->corpus) cudaFree(ix->corpus);
         if (ix->keys) cudaFree(ix->keys);
         DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist,
@@ -809,6 +871,10 @@ int fr_index_set_option(fr_index *ix, const char *name, int64_t value) {
     if (std::strcmp(name, "mma_co_groups") == 0) {
         if (value < 1 || value > 8) return fail(FR_EINVAL, "mma_co_groups must be in [1, 8]");
         ix->mma_co_groups = static_cast<int>(value);
+        return FR_OK;
+    }
+    if (std::strcmp(name, "mma_f32_shadow") == 0) {
+        ix->mma_f32_shadow = value != 0;
         return FR_OK;
     }
     if (std::strcmp(name, "mma_wide_lists") == 0) {
@@ -977,6 +1043,7 @@ int fr_index_upsert(fr_index *ix, const float *vecs, const int64_t *keys, int64_
         ix->keymap_valid = false;
         return fail(FR_EUNSUP, "a shard holds at most 2^32-16 rows");
     }
+    if (static_cast<int64_t>(last_writer.size()) != new_rows - ix->rows) ix->shadow_dirty = true;  // an existing row is overwritten
     rc = grow(ix, new_rows, false);
     if (rc != FR_OK) {
         ix->keymap_valid = false;  // the map now names rows that were never written

@@ -101,7 +101,9 @@ struct RescoreArgs {
     int ksel;
     const float *queries;  // [B][dim] fp32 prepared queries
     int dim;
-    const uint8_t *corpus;
+    const uint8_t *corpus;   // the rows the collection stores: bf16, or fp32 when f32_rows
+    int f32_rows;            // the scan read a bf16 copy of fp32 rows: exact scores come from the fp32 rows, and
+    float extra_bound;       // the copy's rounding (<= 2^-9 sum|q_i c_i| <= 2^-9) widens the certification bound
     const int64_t *row_keys;
     const float *err_bound;  // [B] |e|_2, e = q - (what the scan read)
     const float *err_alpha;  // [B] |e . q|
@@ -130,6 +132,7 @@ struct RetryPrepArgs {
     const float *queries;     // [B][384] fp32 prepared queries
     const float *err_bound;   // [B] |q - bf16(q)|_2 (the second-chance scan reads plain bf16 queries)
     const float *err_alpha;   // [B] |(q - bf16(q)) . q|
+    float extra_bound;        // see RescoreArgs
     const float *kth_exact;   // [B]
     const int *fail_count;    // first-pass failures
     const int *fail_list;
@@ -187,6 +190,8 @@ struct IngestArgs {
 };
 cudaError_t launch_ingest(const IngestArgs &a);
 cudaError_t launch_fill_keys(int64_t *keys, const int64_t *rows, int64_t n, int64_t value, cudaStream_t s);
+// fp32 rows -> bf16 (RNE): the selection copy of an fp32 collection the tensor-core scans read (n_elems % 8 == 0)
+cudaError_t launch_shadow_convert(const float *src, void *dst_bf16, int64_t n_elems, cudaStream_t s);
 
 // ---- K5 rrf_fuse -------------------------------------------------------------------------------
 struct RrfArgs {

@@ -75,6 +75,31 @@ cudaError_t launch_ingest(const IngestArgs &a) {
     return cudaGetLastError();
 }
 
+// fp32 rows -> bf16 (RNE), 8 elements per thread: the selection copy ("shadow") of an fp32 collection
+__global__ void shadow_convert_kernel(const float4 *__restrict__ src, uint4 *__restrict__ dst, int64_t n8) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const float4 a = src[2 * i], b = src[2 * i + 1];
+    const __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    const __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 o;
+    o.x = *reinterpret_cast<const uint32_t *>(&p0);
+    o.y = *reinterpret_cast<const uint32_t *>(&p1);
+    o.z = *reinterpret_cast<const uint32_t *>(&p2);
+    o.w = *reinterpret_cast<const uint32_t *>(&p3);
+    dst[i] = o;
+}
+
+cudaError_t launch_shadow_convert(const float *src, void *dst_bf16, int64_t n_elems, cudaStream_t s) {
+    if (n_elems <= 0) return cudaSuccess;
+    if (n_elems % 8 != 0) return cudaErrorInvalidValue;
+    const int64_t n8 = n_elems / 8;
+    shadow_convert_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4 *>(src),
+                                                                               static_cast<uint4 *>(dst_bf16), n8);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fill_keys(int64_t *keys, const int64_t *rows, int64_t n, int64_t value, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     fill_keys_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(keys, rows, n, value);

@@ -626,7 +626,7 @@ __device__ __forceinline__ float selection_error_bound(float t, float e_norm, fl
 //   second pass: CTA j < *limit handles query idx_list[j], whose selection list (sel[j]) was collected above the
 //                fixed threshold tau0[j].  A list that did not fill up holds EVERY row above tau0[j]; everything
 //                else scores at most tau0[j] + bound, so the query is certified iff its k-th exact score beats that.
-template <int KPL>
+template <int KPL, bool F32ROWS>
 __global__ void __launch_bounds__(256)
 rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restrict__ queries,
                const uint8_t *__restrict__ corpus, const int64_t *__restrict__ row_keys,
@@ -634,7 +634,8 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
                uint64_t *__restrict__ out_packed, int64_t *__restrict__ out_keys, uint8_t *__restrict__ flags,
                int *__restrict__ fail_count, int *__restrict__ fail_list, unsigned long long *__restrict__ fail_total,
                float *__restrict__ kth_exact_out, const int *__restrict__ idx_list, const int *__restrict__ limit,
-               const float *__restrict__ tau0, int dim, unsigned long long *__restrict__ fail_total2, float acc_slack) {
+               const float *__restrict__ tau0, int dim, unsigned long long *__restrict__ fail_total2, float acc_slack,
+               float extra_bound) {
     __shared__ float sq[RESCORE_MAX_DIM];
     __shared__ uint64_t exact[32 * KPL];
     const int j_cta = blockIdx.x;
@@ -650,16 +651,28 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
         const uint64_t key = s[j];
         if (key == 0ull) continue;  // warp-uniform
         const uint32_t row = key_row(key);
-        // 8-byte pieces (4 bf16) of the row, lane-strided: coalesced 256 bytes per warp step
-        const uint2 *rp = reinterpret_cast<const uint2 *>(corpus + static_cast<size_t>(row) * (static_cast<size_t>(dim) * 2));
         float acc = 0.0f;
-        for (int c = lane; c < dim / 4; c += 32) {
-            const uint2 w = rp[c];
-            const float *qq = sq + c * 4;
-            acc = fmaf(__uint_as_float(w.x << 16), qq[0], acc);
-            acc = fmaf(__uint_as_float(w.x & 0xffff0000u), qq[1], acc);
-            acc = fmaf(__uint_as_float(w.y << 16), qq[2], acc);
-            acc = fmaf(__uint_as_float(w.y & 0xffff0000u), qq[3], acc);
+        if constexpr (F32ROWS) {  // fp32 collection: the exact score is taken from the fp32 row, 16 bytes per lane and step
+            const float4 *rp = reinterpret_cast<const float4 *>(corpus + static_cast<size_t>(row) * (static_cast<size_t>(dim) * 4));
+            for (int c = lane; c < dim / 4; c += 32) {
+                const float4 w = rp[c];
+                const float *qq = sq + c * 4;
+                acc = fmaf(w.x, qq[0], acc);
+                acc = fmaf(w.y, qq[1], acc);
+                acc = fmaf(w.z, qq[2], acc);
+                acc = fmaf(w.w, qq[3], acc);
+            }
+        } else {
+            // 8-byte pieces (4 bf16) of the row, lane-strided: coalesced 256 bytes per warp step
+            const uint2 *rp = reinterpret_cast<const uint2 *>(corpus + static_cast<size_t>(row) * (static_cast<size_t>(dim) * 2));
+            for (int c = lane; c < dim / 4; c += 32) {
+                const uint2 w = rp[c];
+                const float *qq = sq + c * 4;
+                acc = fmaf(__uint_as_float(w.x << 16), qq[0], acc);
+                acc = fmaf(__uint_as_float(w.x & 0xffff0000u), qq[1], acc);
+                acc = fmaf(__uint_as_float(w.y << 16), qq[2], acc);
+                acc = fmaf(__uint_as_float(w.y & 0xffff0000u), qq[3], acc);
+            }
         }
 #pragma unroll
         for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, sft);
@@ -688,7 +701,10 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
     // products) covers the fp32 accumulation orders of the two kernels.
     const uint64_t last_sel = s[ksel - 1];
     const float kth_exact = n_valid >= k ? key_score(lst.kth(k)) : -INFINITY;
-    const float floor_sel = kth_exact - selection_error_bound(kth_exact, err_bound[b], err_alpha[b]) - acc_slack;
+    // (extra_bound: the scan scored a bf16 copy c16 of an fp32 row c; q . (c - c16) is at most 2^-9 sum|q_i c_i|, so a
+    //  row whose exact score reaches t scores at least t - extra_bound against the query on the copy)
+    const float t_copy = kth_exact - extra_bound;
+    const float floor_sel = t_copy - selection_error_bound(t_copy, err_bound[b], err_alpha[b]) - acc_slack;
     bool certified = true;
     if (last_sel != 0ull) {                       // list full: ceiling = the k'-th selection score
         certified = n_valid >= k && floor_sel > key_score(last_sel);
@@ -733,7 +749,8 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
 // One CTA per retry slot; slot j belongs to slice j / RETRY_MAX, which is one more launch of the scan kernel
 // (its own query block, thresholds and live count retry_n[slice]; an empty slice's launches exit at once).
 __global__ void retry_prep_kernel(const float *__restrict__ queries, const float *__restrict__ err_bound,
-                                  const float *__restrict__ err_alpha, const float *__restrict__ kth_exact, const int *__restrict__ fail_count,
+                                  const float *__restrict__ err_alpha, float extra_bound,
+                                  const float *__restrict__ kth_exact, const int *__restrict__ fail_count,
                                   const int *__restrict__ fail_list, __nv_bfloat16 *__restrict__ qb_retry,
                                   float *__restrict__ tau0, int *__restrict__ retry_n, uint32_t *__restrict__ tau_g_retry,
                                   int ksel, uint8_t *__restrict__ flags) {
@@ -753,7 +770,8 @@ __global__ void retry_prep_kernel(const float *__restrict__ queries, const float
     for (int e = lane; e < DIM; e += 32)
         qb_retry[static_cast<size_t>(j) * DIM + e] = __float2bfloat16_rn(on ? queries[static_cast<size_t>(b) * DIM + e] : 0.0f);
     if (lane == 0) {
-        tau0[j] = on ? kth_exact[b] - selection_error_bound(kth_exact[b], err_bound[b], err_alpha[b]) - 2e-5f : INFINITY;
+        const float t_copy = on ? kth_exact[b] - extra_bound : 0.0f;
+        tau0[j] = on ? t_copy - selection_error_bound(t_copy, err_bound[b], err_alpha[b]) - 2e-5f : INFINITY;
         if (on) flags[b] = 1;  // stays flagged until the second rescore pass certifies it
     }
 }
@@ -869,16 +887,24 @@ cudaError_t launch_scan_mma(const MmaScanArgs &a) {
 cudaError_t launch_rescore(const RescoreArgs &a) {
     if (a.B <= 0) return cudaSuccess;
     if (a.dim > mma::RESCORE_MAX_DIM || a.dim % 4 != 0) return cudaErrorInvalidValue;
-#define FR_RESCORE(KPL)                                                                                       \
-    mma::rescore_kernel<KPL><<<a.B, 256, 0, a.stream>>>(a.sel, a.ksel, a.queries, a.corpus, a.row_keys, a.err_bound, \
-                                                       a.err_alpha, a.k, a.out_dist, a.out_packed, a.out_keys, a.flags, \
-                                                       a.fail_count, a.fail_list, a.fail_total, a.kth_exact,     \
-                                                       a.idx_list, a.limit, a.tau0, a.dim, a.fail_total2,        \
-                                                       1e-5f * static_cast<float>(((a.dim + 383) / 384) * (1 + a.split)))
+#define FR_RESCORE_T(KPL, F32)                                                                                 \
+    mma::rescore_kernel<KPL, F32><<<a.B, 256, 0, a.stream>>>(a.sel, a.ksel, a.queries, a.corpus, a.row_keys,        \
+                                                            a.err_bound, a.err_alpha, a.k, a.out_dist, a.out_packed, \
+                                                            a.out_keys, a.flags, a.fail_count, a.fail_list,        \
+                                                            a.fail_total, a.kth_exact, a.idx_list, a.limit, a.tau0, \
+                                                            a.dim, a.fail_total2,                                   \
+                                                            1e-5f * static_cast<float>(((a.dim + 383) / 384) * (1 + a.split)), \
+                                                            a.extra_bound)
+#define FR_RESCORE(KPL)                  \
+    do {                                 \
+        if (a.f32_rows) FR_RESCORE_T(KPL, true); \
+        else FR_RESCORE_T(KPL, false);   \
+    } while (0)
     if (a.ksel <= 32) FR_RESCORE(1);
     else if (a.ksel <= 64) FR_RESCORE(2);
     else if (a.ksel <= 128) FR_RESCORE(4);
     else FR_RESCORE(8);
+#undef FR_RESCORE_T
 #undef FR_RESCORE
     count_launch();
     return cudaGetLastError();
@@ -891,7 +917,7 @@ int scan_mma_retry_ksel(int ksel) { return ksel >= 128 ? 256 : 128; }
 
 cudaError_t launch_retry_prep(const RetryPrepArgs &a) {
     if (a.slices <= 0) return cudaSuccess;
-    mma::retry_prep_kernel<<<a.slices * mma::RETRY_MAX, 32, 0, a.stream>>>(a.queries, a.err_bound, a.err_alpha, a.kth_exact, a.fail_count,
+    mma::retry_prep_kernel<<<a.slices * mma::RETRY_MAX, 32, 0, a.stream>>>(a.queries, a.err_bound, a.err_alpha, a.extra_bound, a.kth_exact, a.fail_count,
                                                                          a.fail_list, static_cast<__nv_bfloat16 *>(a.qb_retry),
                                                                          a.tau0, a.retry_n, a.tau_g_retry, a.ksel, a.flags);
     count_launch();

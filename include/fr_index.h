@@ -82,7 +82,9 @@ int fr_index_set_option(fr_index *idx, const char *name, int64_t value);
  * "mma_split_max", "use_graphs" (host search replays a captured CUDA graph on small collections; default 1),
  * "graph_max_bytes", "small_rows_b1" / "small_rows_b4" (FR_PATH_AUTO: collections up to this many rows send
  * batch 1 / batch <= 4 to the 3-launch streaming kernel), "mma_bound_scale_pct" (diagnostics: inflate the
- * certification bounds).  Further stat: "graph_replays". */
+ * certification bounds), "mma_wide_lists", "mma_max_lead", "mma_f32_shadow" (fp32 cosine collections of width 384:
+ * tensor-core scans select on a lazily built bf16 copy of the rows, +50 % memory; default 1).
+ * Further stat: "graph_replays". */
 int fr_index_get_stat(fr_index *idx, const char *name, int64_t *out);
 
 /* Replaces Collection.count()                     parent_child/chroma_child_store.py:76-80

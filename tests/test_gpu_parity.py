@@ -665,6 +665,53 @@ def test_scheduling_options_do_not_change_results(frb):
     ix.close()
 
 
+@pytest.mark.parametrize("B,k", [(2, 10), (24, 10), (200, 10), (300, 50)])
+def test_f32_collection_batched_search_selects_on_a_bf16_copy(frb, B, k):
+    """fp32 collections (the storage that keeps scores within 1e-5): batches run on the tensor cores against a lazily
+    built bf16 copy of the rows, every result is rescored on the fp32 rows and certified with the copy's rounding in
+    the bound.  Same answer as the CUDA-core stream kernel, through appends, in-place overwrites and deletes."""
+    from financial_rag_b200._lib import FrError
+
+    n = 30000
+    corpus = make_corpus(n, 384, seed=7100 + B, dup_pairs=[(21, 17000)])
+    queries = make_queries(B, corpus, seed=7101 + k)
+    queries[1] = corpus[21]
+    ix = build_index(frb, corpus[:20000], "cosine", "f32")
+    ix.set_option("small_rows_b4", 0)  # keep batch 2 on the tensor-core path for this test
+    ix.set_path("mma")
+    ix.search(queries, k)                       # builds the copy for the first 20000 rows ...
+    ix.upsert(corpus[20000:], np.arange(20000, n, dtype=np.int64) + KEY_BASE)  # ... an append extends it
+    for round_ in range(3):
+        ix.set_path("stream")
+        d_s, k_s = ix.search(queries, k)
+        ix.set_path("mma")
+        d_m, k_m = ix.search(queries, k)
+        assert ix.stat("mma_queries") >= B
+        np.testing.assert_allclose(d_m, d_s, rtol=0, atol=2e-6)
+        mism = k_m != k_s
+        if mism.any():
+            assert np.abs(d_m[mism] - d_s[mism]).max() <= 2e-6
+        live = None
+        if round_ == 2:
+            live = np.ones(n, bool)
+            live[victims - KEY_BASE] = False
+        assert_matches_oracle(d_m, keys_to_rows(k_m, KEY_BASE), queries, corpus, k, "cosine", "f32", stored=stored_rows(ix),
+                              live=live, strict=True, label=f"f32 on the tensor cores B={B} k={k} round {round_}")
+        if round_ == 0:
+            assert keys_to_rows(k_m[1], KEY_BASE)[0] == 21 and keys_to_rows(k_m[1], KEY_BASE)[1] == 17000
+            # overwrite a row in place with query 0's direction: the copy must follow
+            corpus[12345] = queries[0] * 2.0
+            ix.upsert(corpus[12345:12346], np.array([12345 + KEY_BASE], dtype=np.int64))
+        elif round_ == 1:
+            assert keys_to_rows(k_m[0], KEY_BASE)[0] == 12345
+            victims = np.unique(k_m[:, 0])
+            ix.delete(victims)
+    ix.set_option("mma_f32_shadow", 0)
+    with pytest.raises(FrError):
+        ix.search(queries, k)  # FR_PATH_MMA without the copy: not served
+    ix.close()
+
+
 def make_clustered(n, centres, spread, seed):
     """Rows = centre + spread * noise: hundreds of rows score within 1e-2 of a query's best hits, like the chunks of
     one document family in a real collection (isotropic Gaussian rows never do)."""
@@ -818,7 +865,7 @@ def test_mma_path_with_deletes_and_eligibility(frb):
     with pytest.raises(FrError):
         ix.search(queries, 101)
     ix.close()
-    for kw in ({"dtype": "f32"}, {"space": "l2"}, {"dim": 128}):
+    for kw in ({"dtype": "f32", "dim": 768}, {"space": "l2"}, {"dim": 128}):
         args = {"dim": 384, "space": "cosine", "dtype": "bf16"}
         args.update(kw)
         jx = frb.ShardIndex(**args)
