@@ -421,7 +421,6 @@ int search_stream(fr_index *ix, const float *q, int B, int k, float *d_out_dist,
 // of whatever is still open after that.
 int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_out_dist, uint64_t *d_out_packed,
                int64_t *d_out_keys, cudaStream_t s) {
-    int rc0 = FR_OK;
     const int ksel = fr::scan_mma_ksel(k, ix->mma_wide_lists);
     const int group = fr::scan_mma_group(B);
     const int nq_pad = ((B + group - 1) / group) * group;
@@ -477,11 +476,9 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     FR_CUDA(fr::launch_prep_queries(pa));
     const float *q = pa.q_prep;
 
-    const bool f32_rows = ix->dtype == FR_F32;
-    if (f32_rows) {
-        rc0 = ensure_shadow(ix, s);
-        if (rc0 != FR_OK) return rc0;
-    }
+    const bool f32_rows = ix->dtype == FR_F32;  // search_on_stream has brought the bf16 copy up to date
+    if (f32_rows && (ix->shadow == nullptr || ix->shadow_rows != ix->rows || ix->shadow_dirty))
+        return fail(FR_ECUDA, "internal: the bf16 selection copy is not up to date");
     // |q . (c - bf16(c))| <= 2^-9 sum|q_i c_i| <= 2^-9 |q||c| for an fp32 unit row c
     const float extra_bound = f32_rows ? 0.001953125f * 1.001f : 0.0f;
     fr::MmaScanArgs ms{};
@@ -716,8 +713,18 @@ int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *
     // small collections are launch-bound, not bandwidth-bound: K1 is 3 launches, the tensor-core path 11+
     // (scripts/latency_small.py: batch 1 over 1M rows 148 vs 165 us, over 10k rows 25 vs 53 us)
     const bool launch_bound = (B == 1 && ix->rows <= ix->small_rows_b1) || (B <= 4 && ix->rows <= ix->small_rows_b4);
-    const bool use_mma = eligible && (ix->path == FR_PATH_MMA ||
+    bool use_mma = eligible && (ix->path == FR_PATH_MMA ||
                                       (ix->path == FR_PATH_AUTO && !launch_bound && (B >= ix->mma_min_batch || k2s)));
+    if (use_mma && ix->dtype == FR_F32) {
+        // fp32 rows: the tensor-core scans need their bf16 copy.  If it cannot be allocated (a shard that fills the
+        // HBM on its own) FR_PATH_AUTO stops asking for it and stays on the stream kernel.
+        const int rs = ensure_shadow(ix, s);
+        if (rs != FR_OK) {
+            if (ix->path != FR_PATH_AUTO) return rs;
+            ix->mma_f32_shadow = 0;
+            use_mma = false;
+        }
+    }
     if (use_mma) return search_mma(ix, d_queries, B, k, d_out_dist, d_out_packed, d_out_keys, s);
     const size_t qbytes = static_cast<size_t>(B) * ix->dim * sizeof(float);
     const float *q = d_queries;
