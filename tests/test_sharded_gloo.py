@@ -79,11 +79,21 @@ def _worker(rank, world, port, out_dir):
                     s.out_dist[i, j] = float("inf")
                     s.out_keys[i, j] = -1
 
+    # a searcher sized for a larger batch exchanges only the lists of the batch at hand and gives the same answer
+    big = ShardedSearcher(FakeIndex(), K, B + 5, device=torch.device("cpu"), local_search=local_search, merge=merge)
+    holder["s"] = big
+    q = torch.from_numpy(queries)
+    d_big, kk_big = big.search_device(q)
+    assert big.local.shape == (2, B * K) and big.gathered.shape == (world, 2, B * K)
+    d_big, kk_big = d_big.clone(), kk_big.clone()
+    d_one, kk_one = big.search_device(q[:1])
+    assert big.local.shape == (2, K) and torch.equal(kk_one[0], kk_big[0])
+    assert torch.allclose(d_one[0], d_big[0], rtol=0, atol=1e-6)  # (numpy's gemv vs gemm: last-bit differences)
     s = ShardedSearcher(FakeIndex(), K, B, device=torch.device("cpu"), local_search=local_search, merge=merge)
     holder["s"] = s
-    q = torch.from_numpy(queries)
     d, kk = s.search_device(q)
     d, kk = d.clone(), kk.clone()
+    assert torch.equal(kk, kk_big) and torch.equal(d, d_big)
     # host path: only rank 0 owns the query block; the others receive it through the broadcast
     q_dev = torch.zeros_like(q)
     od, ok = torch.zeros((B, K)), torch.zeros((B, K), dtype=torch.int64)
