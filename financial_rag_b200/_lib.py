@@ -18,7 +18,8 @@ FR_BF16, FR_F32 = 0, 1
 FR_PATH_AUTO, FR_PATH_STREAM, FR_PATH_MMA = 0, 1, 2
 FR_MAX_K = 128
 FR_KEY_NONE = -1
-FR_ABI_VERSION = 1
+FR_ABI_VERSION = 2
+FR_XCHG_AUTO, FR_XCHG_NCCL, FR_XCHG_COPY = 0, 1, 2
 
 # every symbol include/fr_index.h declares: name -> (restype, argtypes)
 SYMBOLS = {
@@ -45,9 +46,32 @@ SYMBOLS = {
     "fr_index_search_partial_device": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "fr_merge_shards_device": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                        c_void_p, c_void_p, c_void_p]),
+    "fr_nccl_load": (c_int, [c_char_p]),
+    "fr_nccl_version": (c_int, [POINTER(c_int)]),
+    "fr_nccl_unique_id": (c_int, [c_void_p, c_int]),
+    "fr_group_create": (c_int, [c_int, c_int, c_int, POINTER(c_int), c_int, c_int, c_int, c_void_p, c_int, c_int64,
+                                POINTER(c_void_p)]),
+    "fr_group_destroy": (c_int, [c_void_p]),
+    "fr_group_info": (c_int, [c_void_p, c_char_p, POINTER(c_int64)]),
+    "fr_group_set_option": (c_int, [c_void_p, c_char_p, c_int64]),
+    "fr_group_reserve": (c_int, [c_void_p, c_int64]),
+    "fr_group_shard": (c_int, [c_void_p, c_int, POINTER(c_void_p)]),
+    "fr_group_adopt_rows": (c_int, [c_void_p, c_int64]),
+    "fr_group_count": (c_int, [c_void_p, POINTER(c_int64)]),
+    "fr_group_rows": (c_int, [c_void_p, POINTER(c_int64)]),
+    "fr_group_upsert": (c_int, [c_void_p, c_void_p, c_void_p, c_int64]),
+    "fr_group_delete": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int64)]),
+    "fr_group_get_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "fr_group_export_raw": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "fr_group_import_raw": (c_int, [c_void_p, c_void_p, c_void_p, c_int64]),
+    "fr_group_lookup_rows": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "fr_group_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "fr_group_search_device": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "fr_rrf_fuse": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "fr_rrf_fuse_device": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p]),
+    "fr_score_fuse": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "fr_score_fuse_device": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "fr_maxsim_aggregate": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "fr_maxsim_aggregate_device": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                            c_void_p, c_void_p]),
@@ -84,6 +108,35 @@ def load() -> ctypes.CDLL:
         raise ImportError(f"libfrb200.so has ABI version {got}, binding expects {FR_ABI_VERSION}")
     _lib = lib
     return lib
+
+
+_nccl_bound = False
+
+
+def ensure_nccl() -> None:
+    """Bind NCCL for the row-sharded groups (fr_group).  The library binds at run time (dlopen) so that the process
+    holds ONE copy of NCCL: torch's bundled libnccl.so.2 when torch is (or will be) imported, else the system's."""
+    global _nccl_bound
+    if _nccl_bound:
+        return
+    import sys
+
+    lib = load()
+    path = None
+    if "torch" not in sys.modules:  # with torch loaded, its copy is found by soname
+        try:
+            import importlib.util
+
+            spec = importlib.util.find_spec("nvidia.nccl")
+            for loc in (spec.submodule_search_locations if spec else []):
+                cand = os.path.join(loc, "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    path = cand
+                    break
+        except Exception:  # noqa: BLE001 - no bundled copy: the system's is next
+            path = None
+    check(lib.fr_nccl_load(path.encode() if path else None))
+    _nccl_bound = True
 
 
 def check(rc: int) -> None:

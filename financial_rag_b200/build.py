@@ -16,7 +16,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libfrb200.so")
-SOURCES = ["api.cu", "scan_stream.cu", "scan_mma.cu", "scan_mma_small.cu", "merge_topk.cu", "ingest.cu", "rrf.cu", "maxsim.cu"]
+SOURCES = ["api.cu", "scan_stream.cu", "scan_mma.cu", "scan_mma_small.cu", "merge_topk.cu", "ingest.cu", "rrf.cu", "maxsim.cu",
+           "group.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -65,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static"]
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

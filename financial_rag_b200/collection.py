@@ -36,6 +36,7 @@ from typing import Any, Dict, List, Optional, Sequence
 
 import numpy as np
 
+from .group import ShardGroup, parse_devices
 from .index import FR_MAX_K, ShardIndex, canonical_space
 
 _INT64_MAX = (1 << 63) - 1
@@ -67,7 +68,11 @@ def _as_matrix(embeddings, dim: Optional[int]) -> np.ndarray:
 
 class B200Collection:
     def __init__(self, name: str, metadata: Optional[Dict[str, Any]] = None, *, dtype: Optional[str] = None,
-                 device: Optional[int] = None, directory: Optional[str] = None):
+                 device: Optional[int] = None, directory: Optional[str] = None,
+                 devices: Optional[Sequence[int]] = None):
+        """``devices`` (or ``B200_CHILD_DEVICES=0,1,...|all``): row-shard the collection over these GPUs (SURVEY.md 8e:
+        cyclic placement, local top-k per GPU, NCCL all-gather, merge kernel) -- same calls, same answers as on one GPU.
+        Without it the collection is one shard on ``device`` / ``B200_CHILD_DEVICE``."""
         self.name = name
         self.directory = directory          # <persist_dir>/<name>.b200, None = memory only
         self._persisted_rows = 0            # rows already in rows.bin / keys.bin
@@ -77,6 +82,11 @@ class B200Collection:
         self.space = canonical_space(self.metadata.get("hnsw:space"))
         self.dtype = dtype or os.getenv("B200_CHILD_DTYPE", "bf16")
         self.device = int(os.getenv("B200_CHILD_DEVICE", "0")) if device is None else int(device)
+        if devices is None and device is None:
+            devices = parse_devices(os.getenv("B200_CHILD_DEVICES"))
+        self.devices: Optional[List[int]] = [int(d) for d in devices] if devices else None
+        if self.devices and len(self.devices) == 1:
+            self.device, self.devices = self.devices[0], None
         self._index: Optional[ShardIndex] = None  # created at first upsert: the dimension is not known before
         self._lock = threading.RLock()
         self._key_of_id: Dict[str, int] = {}
@@ -107,8 +117,13 @@ class B200Collection:
 
     def _ensure_index(self, dim: int, reserve_rows: int = 0) -> ShardIndex:
         if self._index is None:
-            self._index = ShardIndex(dim=dim, space=self.space, dtype=self.dtype, device=self.device,
-                                     reserve_rows=reserve_rows)
+            if self.devices:  # one process, several GPUs: the row-sharded group behind the same calls
+                self._index = ShardGroup(dim=dim, space=self.space, dtype=self.dtype, devices=self.devices,
+                                         reserve_rows=reserve_rows,
+                                         exchange=os.getenv("B200_CHILD_EXCHANGE", "auto").strip().lower())
+            else:
+                self._index = ShardIndex(dim=dim, space=self.space, dtype=self.dtype, device=self.device,
+                                         reserve_rows=reserve_rows)
         return self._index
 
     # -- chromadb.Collection surface -------------------------------------------------------------
@@ -355,7 +370,8 @@ class B200Collection:
             self._dirty_payload.clear()
 
     @classmethod
-    def load(cls, directory: str, *, device: Optional[int] = None) -> "B200Collection":
+    def load(cls, directory: str, *, device: Optional[int] = None,
+             devices: Optional[Sequence[int]] = None) -> "B200Collection":
         """Reopen a persisted collection: mmap the shard files, one H2D copy, payload from sqlite.
         Rows deleted before the flush are dropped on the way in (the shard comes back compacted, in the
         same insertion order), after which the files are rewritten to match."""
@@ -364,7 +380,7 @@ class B200Collection:
         if meta.get("format") != FORMAT_VERSION:
             raise ValueError(f"{directory}: unknown shard format {meta.get('format')!r}")
         col = cls(meta["name"], meta.get("metadata") or {"hnsw:space": meta["space"]}, dtype=meta["dtype"],
-                  device=device, directory=directory)
+                  device=device, directory=directory, devices=devices)
         col._next_synthetic = int(meta.get("next_synthetic", -2))
         n_rows, dim = int(meta["rows"]), meta.get("dim")
         _, rows_p, keys_p, pay_p = col._paths()
@@ -438,7 +454,7 @@ class B200Client:
             if col is None:
                 d = self._dir_of(name)
                 if os.path.exists(os.path.join(d, "meta.json")):
-                    col = B200Collection.load(d, device=kw.get("device"))  # restart: mmap + H2D
+                    col = B200Collection.load(d, device=kw.get("device"), devices=kw.get("devices"))  # restart: mmap + H2D
                 else:
                     col = B200Collection(name, metadata, directory=d, **kw)
                 _REGISTRY[key] = col

@@ -18,12 +18,17 @@
 
 #include "../../include/fr_index.h"
 #include "fr_common.cuh"
+#include "fr_host.h"
 #include "fr_kernels.h"
 
 namespace {
-
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
+std::mutex g_dev_mu;
+fr::DevInfo g_dev[64];
+}  // namespace
+
+namespace fr {
 
 int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -34,78 +39,6 @@ int fail(int code, const char *fmt, ...) {
     g_last_error = buf;
     return code;
 }
-
-#define FR_CUDA(expr)                                                                          \
-    do {                                                                                       \
-        cudaError_t _e = (expr);                                                               \
-        if (_e != cudaSuccess)                                                                 \
-            return fail(_e == cudaErrorMemoryAllocation ? FR_ENOMEM : FR_ECUDA, "%s failed: %s (%s:%d)", #expr, \
-                        cudaGetErrorString(_e), __FILE__, __LINE__);                           \
-    } while (0)
-
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = false;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        ok = cudaSetDevice(dev) == cudaSuccess;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
-// grow-only device / pinned buffers
-struct DevBuf {
-    void *p = nullptr;
-    size_t bytes = 0;
-    cudaError_t need(size_t n) {
-        if (n <= bytes) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-        size_t want = n + n / 4;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            want = n;
-            e = cudaMalloc(&p, want);
-        }
-        if (e == cudaSuccess) bytes = want;
-        return e;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-    }
-};
-struct PinBuf {
-    void *p = nullptr;
-    size_t bytes = 0;
-    cudaError_t need(size_t n) {
-        if (n <= bytes) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        bytes = 0;
-        cudaError_t e = cudaMallocHost(&p, n + n / 4);
-        if (e == cudaSuccess) bytes = n + n / 4;
-        return e;
-    }
-    void release() {
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        bytes = 0;
-    }
-};
-
-// cudaGetDeviceProperties costs milliseconds; the answer never changes, so ask once per device.
-struct DevInfo {
-    int state = 0;  // 0 unknown, 1 ok, -1 not sm_100
-    int sm_count = 0, major = 0, minor = 0;
-};
-std::mutex g_dev_mu;
-DevInfo g_dev[64];
 
 int check_device(int device, int *sm_count) {
     std::lock_guard<std::mutex> lk(g_dev_mu);
@@ -139,6 +72,16 @@ int check_device(int device, int *sm_count) {
     if (sm_count) *sm_count = d.sm_count;
     return FR_OK;
 }
+
+}  // namespace fr
+
+namespace {
+
+using fr::check_device;
+using fr::DevBuf;
+using fr::DeviceGuard;
+using fr::fail;
+using fr::PinBuf;
 
 constexpr int64_t PAD_ROWS = 32;
 
@@ -788,6 +731,39 @@ int check_search_args(fr_index *ix, const void *q, int B, int k, const void *o1,
     return FR_OK;
 }
 
+// Host forms of the fusion / aggregation kernels: grow-only staging per device (a store object is constructed per
+// request, rag_backend.py:611-643 -- allocating device memory and a stream per call cost more than the kernel).
+struct FuseScratch {
+    std::mutex mu;
+    DevBuf in_a, in_b, out_a, out_b;
+    cudaStream_t s = nullptr;
+};
+FuseScratch g_fuse[64];
+
+// in_a / in_b: host inputs (in_b may be NULL) -> device; run(d_in_a, d_in_b, d_out_a, d_out_b, stream); outputs back.
+template <typename Run>
+int fuse_on_device(int device, const void *in_a, size_t in_a_bytes, const void *in_b, size_t in_b_bytes, void *out_a,
+                          void *out_b, size_t out_bytes, Run run) {
+    int rc = check_device(device, nullptr);
+    if (rc != FR_OK) return rc;
+    DeviceGuard g(device);
+    FuseScratch &fs = g_fuse[device];
+    std::lock_guard<std::mutex> lk(fs.mu);
+    if (!fs.s) FR_CUDA(cudaStreamCreateWithFlags(&fs.s, cudaStreamNonBlocking));
+    FR_CUDA(fs.in_a.need(in_a_bytes));
+    FR_CUDA(fs.in_b.need(in_b_bytes ? in_b_bytes : 8));
+    FR_CUDA(fs.out_a.need(out_bytes));
+    FR_CUDA(fs.out_b.need(out_bytes));
+    FR_CUDA(cudaMemcpyAsync(fs.in_a.p, in_a, in_a_bytes, cudaMemcpyHostToDevice, fs.s));
+    if (in_b) FR_CUDA(cudaMemcpyAsync(fs.in_b.p, in_b, in_b_bytes, cudaMemcpyHostToDevice, fs.s));
+    rc = run(fs.in_a.p, fs.in_b.p, fs.out_a.p, fs.out_b.p, fs.s);
+    if (rc != FR_OK) return rc;
+    FR_CUDA(cudaMemcpyAsync(out_a, fs.out_a.p, out_bytes, cudaMemcpyDeviceToHost, fs.s));
+    FR_CUDA(cudaMemcpyAsync(out_b, fs.out_b.p, out_bytes, cudaMemcpyDeviceToHost, fs.s));
+    FR_CUDA(cudaStreamSynchronize(fs.s));
+    return FR_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1420,38 +1396,42 @@ int fr_rrf_fuse(int device, const int64_t *keys, int L, int B, int kp, int k_rrf
     if (L < 1 || B < 0 || kp < 1 || k_out < 1 || k_rrf < 0) return fail(FR_EINVAL, "bad L/B/kp/k_rrf/k_out");
     if (B == 0) return FR_OK;
     if (!keys || !out_score || !out_keys) return fail(FR_EINVAL, "NULL buffer");
+    return fuse_on_device(device, keys, static_cast<size_t>(L) * B * kp * sizeof(int64_t), nullptr, 0, out_score, out_keys,
+                          static_cast<size_t>(B) * k_out * 8,
+                          [&](void *d_in, void *, void *d_sc, void *d_k, cudaStream_t s) {
+                              return fr_rrf_fuse_device(device, static_cast<const int64_t *>(d_in), L, B, kp, k_rrf, k_out,
+                                                        static_cast<double *>(d_sc), static_cast<int64_t *>(d_k), s);
+                          });
+}
+
+int fr_score_fuse_device(int device, const float *d_dist, const int64_t *d_keys, int L, int B, int kp, int k_out,
+                         double *d_out_score, int64_t *d_out_keys, void *stream) {
+    if (L < 1 || B < 0 || kp < 1 || k_out < 1) return fail(FR_EINVAL, "bad L/B/kp/k_out");
+    if (static_cast<int64_t>(L) * kp > 2048 || L > 64)
+        return fail(FR_EUNSUP, "L*kp = %d exceeds 2048 candidates per query (or L > 64)", L * kp);
+    if (B == 0) return FR_OK;
+    if (!d_dist || !d_keys || !d_out_score || !d_out_keys) return fail(FR_EINVAL, "NULL buffer");
     int rc = check_device(device, nullptr);
     if (rc != FR_OK) return rc;
     DeviceGuard g(device);
-    const size_t inb = static_cast<size_t>(L) * B * kp * sizeof(int64_t);
-    const size_t ob = static_cast<size_t>(B) * k_out * 8;
-    void *d_in = nullptr, *d_sc = nullptr, *d_k = nullptr;
-    cudaStream_t s = nullptr;
-    auto cleanup = [&]() {
-        if (d_in) cudaFree(d_in);
-        if (d_sc) cudaFree(d_sc);
-        if (d_k) cudaFree(d_k);
-        if (s) cudaStreamDestroy(s);
-    };
-    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&d_in, inb);
-    if (e == cudaSuccess) e = cudaMalloc(&d_sc, ob);
-    if (e == cudaSuccess) e = cudaMalloc(&d_k, ob);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, keys, inb, cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess) {
-        cleanup();
-        return fail(FR_ECUDA, "rrf staging failed: %s", cudaGetErrorString(e));
-    }
-    rc = fr_rrf_fuse_device(device, static_cast<const int64_t *>(d_in), L, B, kp, k_rrf, k_out,
-                            static_cast<double *>(d_sc), static_cast<int64_t *>(d_k), s);
-    if (rc == FR_OK) {
-        e = cudaMemcpyAsync(out_score, d_sc, ob, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out_keys, d_k, ob, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) rc = fail(FR_ECUDA, "rrf copy-back failed: %s", cudaGetErrorString(e));
-    }
-    cleanup();
-    return rc;
+    fr::ScoreFuseArgs sa{d_dist, d_keys, L, B, kp, k_out, d_out_score, d_out_keys, static_cast<cudaStream_t>(stream)};
+    FR_CUDA(fr::launch_score_fuse(sa));
+    return FR_OK;
+}
+
+int fr_score_fuse(int device, const float *dist, const int64_t *keys, int L, int B, int kp, int k_out, double *out_score,
+                  int64_t *out_keys) {
+    if (L < 1 || B < 0 || kp < 1 || k_out < 1) return fail(FR_EINVAL, "bad L/B/kp/k_out");
+    if (B == 0) return FR_OK;
+    if (!dist || !keys || !out_score || !out_keys) return fail(FR_EINVAL, "NULL buffer");
+    const size_t ne = static_cast<size_t>(L) * B * kp;
+    return fuse_on_device(device, dist, ne * sizeof(float), keys, ne * sizeof(int64_t), out_score, out_keys,
+                          static_cast<size_t>(B) * k_out * 8,
+                          [&](void *d_d, void *d_k, void *d_sc, void *d_ok, cudaStream_t s) {
+                              return fr_score_fuse_device(device, static_cast<const float *>(d_d),
+                                                          static_cast<const int64_t *>(d_k), L, B, kp, k_out,
+                                                          static_cast<double *>(d_sc), static_cast<int64_t *>(d_ok), s);
+                          });
 }
 
 int fr_maxsim_aggregate_device(int device, const float *d_dist, const int64_t *d_keys, int B, int T, int kp,
@@ -1475,39 +1455,14 @@ int fr_maxsim_aggregate(int device, const float *dist, const int64_t *keys, int 
     if (B < 0 || T < 1 || kp < 1 || k_out < 1) return fail(FR_EINVAL, "bad B/T/kp/k_out");
     if (B == 0) return FR_OK;
     if (!dist || !keys || !out_score || !out_group) return fail(FR_EINVAL, "NULL buffer");
-    int rc = check_device(device, nullptr);
-    if (rc != FR_OK) return rc;
-    DeviceGuard g(device);
     const size_t ne = static_cast<size_t>(B) * T * kp;
-    const size_t ob = static_cast<size_t>(B) * k_out * 8;
-    void *d_d = nullptr, *d_k = nullptr, *d_sc = nullptr, *d_g = nullptr;
-    cudaStream_t s = nullptr;
-    auto cleanup = [&]() {
-        for (void *p : {d_d, d_k, d_sc, d_g})
-            if (p) cudaFree(p);
-        if (s) cudaStreamDestroy(s);
-    };
-    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&d_d, ne * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&d_k, ne * sizeof(int64_t));
-    if (e == cudaSuccess) e = cudaMalloc(&d_sc, ob);
-    if (e == cudaSuccess) e = cudaMalloc(&d_g, ob);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_d, dist, ne * sizeof(float), cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_k, keys, ne * sizeof(int64_t), cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess) {
-        cleanup();
-        return fail(FR_ECUDA, "maxsim staging failed: %s", cudaGetErrorString(e));
-    }
-    rc = fr_maxsim_aggregate_device(device, static_cast<const float *>(d_d), static_cast<const int64_t *>(d_k), B, T, kp,
-                                    group_shift, k_out, static_cast<double *>(d_sc), static_cast<int64_t *>(d_g), s);
-    if (rc == FR_OK) {
-        e = cudaMemcpyAsync(out_score, d_sc, ob, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out_group, d_g, ob, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) rc = fail(FR_ECUDA, "maxsim copy-back failed: %s", cudaGetErrorString(e));
-    }
-    cleanup();
-    return rc;
+    return fuse_on_device(device, dist, ne * sizeof(float), keys, ne * sizeof(int64_t), out_score, out_group,
+                          static_cast<size_t>(B) * k_out * 8,
+                          [&](void *d_d, void *d_k, void *d_sc, void *d_g, cudaStream_t s) {
+                              return fr_maxsim_aggregate_device(device, static_cast<const float *>(d_d),
+                                                                static_cast<const int64_t *>(d_k), B, T, kp, group_shift, k_out,
+                                                                static_cast<double *>(d_sc), static_cast<int64_t *>(d_g), s);
+                          });
 }
 
 }  // extern "C"

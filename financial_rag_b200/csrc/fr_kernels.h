@@ -169,6 +169,8 @@ struct MergeArgs {
     int64_t *out_keys;          // [B][k]
     const uint8_t *only_flagged;  // optional [B]: CTAs of unflagged queries exit at once (K2 fallback)
     const int *limit;             // optional: CTAs b >= *limit exit at once (K2 second-chance pass)
+    int cyclic_world;             // SHARDS: 0 = shards hold contiguous row blocks (ties -> shard, position); W = global row s
+                                  // lives on shard s % W at local row s / W (ties -> local_row * W + shard == global row)
     cudaStream_t stream;
 };
 cudaError_t launch_merge_topk(const MergeArgs &a);
@@ -202,6 +204,16 @@ struct RrfArgs {
     cudaStream_t stream;
 };
 cudaError_t launch_rrf_fuse(const RrfArgs &a);
+// K5b: mean of per-list min-max normalised scores (rag_backend.py:732-754)
+struct ScoreFuseArgs {
+    const float *dist;    // [L][B][kp] distances as the searches return them (score = 1.0 - dist)
+    const int64_t *keys;  // [L][B][kp] (-1 = empty slot)
+    int L, B, kp, k_out;
+    double *out_score;    // [B][k_out]
+    int64_t *out_keys;    // [B][k_out] (-1 padded)
+    cudaStream_t stream;
+};
+cudaError_t launch_score_fuse(const ScoreFuseArgs &a);
 
 // ---- K6 maxsim_aggregate -------------------------------------------------------------------------
 struct MaxSimArgs {

@@ -14,13 +14,46 @@
 
 namespace fr {
 
+// SHARDS mode, two tie orders (a tie = equal score bits):
+//   block layout  (cyclic_w == 0): shard g holds a contiguous block of global rows, so the global insertion order of
+//                 tied candidates is (shard, position in the shard's sorted list): low word = ~(g * k + position);
+//   cyclic layout (cyclic_w == W): global row s lives on shard s % W at local row s / W (fr_group: a collection that
+//                 grows by upserts cannot know its final block boundaries), so the global insertion order is
+//                 local_row * W + shard -- that IS the global row, and it goes into the low word (fits 32 bits:
+//                 fr_group caps a shard at (2^32 - 16) / W rows).  The position needed to fetch the int64 key is
+//                 recovered by a binary search of the shard's (strictly descending) list.
+__device__ __forceinline__ uint64_t shard_order_key(uint64_t key, int p, int pos, int k, int cyclic_w) {
+    const uint32_t ord = cyclic_w > 0 ? key_row(key) * static_cast<uint32_t>(cyclic_w) + static_cast<uint32_t>(p)
+                                      : static_cast<uint32_t>(p * k + pos);
+    return (key & 0xffffffff00000000ull) | static_cast<uint64_t>(0xffffffffu - ord);
+}
+__device__ __forceinline__ int64_t shard_key_of(uint64_t key, const uint64_t *__restrict__ packed,
+                                                const int64_t *__restrict__ shard_keys, int64_t shard_stride, int b,
+                                                int k, int cyclic_w) {
+    const uint32_t idx = key_row(key);
+    if (cyclic_w == 0) {
+        const int g = idx / k, jj = idx - g * k;
+        return shard_keys[static_cast<int64_t>(g) * shard_stride + static_cast<int64_t>(b) * k + jj];
+    }
+    const int g = idx % static_cast<uint32_t>(cyclic_w);
+    const uint32_t local_row = idx / static_cast<uint32_t>(cyclic_w);
+    const uint64_t orig = (key & 0xffffffff00000000ull) | static_cast<uint64_t>(0xffffffffu - local_row);
+    const int64_t base = static_cast<int64_t>(g) * shard_stride + static_cast<int64_t>(b) * k;
+    int lo = 0, hi = k - 1;  // descending list, `orig` is in it
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (packed[base + mid] > orig) lo = mid + 1; else hi = mid;
+    }
+    return shard_keys[base + lo];
+}
+
 template <int KPL, bool SHARDS>
 __global__ void __launch_bounds__(128)
 merge_topk_kernel(const uint64_t *__restrict__ packed, int P, int64_t shard_stride, int B, int k,
                   const int64_t *__restrict__ row_keys, const int64_t *__restrict__ shard_keys, bool l2,
                   float *__restrict__ out_dist, uint64_t *__restrict__ out_packed,
                   int64_t *__restrict__ out_keys, const uint8_t *__restrict__ only_flagged,
-                  const int *__restrict__ limit) {
+                  const int *__restrict__ limit, int cyclic_w) {
     __shared__ uint64_t lists[4 * 32 * KPL];
     const int b = blockIdx.x;
     if (only_flagged != nullptr && only_flagged[b] == 0) return;  // uniform per CTA
@@ -37,8 +70,7 @@ merge_topk_kernel(const uint64_t *__restrict__ packed, int P, int64_t shard_stri
         for (int i0 = 0; i0 < k; i0 += 32) {
             const int i = i0 + lane;
             uint64_t key = (i < k) ? src[i] : 0ull;
-            if (SHARDS && key != 0ull)
-                key = (key & 0xffffffff00000000ull) | static_cast<uint64_t>(0xffffffffu - static_cast<uint32_t>(p * k + i));
+            if (SHARDS && key != 0ull) key = shard_order_key(key, p, i, k, cyclic_w);
             unsigned m = __ballot_sync(FULL_MASK, key != 0ull && key > thr);
             if (m == 0u) break;  // list is sorted: nothing further in it can enter
             while (m) {
@@ -69,8 +101,7 @@ merge_topk_kernel(const uint64_t *__restrict__ packed, int P, int64_t shard_stri
         if (out_dist) out_dist[o] = l2 ? -s : 1.0f - s;
         if (out_packed) out_packed[o] = key;
         if (SHARDS) {
-            const int g = idx / k, jj = idx - g * k;
-            out_keys[o] = shard_keys[static_cast<int64_t>(g) * shard_stride + static_cast<int64_t>(b) * k + jj];
+            out_keys[o] = shard_key_of(key, packed, shard_keys, shard_stride, b, k, cyclic_w);
         } else {
             out_keys[o] = row_keys[idx];
         }
@@ -86,7 +117,7 @@ merge_topk32_kernel(const uint64_t *__restrict__ packed, int P, int64_t shard_st
                     const int64_t *__restrict__ row_keys, const int64_t *__restrict__ shard_keys, bool l2,
                     float *__restrict__ out_dist, uint64_t *__restrict__ out_packed,
                     int64_t *__restrict__ out_keys, const uint8_t *__restrict__ only_flagged,
-                    const int *__restrict__ limit) {
+                    const int *__restrict__ limit, int cyclic_w) {
     __shared__ uint64_t lists[8][32];
     const int b = blockIdx.x;
     if (only_flagged != nullptr && only_flagged[b] == 0) return;  // uniform per CTA
@@ -96,8 +127,7 @@ merge_topk32_kernel(const uint64_t *__restrict__ packed, int P, int64_t shard_st
     auto load = [&](int p) -> uint64_t {
         if (p >= P || lane >= k) return 0ull;
         uint64_t key = packed[static_cast<int64_t>(p) * shard_stride + static_cast<int64_t>(b) * k + lane];
-        if (SHARDS && key != 0ull)
-            key = (key & 0xffffffff00000000ull) | static_cast<uint64_t>(0xffffffffu - static_cast<uint32_t>(p * k + lane));
+        if (SHARDS && key != 0ull) key = shard_order_key(key, p, lane, k, cyclic_w);
         return key;
     };
     uint64_t run = 0ull;
@@ -128,8 +158,7 @@ merge_topk32_kernel(const uint64_t *__restrict__ packed, int P, int64_t shard_st
     if (out_dist) out_dist[o] = l2 ? -sc : 1.0f - sc;
     if (out_packed) out_packed[o] = run;
     if (SHARDS) {
-        const int g = idx / k, jj = idx - g * k;
-        out_keys[o] = shard_keys[static_cast<int64_t>(g) * shard_stride + static_cast<int64_t>(b) * k + jj];
+        out_keys[o] = shard_key_of(run, packed, shard_keys, shard_stride, b, k, cyclic_w);
     } else {
         out_keys[o] = row_keys[idx];
     }
@@ -141,16 +170,16 @@ cudaError_t launch_merge_topk(const MergeArgs &a) {
 #define FR_MERGE(KPL, SH)                                                                          \
     merge_topk_kernel<KPL, SH><<<grid, block, 0, a.stream>>>(a.packed, a.P, a.shard_stride, a.B, a.k, \
                                                              a.row_keys, a.shard_keys, a.l2, a.out_dist, \
-                                                             a.out_packed, a.out_keys, a.only_flagged, a.limit)
+                                                             a.out_packed, a.out_keys, a.only_flagged, a.limit, a.cyclic_world)
     if (a.k <= 32) {
         if (a.shards)
             merge_topk32_kernel<true><<<grid, 256, 0, a.stream>>>(a.packed, a.P, a.shard_stride, a.B, a.k, a.row_keys,
                                                                  a.shard_keys, a.l2, a.out_dist, a.out_packed, a.out_keys,
-                                                                 a.only_flagged, a.limit);
+                                                                 a.only_flagged, a.limit, a.cyclic_world);
         else
             merge_topk32_kernel<false><<<grid, 256, 0, a.stream>>>(a.packed, a.P, a.shard_stride, a.B, a.k, a.row_keys,
                                                                   a.shard_keys, a.l2, a.out_dist, a.out_packed, a.out_keys,
-                                                                  a.only_flagged, a.limit);
+                                                                  a.only_flagged, a.limit, a.cyclic_world);
     } else if (a.k <= 128) {
         if (a.shards) FR_MERGE(4, true); else FR_MERGE(4, false);
     } else if (a.k <= 256 && !a.shards) {

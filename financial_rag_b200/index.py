@@ -32,11 +32,13 @@ def canonical_space(space: Optional[str]) -> str:
     return "cosine"
 
 
-def _stream_ptr(stream) -> ctypes.c_void_p:
+def _stream_ptr(stream, device: Optional[int] = None) -> ctypes.c_void_p:
+    """``stream`` = a torch stream, a raw cudaStream_t, or None = torch's current stream ON ``device`` (the index's
+    device, which need not be torch's current device)."""
     if stream is None:
         import torch
 
-        stream = torch.cuda.current_stream()
+        stream = torch.cuda.current_stream(device)
     return ctypes.c_void_p(int(getattr(stream, "cuda_stream", stream)))
 
 
@@ -54,11 +56,22 @@ class ShardIndex:
         check(self._lib.fr_index_create(self.dim, _METRICS[self.space], _DTYPES[dtype], self.device,
                                         int(reserve_rows), ctypes.byref(h)))
         self._h = h
+        self._owned = True
+
+    @classmethod
+    def _borrowed(cls, handle, dim: int, space: str, dtype: str, device: int) -> "ShardIndex":
+        """View of a shard some fr_group owns (ShardGroup.shard): same calls, never destroyed from here."""
+        self = cls.__new__(cls)
+        self._lib = _lib.load()
+        self.dim, self.space, self.dtype, self.device = int(dim), space, dtype, int(device)
+        self._h = handle
+        self._owned = False
+        return self
 
     # -- lifecycle ---------------------------------------------------------------------------
     def close(self) -> None:
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and getattr(self, "_owned", True):
             self._lib.fr_index_destroy(h)
 
     def __del__(self):
@@ -202,7 +215,7 @@ class ShardIndex:
             self._check_dev(keys, torch.int64, "keys")
             kp = keys.data_ptr()
         check(self._lib.fr_index_append_device(self._handle(), vectors.data_ptr(), kp, int(first_key),
-                                               vectors.shape[0], _stream_ptr(stream)))
+                                               vectors.shape[0], _stream_ptr(stream, self.device)))
 
     def search_device(self, queries, k: int, out_dist=None, out_keys=None, stream=None):
         import torch
@@ -214,7 +227,7 @@ class ShardIndex:
         if out_keys is None:
             out_keys = torch.empty((b, k), dtype=torch.int64, device=queries.device)
         check(self._lib.fr_index_search_device(self._handle(), queries.data_ptr(), b, int(k),
-                                               out_dist.data_ptr(), out_keys.data_ptr(), _stream_ptr(stream)))
+                                               out_dist.data_ptr(), out_keys.data_ptr(), _stream_ptr(stream, self.device)))
         return out_dist, out_keys
 
     def search_partial_device(self, queries, k: int, out_packed, out_keys, stream=None) -> None:
@@ -225,7 +238,7 @@ class ShardIndex:
         self._check_dev(queries, torch.float32, "queries")
         check(self._lib.fr_index_search_partial_device(self._handle(), queries.data_ptr(), queries.shape[0],
                                                        int(k), out_packed.data_ptr(), out_keys.data_ptr(),
-                                                       _stream_ptr(stream)))
+                                                       _stream_ptr(stream, self.device)))
 
 
 def merge_shards_device(device: int, space: str, packed, keys, shard_stride: int, g: int, b: int, k: int,
@@ -234,7 +247,7 @@ def merge_shards_device(device: int, space: str, packed, keys, shard_stride: int
     lib = _lib.load()
     check(lib.fr_merge_shards_device(int(device), _METRICS[canonical_space(space)], packed.data_ptr(),
                                      keys.data_ptr(), int(shard_stride), int(g), int(b), int(k),
-                                     out_dist.data_ptr(), out_keys.data_ptr(), _stream_ptr(stream)))
+                                     out_dist.data_ptr(), out_keys.data_ptr(), _stream_ptr(stream, int(device))))
 
 
 def rrf_fuse_host(keys: np.ndarray, k_rrf: int = 60, k_out: int = 10, device: int = 0):
@@ -278,7 +291,7 @@ def maxsim_aggregate_device(dist, keys, group_shift: int, k_out: int = 24, strea
     sc = torch.empty((b, k_out), dtype=torch.float64, device=dist.device)
     og = torch.empty((b, k_out), dtype=torch.int64, device=dist.device)
     check(lib.fr_maxsim_aggregate_device(dist.device.index, dist.data_ptr(), keys.data_ptr(), b, t, kp, int(group_shift),
-                                         int(k_out), sc.data_ptr(), og.data_ptr(), _stream_ptr(stream)))
+                                         int(k_out), sc.data_ptr(), og.data_ptr(), _stream_ptr(stream, dist.device.index)))
     return sc, og
 
 
@@ -293,9 +306,39 @@ def rrf_fuse_device(keys, k_rrf: int = 60, k_out: int = 10, stream=None):
     sc = torch.empty((b, k_out), dtype=torch.float64, device=keys.device)
     ok = torch.empty((b, k_out), dtype=torch.int64, device=keys.device)
     check(lib.fr_rrf_fuse_device(keys.device.index, keys.data_ptr(), l, b, kp, int(k_rrf), int(k_out),
-                                 sc.data_ptr(), ok.data_ptr(), _stream_ptr(stream)))
+                                 sc.data_ptr(), ok.data_ptr(), _stream_ptr(stream, keys.device.index)))
     return sc, ok
 
 
-__all__ = ["ShardIndex", "canonical_space", "merge_shards_device", "rrf_fuse_host", "rrf_fuse_device",
+def score_fuse_host(dist: np.ndarray, keys: np.ndarray, k_out: int = 10, device: int = 0):
+    """``avg`` fusion (rag_backend.py:732-754): dist/keys [L, B, kp] -> (score [B,k_out] fp64, keys [B,k_out])."""
+    lib = _lib.load()
+    d = np.ascontiguousarray(dist, dtype=np.float32)
+    k = np.ascontiguousarray(keys, dtype=np.int64)
+    if d.ndim != 3 or d.shape != k.shape:
+        raise ValueError("dist and keys must both be [L, B, kp]")
+    l, b, kp = d.shape
+    sc = np.zeros((b, k_out), dtype=np.float64)
+    ok = np.full((b, k_out), -1, dtype=np.int64)
+    check(lib.fr_score_fuse(int(device), d.ctypes.data, k.ctypes.data, l, b, kp, int(k_out), sc.ctypes.data, ok.ctypes.data))
+    return sc, ok
+
+
+def score_fuse_device(dist, keys, k_out: int = 10, stream=None):
+    """CUDA tensors [L, B, kp] (fp32 dist, int64 keys) -> CUDA tensors (score fp64 [B,k_out], keys [B,k_out])."""
+    import torch
+
+    lib = _lib.load()
+    if not (dist.is_cuda and keys.is_cuda and dist.dtype == torch.float32 and keys.dtype == torch.int64
+            and dist.is_contiguous() and keys.is_contiguous() and dist.ndim == 3 and dist.shape == keys.shape):
+        raise ValueError("dist (fp32) and keys (int64) must be contiguous CUDA tensors [L, B, kp]")
+    l, b, kp = dist.shape
+    sc = torch.empty((b, k_out), dtype=torch.float64, device=dist.device)
+    ok = torch.empty((b, k_out), dtype=torch.int64, device=dist.device)
+    check(lib.fr_score_fuse_device(dist.device.index, dist.data_ptr(), keys.data_ptr(), l, b, kp, int(k_out),
+                                   sc.data_ptr(), ok.data_ptr(), _stream_ptr(stream, dist.device.index)))
+    return sc, ok
+
+
+__all__ = ["ShardIndex", "score_fuse_host", "score_fuse_device", "canonical_space", "merge_shards_device", "rrf_fuse_host", "rrf_fuse_device",
            "maxsim_aggregate_host", "maxsim_aggregate_device", "FR_MAX_K"]

@@ -30,9 +30,10 @@
 extern "C" {
 #endif
 
-#define FR_ABI_VERSION 1
+#define FR_ABI_VERSION 2
 
-typedef struct fr_index fr_index; /* opaque */
+typedef struct fr_index fr_index; /* opaque: one collection shard on one GPU */
+typedef struct fr_group fr_group; /* opaque: one collection row-sharded over several GPUs */
 
 /* metric vocabulary: parent_child/pgvector_child_store.py:7-26, chroma_child_store.py:34 */
 enum { FR_COSINE = 0, FR_L2 = 1, FR_IP = 2 };
@@ -40,6 +41,9 @@ enum { FR_COSINE = 0, FR_L2 = 1, FR_IP = 2 };
 enum { FR_BF16 = 0, FR_F32 = 1 };
 /* kernel selection for fr_index_set_option("path", v): tests and bench pin a regime with it */
 enum { FR_PATH_AUTO = 0, FR_PATH_STREAM = 1, FR_PATH_MMA = 2 };
+
+/* how the shards of an fr_group bring their local top-k lists together */
+enum { FR_XCHG_AUTO = 0, FR_XCHG_NCCL = 1, FR_XCHG_COPY = 2 };
 
 enum {
     FR_OK = 0,
@@ -145,6 +149,65 @@ int fr_merge_shards_device(int device, int metric, const uint64_t *d_packed,
                            const int64_t *d_keys, int64_t shard_stride_elems, int G, int B, int k,
                            float *d_out_dist, int64_t *d_out_keys, void *stream);
 
+/* ---- row-sharded collection (north star: "the corpus is row-sharded across the 8 GPUs of one box;
+ * each GPU computes a local top-k, then an NCCL all-gather over NVLink feeds a final merge kernel") -------------
+ * An fr_group is the same collection as an fr_index, spread over `world_shards` GPUs, behind the same calls:
+ * it replaces the SAME reference calls (Collection.upsert / delete / query / count, chroma_child_store.py:54-63,78),
+ * so get_child_vector_store(...) hands the reference's callers (rag_backend.py:632,699, retriever.py:55-56,88,
+ * pipeline.py:137-143) a store whose corpus lives on all the GPUs of the box.
+ *
+ * Placement is cyclic: the s-th vector ever inserted (its "global row") lives on shard s % W at local row s / W; an
+ * upsert of an existing key overwrites it where it is.  Results are identical to a one-GPU index for every W,
+ * ties included (ascending distance, then insertion order).  A shard holds at most (2^32 - 16) / W rows.
+ *
+ * devices[n_local]: CUDA ordinals of the shards THIS process owns = world shards [first_shard, first_shard + n_local).
+ *   One process, all GPUs (the reference's server): n_local == world_shards, first_shard 0, nccl_id NULL
+ *   (ncclCommInitAll).  One process per GPU (torchrun): n_local 1, first_shard = rank, nccl_id = the 128 bytes
+ *   rank 0 got from fr_nccl_unique_id and sent to everybody (ncclCommInitRank); every process then makes the same
+ *   calls in the same order (SPMD), upserts included -- each keeps the rows that are its own.
+ * exchange: FR_XCHG_NCCL = one grouped ncclAllGather of [packed | keys] (16 B per query and result per shard);
+ *   FR_XCHG_COPY = peer copies to the devices that want the result (single process only; the only choice when two
+ *   shards share a device, e.g. tests on a one-GPU box); FR_XCHG_AUTO = NCCL when the devices are distinct.
+ * NCCL is bound at run time: the copy the process has already loaded (torch's bundled libnccl.so.2), else the
+ * system's; fr_nccl_load(path) binds a specific one first. */
+int fr_nccl_load(const char *path_or_null);
+int fr_nccl_version(int *out);
+int fr_nccl_unique_id(void *out, int nbytes /* >= 128 */);
+int fr_group_create(int dim, int metric, int dtype, const int *devices, int n_local, int world_shards,
+                    int first_shard, const void *nccl_id, int exchange, int64_t reserve_rows_per_shard,
+                    fr_group **out);
+int fr_group_destroy(fr_group *grp);
+/* "world_shards" | "local_shards" | "first_shard" | "exchange" | "rows" | "count" | "searches" | "nccl_version" */
+int fr_group_info(fr_group *grp, const char *name, int64_t *out);
+/* fr_index_set_option on every local shard */
+int fr_group_set_option(fr_group *grp, const char *name, int64_t value);
+int fr_group_reserve(fr_group *grp, int64_t total_rows);
+/* Borrowed handle of a local shard: bulk loads from device memory (fr_index_append_device with the shard's own rows
+ * s, s + W, s + 2W, ... in order), per-shard options, statistics and scan profiling.  After bulk loads,
+ * fr_group_adopt_rows(total) checks that every local shard holds exactly its share of `total` rows and adopts them. */
+int fr_group_shard(fr_group *grp, int local_shard, fr_index **out);
+int fr_group_adopt_rows(fr_group *grp, int64_t total_rows);
+/* Same contracts as fr_index_count / rows / upsert / delete / get_rows / export_raw / import_raw / lookup_rows; a "row"
+ * is a global row (insertion order over the whole collection), so a shard file written by a group of one size loads
+ * into a group of any other size.  Row-order reads and the key map need every shard in this process. */
+int fr_group_count(fr_group *grp, int64_t *out_count);
+int fr_group_rows(fr_group *grp, int64_t *out_rows);
+int fr_group_upsert(fr_group *grp, const float *vecs, const int64_t *keys, int64_t n);
+int fr_group_delete(fr_group *grp, const int64_t *keys, int64_t n, int64_t *out_deleted);
+int fr_group_get_rows(fr_group *grp, int64_t first_row, int64_t n, float *out_vecs, int64_t *out_keys);
+int fr_group_export_raw(fr_group *grp, int64_t first_row, int64_t n, void *out_rows, int64_t *out_keys);
+int fr_group_import_raw(fr_group *grp, const void *rows, const int64_t *keys, int64_t n);
+int fr_group_lookup_rows(fr_group *grp, const int64_t *keys, int64_t n, int64_t *out_rows);
+/* The hot path, same contract as fr_index_search (host buffers; the copies are inside).  With several processes the
+ * one that owns shard 0 supplies `queries` (the others may pass NULL; the block is broadcast over NCCL) and every
+ * process receives the result. */
+int fr_group_search(fr_group *grp, const float *queries, int B, int k, float *out_dist, int64_t *out_keys);
+/* Device-resident form: d_queries[j] = the B x dim query block on the device of local shard j (the same block
+ * everywhere); where d_out_keys[j] / d_out_dist[j] are non-NULL the merged result is written on that device.
+ * streams[j]: the stream of local shard j's device to enqueue on (streams == NULL: the group's own). */
+int fr_group_search_device(fr_group *grp, const float *const *d_queries, int B, int k, float *const *d_out_dist,
+                           int64_t *const *d_out_keys, void *const *streams);
+
 /* Scan-kernel timing for the roofline line of bench.py.  After fr_index_set_option("profile", 1)
  * every search brackets its scan launches (K1 or K2, not the query normalisation or the merge)
  * with CUDA events on the stream they run on.  fr_index_profile_read waits for those events,
@@ -163,6 +226,15 @@ int fr_rrf_fuse(int device, const int64_t *keys, int L, int B, int kp, int k_rrf
                 double *out_score, int64_t *out_keys);
 int fr_rrf_fuse_device(int device, const int64_t *d_keys, int L, int B, int kp, int k_rrf,
                        int k_out, double *d_out_score, int64_t *d_out_keys, void *stream);
+
+/* Replaces the other fusion mode of rag_backend.py:732-754 ("average of per-list min-max normalized scores"): per list
+ * score = 1.0 - dist, norm = (score - min) / (max - min) (0.0 for a constant list), summed per key in list order,
+ * divided by L; output sorted descending, ties in first-seen order.  fp64, bit-exact against the Python loop.
+ * dist/keys: [L][B][kp] as the searches return them (key FR_KEY_NONE = empty slot); out_*: [B][k_out]. */
+int fr_score_fuse(int device, const float *dist, const int64_t *keys, int L, int B, int kp, int k_out,
+                  double *out_score, int64_t *out_keys);
+int fr_score_fuse_device(int device, const float *d_dist, const int64_t *d_keys, int L, int B, int kp, int k_out,
+                         double *d_out_score, int64_t *d_out_keys, void *stream);
 
 /* ---- multi-vector (late interaction) aggregation ---------------------------------
  * Replaces the per-token loop of parent_child/multivector_store.py:150-176.  The T query-token vectors
