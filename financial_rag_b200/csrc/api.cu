@@ -109,7 +109,7 @@ struct fr_index {
     cudaStream_t stream = nullptr;   // host-path stream
     cudaEvent_t last_use = nullptr;  // orders scratch reuse across caller streams
     DevBuf q_raw, q_prep, q_keys, partials, out_dist, out_keys, stage_vecs, stage_keys, stage_rows;
-    DevBuf q_bf16, err_bound, sel, sel_keys, flags, fail, fb_partials, tau, progress;  // K2 path
+    DevBuf q_bf16, err_bound, sel, sel_keys, flags, fail, fb_partials, tau, progress, s_lists;  // K2 path
     DevBuf kth_exact, r_q, r_misc, r_tau, r_partials, r_sel, r_sel_keys;     // K2 second-chance pass
     int mma_min_batch = 2;  // FR_PATH_AUTO: batches at least this large go to the tensor-core scans; smaller ones
                             // too when the swapped-operand kernel K2s serves them (it out-streams K1: TMA ring)
@@ -125,6 +125,11 @@ struct fr_index {
                             // by the lead throttle (100M rows: batch 1024 = 4 groups, one HBM pass per 1024 queries,
                             // 14.4k -> 17.0k QPS; batch 4096 with 8 groups another +2 % over 4: the board is power-bound
                             // and every HBM byte not fetched is clock for the tensor cores)
+    int mma_retry_blocks = 0;  // second-chance blocks enqueued per call: 0 = as many as the last finished search needed (at
+                               // least one; a block = 3 launches that exit at once when nobody failed into it -- a 4096-query
+                               // search used to enqueue 32 of them, ~100 empty launches), -1 = one per 128 queries, n = fixed
+    int retry_blocks_cur = 1;
+    int *fail_mirror = nullptr;  // pinned: first-pass failure count of the last finished search (written by retry_prep_kernel)
     DevBuf stats;           // [0] queries K2 could not certify (re-scanned by the stream kernel), cumulative
     int64_t n_searches = 0, n_queries = 0, n_mma_queries = 0;
     PinBuf pin;
@@ -359,6 +364,20 @@ int search_stream(fr_index *ix, const float *q, int B, int k, float *d_out_dist,
     return FR_OK;
 }
 
+// Second-chance blocks the next search enqueues (see fr_index::mma_retry_blocks).  A pure function of the option and of
+// the pinned failure count, so calling it twice for one search changes nothing.
+int plan_retry_blocks(fr_index *ix) {
+    const int R = fr::scan_mma_retry_max();
+    if (ix->mma_retry_blocks != 0) {
+        ix->retry_blocks_cur = ix->mma_retry_blocks;
+    } else {
+        const int last = ix->fail_mirror ? *static_cast<volatile int *>(ix->fail_mirror) : 0;
+        const int need = (last + R - 1) / R;
+        ix->retry_blocks_cur = need < 1 ? 1 : need;
+    }
+    return ix->retry_blocks_cur;
+}
+
 // K2 path: tensor-core selection of k' candidates per query, exact fp32-query rescoring with
 // certification, a second tensor-core pass for what could not be certified, and a device-side re-scan
 // of whatever is still open after that.
@@ -376,7 +395,15 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     const int grid = plan.lists_max;  // partial lists per query (at most)
     // second-chance blocks: R queries each, enough of them for every query of the call
     const int R = fr::scan_mma_retry_max();
-    const int slices = second_chance ? (B + R - 1) / R : 0;
+    int slices = 0;
+    if (second_chance) {
+        const int all = (B + R - 1) / R, want = plan_retry_blocks(ix);
+        slices = (want < 0 || want > all) ? all : want;
+        if (!ix->fail_mirror) {
+            FR_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&ix->fail_mirror), 64, cudaHostAllocPortable));
+            ix->fail_mirror[0] = 0;
+        }
+    }
     FR_CUDA(ix->q_bf16.need(static_cast<size_t>(nq_pad) * ix->dim * 2 * (1 + split)));
     FR_CUDA(ix->err_bound.need(4 * static_cast<size_t>(B) * sizeof(float)));  // |e| one-term | two-term | |e.q| one-term | two-term
     FR_CUDA(ix->partials.need(static_cast<size_t>(grid) * B * ksel * sizeof(uint64_t)));
@@ -444,6 +471,13 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     }
     ms.tau_g = static_cast<uint32_t *>(ix->tau.p);
     ms.stream = s;
+    if (small) {  // k' >= 128: K2s keeps its candidate lists in global memory
+        const size_t le = fr::scan_mma_small_list_elems(B, ksel, ix->dim, split);
+        if (le > 0) {
+            FR_CUDA(ix->s_lists.need(static_cast<size_t>(plan.lists) * le * sizeof(uint64_t)));
+            ms.list_scratch = static_cast<uint64_t *>(ix->s_lists.p);
+        }
+    }
     ProfScope prof{ix, s};
     int rc = prof.begin();
     if (rc != FR_OK) return rc;
@@ -529,6 +563,10 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
         rp.fail_count = fail_count;
         rp.fail_list = fail_list;
         rp.slices = slices;
+        rp.fail_count2 = fail_count2;
+        rp.fail_list2 = fail_list2;
+        rp.rescanned_total = stat_rescanned;
+        rp.host_mirror = ix->fail_mirror;
         rp.qb_retry = ix->r_q.p;
         rp.tau0 = tau0;
         rp.retry_n = retry_n;
@@ -698,10 +736,11 @@ uint64_t state_hash(const fr_index *ix) {
     };
     const DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist, &ix->out_keys, &ix->q_bf16,
                             &ix->err_bound, &ix->sel, &ix->sel_keys, &ix->flags, &ix->fail, &ix->fb_partials, &ix->tau,
-                            &ix->progress, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau, &ix->r_partials, &ix->r_sel,
+                            &ix->progress, &ix->s_lists, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau, &ix->r_partials, &ix->r_sel,
                             &ix->r_sel_keys};
     for (const DevBuf *b : bufs) mix(reinterpret_cast<uintptr_t>(b->p));
     mix(reinterpret_cast<uintptr_t>(ix->pin.p));
+    mix(reinterpret_cast<uintptr_t>(ix->fail_mirror));
     mix(reinterpret_cast<uintptr_t>(ix->corpus));
     mix(reinterpret_cast<uintptr_t>(ix->shadow));
     mix(static_cast<uint64_t>(ix->shadow_rows) * 2u + (ix->shadow_dirty ? 1u : 0u));
@@ -709,7 +748,8 @@ uint64_t state_hash(const fr_index *ix) {
     mix(static_cast<uint64_t>(ix->rows));
     mix(ix->n_deleted > 0 ? 1u : 0u);
     for (int v : {ix->path, ix->mma_min_batch, ix->mma_small_max, ix->mma_co_groups, ix->mma_split, ix->mma_split_max,
-                  ix->mma_debug, ix->mma_bound_scale_pct, ix->mma_max_lead, ix->mma_wide_lists, ix->mma_f32_shadow})
+                  ix->mma_debug, ix->mma_bound_scale_pct, ix->mma_max_lead, ix->mma_wide_lists, ix->mma_f32_shadow,
+                  ix->retry_blocks_cur})
         mix(static_cast<uint64_t>(static_cast<int64_t>(v)));
     mix(static_cast<uint64_t>(ix->small_rows_b1));
     mix(static_cast<uint64_t>(ix->small_rows_b4));
@@ -820,10 +860,11 @@ int fr_index_destroy(fr_index *ix) {
         DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist,
                           &ix->out_keys, &ix->stage_vecs, &ix->stage_keys, &ix->stage_rows,
                           &ix->q_bf16, &ix->err_bound, &ix->sel, &ix->sel_keys, &ix->flags, &ix->fail,
-                          &ix->fb_partials, &ix->tau, &ix->progress, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau,
+                          &ix->fb_partials, &ix->tau, &ix->progress, &ix->s_lists, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau,
                           &ix->r_partials, &ix->r_sel, &ix->r_sel_keys};
         for (DevBuf *b : bufs) b->release();
         ix->pin.release();
+        if (ix->fail_mirror) cudaFreeHost(ix->fail_mirror);
         for (auto &pr : ix->prof_events) {
             cudaEventDestroy(pr.first);
             cudaEventDestroy(pr.second);
@@ -905,6 +946,11 @@ int fr_index_set_option(fr_index *ix, const char *name, int64_t value) {
         ix->mma_small_max = static_cast<int>(value);
         return FR_OK;
     }
+    if (std::strcmp(name, "mma_retry_blocks") == 0) {
+        if (value < -1 || value > 4096) return fail(FR_EINVAL, "mma_retry_blocks must be -1 (one per 128 queries), 0 (adaptive) or a count");
+        ix->mma_retry_blocks = static_cast<int>(value);
+        return FR_OK;
+    }
     if (std::strcmp(name, "mma_debug") == 0) {
         ix->mma_debug = static_cast<int>(value);
         return FR_OK;
@@ -957,6 +1003,10 @@ int fr_index_get_stat(fr_index *ix, const char *name, int64_t *out) {
         *out = ix->n_mma_queries;
         return FR_OK;
     }
+    if (std::strcmp(name, "mma_retry_blocks") == 0) {
+        *out = ix->retry_blocks_cur;
+        return FR_OK;
+    }
     if (std::strcmp(name, "graph_replays") == 0) {
         *out = ix->n_graph_replays;
         return FR_OK;
@@ -1003,7 +1053,8 @@ int fr_index_upsert(fr_index *ix, const float *vecs, const int64_t *keys, int64_
     std::unordered_map<int64_t, int64_t> last_writer;  // row -> index of the last vector aimed at it
     int64_t new_rows = ix->rows;
     for (int64_t i = 0; i < n; ++i)
-        if (keys[i] == fr::KEY_TOMBSTONE) return fail(FR_EINVAL, "key INT64_MIN is reserved");
+        if (keys[i] == fr::KEY_TOMBSTONE || keys[i] == FR_KEY_NONE)
+            return fail(FR_EINVAL, "key %lld is reserved (INT64_MIN marks deleted rows, -1 pads result lists)", (long long)keys[i]);
     for (int64_t i = 0; i < n; ++i) {
         auto it = ix->keymap.find(keys[i]);
         int64_t row;
@@ -1034,9 +1085,13 @@ int fr_index_upsert(fr_index *ix, const float *vecs, const int64_t *keys, int64_
     }
     cudaStream_t s = ix->stream;
     rc = begin_use(ix, s);
-    if (rc != FR_OK) return rc;
+    if (rc != FR_OK) {
+        ix->keymap_valid = false;
+        return rc;
+    }
     const int64_t CH = 1 << 16;
     const size_t vb = static_cast<size_t>(ix->dim) * sizeof(float);
+    auto write_chunks = [&]() -> int {
     for (int64_t lo = 0; lo < n; lo += CH) {
         const int64_t m = (n - lo < CH) ? (n - lo) : CH;
         FR_CUDA(ix->stage_vecs.need(static_cast<size_t>(m) * vb));
@@ -1058,6 +1113,15 @@ int fr_index_upsert(fr_index *ix, const float *vecs, const int64_t *keys, int64_
         ia.stream = s;
         FR_CUDA(fr::launch_ingest(ia));
         FR_CUDA(cudaStreamSynchronize(s));  // staging buffers are reused by the next chunk
+    }
+    return FR_OK;
+    };
+    rc = write_chunks();
+    if (rc != FR_OK) {
+        // the map already names rows that were never written: rebuild it from the device before the next use
+        ix->keymap_valid = false;
+        end_use(ix, s);
+        return rc;
     }
     ix->rows = new_rows;
     return end_use(ix, s);
@@ -1182,6 +1246,8 @@ int fr_index_import_raw(fr_index *ix, const void *rows, const int64_t *keys, int
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     if (ix->rows + n > 0xfffffff0ll) return fail(FR_EUNSUP, "a shard holds at most 2^32-16 rows");
+    for (int64_t i = 0; i < n; ++i)
+        if (keys[i] == FR_KEY_NONE) return fail(FR_EINVAL, "key -1 is reserved (it pads result lists)");
     int rc = grow(ix, ix->rows + n, true);
     if (rc != FR_OK) return rc;
     cudaStream_t s = ix->stream;
@@ -1265,6 +1331,7 @@ int fr_index_search(fr_index *ix, const float *queries, int B, int k, float *out
     fr_index::SearchGraph *sg = nullptr;
     if (graphable) {
         if (ix->graphs.size() > 64) drop_graphs(ix);
+        plan_retry_blocks(ix);  // part of what a graph bakes in
         sg = &ix->graphs[(static_cast<uint64_t>(static_cast<uint32_t>(B)) << 32) | static_cast<uint32_t>(k)];
         const uint64_t h = state_hash(ix);
         if (sg->exec && sg->state != h) {
@@ -1332,8 +1399,9 @@ int fr_index_search_device(fr_index *ix, const float *d_queries, int B, int k, f
     rc = begin_use(ix, s);
     if (rc != FR_OK) return rc;
     rc = search_on_stream(ix, d_queries, B, k, d_out_dist, nullptr, d_out_keys, s);
-    if (rc != FR_OK) return rc;
-    return end_use(ix, s);
+    // recorded on failure too: part of the chain may be enqueued, and the next caller must wait for it
+    const int rc2 = end_use(ix, s);
+    return rc != FR_OK ? rc : rc2;
 }
 
 int fr_index_search_partial_device(fr_index *ix, const float *d_queries, int B, int k, uint64_t *d_out_packed,
@@ -1346,8 +1414,8 @@ int fr_index_search_partial_device(fr_index *ix, const float *d_queries, int B, 
     rc = begin_use(ix, s);
     if (rc != FR_OK) return rc;
     rc = search_on_stream(ix, d_queries, B, k, nullptr, d_out_packed, d_out_keys, s);
-    if (rc != FR_OK) return rc;
-    return end_use(ix, s);
+    const int rc2 = end_use(ix, s);
+    return rc != FR_OK ? rc : rc2;
 }
 
 int fr_merge_shards_device(int device, int metric, const uint64_t *d_packed, const int64_t *d_keys,

@@ -753,11 +753,23 @@ __global__ void retry_prep_kernel(const float *__restrict__ queries, const float
                                   const float *__restrict__ kth_exact, const int *__restrict__ fail_count,
                                   const int *__restrict__ fail_list, __nv_bfloat16 *__restrict__ qb_retry,
                                   float *__restrict__ tau0, int *__restrict__ retry_n, uint32_t *__restrict__ tau_g_retry,
-                                  int ksel, uint8_t *__restrict__ flags) {
+                                  int ksel, uint8_t *__restrict__ flags, int slices, int *__restrict__ fail_count2,
+                                  int *__restrict__ fail_list2, unsigned long long *__restrict__ rescanned_total,
+                                  int *__restrict__ host_mirror) {
     const int j = blockIdx.x;  // retry slot
     const int slice = j / RETRY_MAX, jj = j % RETRY_MAX;
     const int lane = threadIdx.x;
     const int nf = *fail_count;
+    if (j == 0) {
+        // The call enqueued `slices` second-chance blocks (as many as the previous searches needed: the host reads
+        // host_mirror, pinned memory, without ever waiting for it).  Failures beyond them go straight to the stream
+        // re-scan -- still exact, only slower -- and the next call brings more blocks.
+        if (lane == 0 && host_mirror != nullptr) *host_mirror = nf;
+        for (int i = slices * RETRY_MAX + lane; i < nf; i += 32) {
+            fail_list2[atomicAdd(fail_count2, 1)] = fail_list[i];
+            if (rescanned_total) atomicAdd(rescanned_total, 1ull);
+        }
+    }
     if (jj == 0 && lane == 0) {
         const int left = nf - slice * RETRY_MAX;
         retry_n[slice] = left < 0 ? 0 : (left < RETRY_MAX ? left : RETRY_MAX);
@@ -919,7 +931,8 @@ cudaError_t launch_retry_prep(const RetryPrepArgs &a) {
     if (a.slices <= 0) return cudaSuccess;
     mma::retry_prep_kernel<<<a.slices * mma::RETRY_MAX, 32, 0, a.stream>>>(a.queries, a.err_bound, a.err_alpha, a.extra_bound, a.kth_exact, a.fail_count,
                                                                          a.fail_list, static_cast<__nv_bfloat16 *>(a.qb_retry),
-                                                                         a.tau0, a.retry_n, a.tau_g_retry, a.ksel, a.flags);
+                                                                         a.tau0, a.retry_n, a.tau_g_retry, a.ksel, a.flags, a.slices, a.fail_count2,
+                                                                         a.fail_list2, a.rescanned_total, a.host_mirror);
     count_launch();
     return cudaGetLastError();
 }

@@ -41,7 +41,11 @@ constexpr int S_TMEM_BUFS = 4;
 // bge-small / gte-small embeddings, 12 for 768-d bert-base token vectors of the multi-vector store), so the
 // offsets are computed, identically, on the host (launch size) and in the kernel.
 constexpr int S_MAX_STAGES = 8;
-template <int NQ, int KPL, int SPLIT>
+// GL: the candidate lists live in global memory (list_scratch, L2-resident) instead of shared memory.  k' = 128 / 256
+// (k up to 100: cfg3's per-collection top-50, cfg5's top-100) times 64 queries times four lane quarters is 256 KB+ of
+// lists; they are only touched on inserts, which the thresholds shared between CTAs make rare after the first tiles
+// (K2 keeps its k' >= 128 lists the same way).
+template <int NQ, int KPL, int SPLIT, bool GL = (KPL >= 4)>
 struct SmallPlan {
     static constexpr int CAP = 32 * KPL;
     static constexpr int N_MMA = NQ * (1 + SPLIT);                               // operand rows: hi terms, then lo terms
@@ -50,7 +54,8 @@ struct SmallPlan {
     static constexpr int EW = small_epilogue_warps(NQ);                          // epilogue warps
     static constexpr int NQH = NQ * 4 / EW;                                      // queries per epilogue warp
     static constexpr int THREADS = 64 + 32 * EW;
-    static constexpr size_t LIST_BYTES = size_t(EW) * NQH * CAP * 8;             // [EW warps][NQH][CAP]
+    static constexpr size_t LIST_ELEMS = size_t(EW) * NQH * CAP;                 // [EW warps][NQH][CAP] per CTA
+    static constexpr size_t LIST_BYTES = GL ? 0 : LIST_ELEMS * 8;
     static constexpr size_t STASH_BYTES = size_t(EW) * NQH * 32 * 4;             // [EW warps][NQH][32 rows] fp32
     static_assert(Q_CHUNK % 1024 == 0, "query chunks must keep the 1024-byte swizzle alignment");
     size_t q_bytes, ring_off, list_off, stash_off, bar_off, alloc;
@@ -89,7 +94,7 @@ __global__ void __launch_bounds__(64 + 32 * small_epilogue_warps(NQ), 1)
 scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                       const int64_t *__restrict__ keys_or_null, int64_t n_rows, int nq, int ksel,
                       uint64_t *__restrict__ partials, int nq_total, uint32_t *__restrict__ tau_g, int k_chunks,
-                      int q0, const int *__restrict__ nq_dev) {
+                      int q0, const int *__restrict__ nq_dev, uint64_t *__restrict__ list_scratch) {
     // q0: first query (row of the query block, index into partials / tau_g) this launch serves; with nq_dev the
     // live count comes from the device (retry slices: *nq_dev queries in all, this slice takes [q0, q0 + nq))
     if (nq_dev != nullptr) {
@@ -108,7 +113,9 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_q = smem;
     uint8_t *smem_ring = smem + plan.ring_off;
-    uint64_t *lists = reinterpret_cast<uint64_t *>(smem + plan.list_off);
+    constexpr bool GL = KPL >= 4;
+    uint64_t *lists = GL ? list_scratch + static_cast<size_t>(blockIdx.x) * Plan::LIST_ELEMS
+                         : reinterpret_cast<uint64_t *>(smem + plan.list_off);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + plan.bar_off);
     // barrier slots: full[8] | empty[8] | tmem_full[4] | tmem_empty[4] | q_full | tmem_ptr
     const uint32_t bar_full = smem_u32(bars);
@@ -264,9 +271,10 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     if (q < nqw) {  // warp-uniform
                         const uint32_t *sp = tau_g + static_cast<size_t>(q0 + qbase + q) * ksel + lane;
                         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(x[q]) : "l"(sp));
-                        if (KPL == 2) {
+#pragma unroll
+                        for (int j = 1; j < KPL; ++j) {  // k' = 32 KPL slots: lane l reads slots l, l + 32, ...
                             uint32_t y;
-                            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(y) : "l"(sp + 32));
+                            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(y) : "l"(sp + 32 * j));
                             x[q] = min(x[q], y);
                         }
                     }
@@ -433,39 +441,45 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 namespace {
 template <int NQ, int KPL, int SPLIT>
 cudaError_t launch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CUtensorMap &tc, int k_chunks, int nq, int q0,
-                         size_t *alloc_out) {
+                         size_t *alloc_out, size_t *list_elems_out) {
     const mma::SmallPlan<NQ, KPL, SPLIT> plan(k_chunks);
     if (alloc_out) {  // planning only: does this instance fit, and with how deep a ring?
         *alloc_out = plan.stages >= mma::S_MIN_STAGES ? plan.alloc : 0;
+        if (list_elems_out) *list_elems_out = KPL >= 4 ? mma::SmallPlan<NQ, KPL, SPLIT>::LIST_ELEMS : 0;
         return cudaSuccess;
     }
     if (plan.stages < mma::S_MIN_STAGES) return cudaErrorInvalidValue;
+    if (KPL >= 4 && a.list_scratch == nullptr) return cudaErrorInvalidValue;
     auto kern = mma::scan_mma_small_kernel<NQ, KPL, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.alloc));
     if (e != cudaSuccess) return e;
     kern<<<a.plan.lists, mma::SmallPlan<NQ, KPL, SPLIT>::THREADS, plan.alloc, a.stream>>>(tq, tc, a.keys_or_null, a.n_rows, nq, a.ksel, a.partials,
-                                                                a.nq_total, a.tau_g, k_chunks, q0, a.nq_dev);
+                                                                a.nq_total, a.tau_g, k_chunks, q0, a.nq_dev, a.list_scratch);
     count_launch();
     return cudaGetLastError();
 }
 
 cudaError_t dispatch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CUtensorMap &tc, int nq_pad, int ksel,
-                           int k_chunks, int split, int nq, int q0, size_t *alloc_out) {
-    const bool k1 = ksel <= 32;
-#define FR_SMALL(NQ, KPL, SPLIT) launch_small<NQ, KPL, SPLIT>(a, tq, tc, k_chunks, nq, q0, alloc_out)
+                           int k_chunks, int split, int nq, int q0, size_t *alloc_out, size_t *list_elems_out = nullptr) {
+#define FR_SMALL(NQ, KPL, SPLIT) launch_small<NQ, KPL, SPLIT>(a, tq, tc, k_chunks, nq, q0, alloc_out, list_elems_out)
+#define FR_SMALL_K(NQ, SPLIT)                                                                      \
+    return ksel <= 32 ? FR_SMALL(NQ, 1, SPLIT)                                                     \
+                      : (ksel <= 64 ? FR_SMALL(NQ, 2, SPLIT) : (ksel <= 128 ? FR_SMALL(NQ, 4, SPLIT) : FR_SMALL(NQ, 8, SPLIT)))
+    if (ksel > 256) return cudaErrorInvalidValue;
     if (split) {
         switch (nq_pad) {
-            case 16: return k1 ? FR_SMALL(16, 1, 1) : FR_SMALL(16, 2, 1);
-            case 32: return k1 ? FR_SMALL(32, 1, 1) : FR_SMALL(32, 2, 1);
+            case 16: FR_SMALL_K(16, 1);
+            case 32: FR_SMALL_K(32, 1);
             default: return cudaErrorInvalidValue;  // 2 x 64 operand rows exceed an accumulator
         }
     }
     switch (nq_pad) {
-        case 16: return k1 ? FR_SMALL(16, 1, 0) : FR_SMALL(16, 2, 0);
-        case 32: return k1 ? FR_SMALL(32, 1, 0) : FR_SMALL(32, 2, 0);
-        case 64: return k1 ? FR_SMALL(64, 1, 0) : FR_SMALL(64, 2, 0);
+        case 16: FR_SMALL_K(16, 0);
+        case 32: FR_SMALL_K(32, 0);
+        case 64: FR_SMALL_K(64, 0);
         default: return cudaErrorInvalidValue;
     }
+#undef FR_SMALL_K
 #undef FR_SMALL
 }
 }  // namespace
@@ -474,7 +488,7 @@ cudaError_t dispatch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CU
 // (`split`: bf16 hi + lo halves of every query, twice the query block), 0 when none fits (too many queries for
 // the shared memory left beside a ring of at least S_MIN_STAGES stages).
 int scan_mma_small_nq(int nq, int ksel, int dim, int split) {
-    if (nq < 1 || nq > (split ? 32 : 64) || ksel > 64 || dim < 64 || dim % 64 != 0 || dim > 1024) return 0;
+    if (nq < 1 || nq > (split ? 32 : 64) || ksel > 256 || dim < 64 || dim % 64 != 0 || dim > 1024) return 0;
     const int nq_pad = nq <= 16 ? 16 : (nq <= 32 ? 32 : 64);
     size_t alloc = 0;
     MmaScanArgs dummy{};
@@ -482,6 +496,17 @@ int scan_mma_small_nq(int nq, int ksel, int dim, int split) {
     if (dispatch_small(dummy, none, none, nq_pad, ksel, dim / mma::K_CHUNK, split, nq, 0, &alloc) != cudaSuccess || alloc == 0)
         return 0;
     return nq_pad;
+}
+
+// uint64 elements of list scratch per CTA (0: the instance keeps its candidate lists in shared memory)
+size_t scan_mma_small_list_elems(int nq, int ksel, int dim, int split) {
+    const int nq_pad = scan_mma_small_nq(nq, ksel, dim, split);
+    if (nq_pad == 0) return 0;
+    size_t alloc = 0, elems = 0;
+    MmaScanArgs dummy{};
+    CUtensorMap none{};
+    dispatch_small(dummy, none, none, nq_pad, ksel, dim / mma::K_CHUNK, split, nq, 0, &alloc, &elems);
+    return elems;
 }
 
 // largest batch one K2s launch can serve for this width, k' and query precision (0 = none)

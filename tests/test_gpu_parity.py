@@ -477,7 +477,9 @@ def test_mma_co_resident_groups_do_not_change_results(frb):
     ix.close()
 
 
-@pytest.mark.parametrize("B,k", [(2, 10), (16, 10), (17, 16), (32, 32), (33, 10), (64, 16), (64, 32)])
+@pytest.mark.parametrize("B,k", [(2, 10), (16, 10), (17, 16), (32, 32), (33, 10), (64, 16), (64, 32),
+                                 # k' = 128 / 256: candidate lists in global memory (cfg3's top-50, cfg5's top-100)
+                                 (1, 50), (16, 50), (24, 64), (64, 50), (8, 100), (32, 100), (64, 100)])
 def test_small_batch_swapped_operand_kernel_equals_k2(frb, B, k):
     """K2s (corpus rows as the MMA's M operand, queries as N; batches <= 64) and K2 select the same candidates:
     after the shared exact rescoring the answers are bit-identical, with and without deleted rows."""
@@ -779,6 +781,7 @@ def test_second_chance_blocks_cover_every_failed_query(frb):
     assert ix.stat("mma_uncertified_queries") < 70, "the score-aware bound certifies (nearly) the whole batch at once"
     before = ix.stat("mma_uncertified_queries")
     ix.set_option("mma_bound_scale_pct", 400)
+    ix.set_option("mma_retry_blocks", -1)  # one second-chance block per 128 queries, whatever the earlier searches needed
     d_m, k_m = ix.search(queries, k)
     fails = ix.stat("mma_uncertified_queries") - before
     assert fails > 128, "need more failures than one second-chance block holds"
@@ -792,6 +795,45 @@ def test_second_chance_blocks_cover_every_failed_query(frb):
         assert np.abs(d_m[mism] - d_s[mism]).max() <= 2e-6
     assert_matches_oracle(d_m[:40], keys_to_rows(k_m[:40], KEY_BASE), queries[:40], corpus, k, "cosine", "bf16",
                           strict=False, stored=stored_rows(ix), label="second-chance blocks")
+    ix.close()
+
+
+def test_second_chance_capacity_follows_the_workload(frb):
+    """By default a search enqueues as many second-chance blocks as the last finished search needed (one when nothing
+    failed), not one per 128 queries: a 4096-query search used to carry ~100 launches that exit at once.  When more
+    queries fail than the blocks hold, the overflow is re-scanned by the stream kernel -- exact all the same -- and
+    the next search brings enough blocks."""
+    n, B, k = 120000, 700, 10
+    corpus, centres = make_clustered(n, 40, 0.3, seed=3200)
+    rng = np.random.default_rng(3201)
+    queries = (centres[rng.integers(0, 40, B)] + 0.3 / np.sqrt(384.0) * rng.standard_normal((B, 384), dtype=np.float32)).astype(np.float32)
+    ix = build_index(frb, corpus, "cosine", "bf16")
+    ix.set_path("stream")
+    d_s, k_s = ix.search(queries, k)
+    ix.set_path("mma")
+    ix.set_option("use_graphs", 0)
+    from financial_rag_b200 import _lib
+    l0 = _lib.launch_count()
+    d_0, k_0 = ix.search(queries, k)
+    quiet_launches = _lib.launch_count() - l0
+    assert ix.stat("mma_retry_blocks") == 1 and quiet_launches <= 16, quiet_launches
+    ix.set_option("mma_bound_scale_pct", 400)  # hundreds of first-pass failures from here on
+    r0, u0 = ix.stat("mma_rescanned_queries"), ix.stat("mma_uncertified_queries")
+    d_1, k_1 = ix.search(queries, k)           # one block enqueued: the overflow takes the stream re-scan
+    r1, fails = ix.stat("mma_rescanned_queries"), ix.stat("mma_uncertified_queries") - u0
+    assert fails > 128 and r1 - r0 >= fails - 128
+    d_2, k_2 = ix.search(queries, k)           # the capacity has followed: (next to) nothing is re-scanned
+    assert ix.stat("mma_retry_blocks") >= 2
+    assert ix.stat("mma_rescanned_queries") - r1 <= 3
+    for d_m, k_m in ((d_1, k_1), (d_2, k_2)):
+        np.testing.assert_allclose(d_m, d_s, rtol=0, atol=2e-6)
+        mism = k_m != k_s
+        if mism.any():
+            assert np.abs(d_m[mism] - d_s[mism]).max() <= 2e-6
+    ix.set_option("mma_bound_scale_pct", 100)
+    ix.search(queries, k)
+    ix.search(queries, k)
+    assert ix.stat("mma_retry_blocks") == 1    # and it shrinks again when the failures stop
     ix.close()
 
 
