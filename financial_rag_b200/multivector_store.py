@@ -13,7 +13,9 @@ Same design as the reference: every token embedding of a child chunk is one poin
     (``fr_maxsim_aggregate_device``); only the ``top_k_children`` (score, child) pairs come back.
 
 Row keys are ``(child_ordinal << 16) | token_idx`` so the kernel recovers a row's child with a shift;
-ordinals are dense per collection and rebuilt from the payload after a reload.
+ordinals are dense per collection and live IN the collection (``B200Collection.group_ordinal``: allocated under
+its lock, persisted with it), because the reference constructs these stores per request and side by side
+(rag_backend.py:656, pipeline.py:25) and every object must see the same child <-> ordinal map.
 
 Token embedding itself (a BERT forward pass, multivector_store.py:88-111) is SURVEY.md row 8f-4 and not
 part of this path: pass ``token_embedder(text, max_tokens) -> list[list[float]]``.  Without one the store
@@ -47,32 +49,11 @@ class B200MultiVectorChildStore:
         self.topk_per_token = int(os.getenv("MULTIVECTOR_TOPK_PER_TOKEN", "10"))
         self._token_embedder = token_embedder
         self._disabled_reason: Optional[str] = None if token_embedder else "No suitable model available for multi-vector store"
-        # child id <-> dense ordinal (the upper bits of the row keys)
-        self._ordinal_of: Dict[str, int] = {}
-        self._child_of: List[str] = []
-        self._rebuild_ordinals()
 
     # -- helpers ------------------------------------------------------------------------------------
-    def _rebuild_ordinals(self) -> None:
-        got = self.col.get(include=["metadatas"])
-        pairs = {}
-        for id_str, md in zip(got["ids"], got["metadatas"]):
-            key = self.col.key_of(id_str)
-            if key is not None and md and md.get("child_id") is not None:
-                pairs[key >> TOKEN_BITS] = str(md["child_id"])
-        if pairs:
-            self._child_of = [""] * (max(pairs) + 1)
-            for o, cid in pairs.items():
-                self._child_of[o] = cid
-                self._ordinal_of[cid] = o
-
     def _ordinal(self, child_id: str) -> int:
-        o = self._ordinal_of.get(child_id)
-        if o is None:
-            o = len(self._child_of)
-            self._ordinal_of[child_id] = o
-            self._child_of.append(child_id)
-        return o
+        """child id -> dense ordinal (the upper bits of the row keys); the map belongs to the collection."""
+        return self.col.group_ordinal(child_id)
 
     def _embed_tokens(self, text: str, max_tokens: int) -> List[List[float]]:
         if not text or self._disabled_reason:
@@ -135,7 +116,9 @@ class B200MultiVectorChildStore:
         for s, g in zip(sc, grp):
             if g == -1:
                 break
-            cid = self._child_of[g]
+            cid = self.col.group_name(g)
+            if cid is None:
+                continue
             meta = self.col.metadata_of_key(g << TOKEN_BITS) or {}
             out.append({"score": float(s), "child_id": cid,
                         "payload": {"parent_id": meta.get("parent_id"), "snippet": meta.get("snippet", "")}})

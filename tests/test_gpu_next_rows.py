@@ -440,3 +440,169 @@ def test_migrate_chroma_wal_replay(frb, golden, tmp_path, monkeypatch):
         assert res["ids"][0] == want
         assert res["metadatas"][0][0] == col["metadatas"][1]
     frb.reset_registry()
+
+
+# ---------------------------------------------------------------------------------------------
+# round-2 additions: shared ordinals, crash-safe flushes, the directory lock, score fusion, the ensemble searcher
+def test_multivector_store_objects_share_the_collections_ordinals(frb, tmp_path, monkeypatch):
+    """The reference builds a MultiVectorChildStore per request (rag_backend.py:656) and another for ingest
+    (pipeline.py:25).  Two live objects that ingest different children must not hand out the same ordinal: the map
+    lives in the collection."""
+    monkeypatch.setenv("CHROMA_CHILD_PERSIST_DIR", str(tmp_path))
+    frb.reset_registry()
+    rng = np.random.default_rng(5)
+    table = {}
+
+    def embedder(text, max_tokens):
+        return [table.setdefault(w, rng.standard_normal(384).astype(np.float32)) for w in text.split()[:max_tokens]]
+
+    a = frb.B200MultiVectorChildStore(token_embedder=embedder)
+    b = frb.B200MultiVectorChildStore(token_embedder=embedder)   # constructed BEFORE a's ingest: no stale state to go wrong
+    a.upsert_child_tokens([_Child(1, 10, "alpha beta gamma"), _Child(2, 10, "delta epsilon")])
+    b.upsert_child_tokens([_Child(3, 11, "zeta eta theta iota"), _Child(1, 10, "alpha beta gamma")])
+    assert a.col is b.col and a.col.count() == 3 + 2 + 4
+    assert [a.col.group_ordinal(str(c), create=False) for c in (1, 2, 3)] == [0, 1, 2]
+    for store in (a, b, frb.B200MultiVectorChildStore(token_embedder=embedder)):
+        hits = store.search_aggregate("zeta eta", top_k_children=3)
+        assert hits[0]["child_id"] == "3" and hits[0]["payload"]["snippet"] == "zeta eta theta iota"
+        hits = store.search_aggregate("delta", top_k_children=3)
+        assert hits[0]["child_id"] == "2" and hits[0]["payload"]["parent_id"] == "10"
+    # an explicit key that belongs to another id is refused instead of silently overwriting its row and payload
+    with pytest.raises(ValueError):
+        a.col.upsert(ids=["99:0"], embeddings=rng.standard_normal((1, 384)), metadatas=[{}], keys=[(0 << 16) | 1])
+    frb.reset_registry()
+    c = frb.B200MultiVectorChildStore(token_embedder=embedder)   # restart: ordinals come back with the collection
+    assert [c.col.group_ordinal(str(x), create=False) for x in (1, 2, 3)] == [0, 1, 2]
+    assert c.search_aggregate("zeta eta", top_k_children=3)[0]["child_id"] == "3"
+    frb.reset_registry()
+
+
+def test_flush_survives_a_crash_before_and_after_the_commit(frb, tmp_path, monkeypatch):
+    """persist() = append past the committed count -> journal the in-place patches -> ONE sqlite commit -> apply the
+    patches.  Kill it before the commit: the reload is the old collection, bit for bit.  Kill it after: the reload
+    finishes the flush.  Never new vector bits under an old payload."""
+    monkeypatch.setenv("CHROMA_CHILD_PERSIST_DIR", str(tmp_path))
+    monkeypatch.setenv("B200_CHILD_DTYPE", "f32")
+    frb.reset_registry()
+    corpus = make_corpus(300, 384, seed=31)
+    store = frb.get_child_vector_store(collection="crashy")
+    store.upsert_children([_Child(100 + i, 1, f"old {i}", corpus[i].tolist()) for i in range(200)])
+    col = store.col
+    before = store.search(corpus[250].tolist(), top_k=5)
+
+    class Boom(RuntimeError):
+        pass
+
+    def boom(*a, **k):
+        raise Boom()
+
+    # (a) crash between the journal and the commit: child 100 is overwritten with vector 250, ten children appended
+    monkeypatch.setattr(col, "_open_payload_db", boom)
+    with pytest.raises(Boom):
+        store.upsert_children([_Child(100, 1, "NEW 0", corpus[250].tolist())] +
+                              [_Child(1000 + i, 2, f"app {i}", corpus[200 + i].tolist()) for i in range(10)])
+    assert os.path.exists(os.path.join(col.directory, "patch.journal"))
+    frb.reset_registry()  # "restart"
+    store = frb.get_child_vector_store(collection="crashy")
+    assert store.count() == 200 and not os.path.exists(os.path.join(store.col.directory, "patch.journal"))
+    assert store.search(corpus[250].tolist(), top_k=5) == before
+    assert store.search(corpus[0].tolist(), top_k=1)[0]["payload"]["snippet"] == "old 0"
+    # (b) crash right after the commit, before the patches reach rows.bin
+    col = store.col
+    monkeypatch.setattr(col, "_apply_patches", boom)
+    with pytest.raises(Boom):
+        store.upsert_children([_Child(100, 1, "NEW 0", corpus[250].tolist())] +
+                              [_Child(1000 + i, 2, f"app {i}", corpus[200 + i].tolist()) for i in range(10)])
+    frb.reset_registry()
+    store = frb.get_child_vector_store(collection="crashy")
+    assert store.count() == 210
+    top = store.search(corpus[250].tolist(), top_k=1)[0]
+    assert top["child_id"] == "100" and top["payload"]["snippet"] == "NEW 0" and top["score"] > 0.9999
+    assert store.search(corpus[205].tolist(), top_k=1)[0]["child_id"] == "1005"
+    # (c) a damaged directory is reported, not guessed at
+    frb.reset_registry()
+    rows_p = os.path.join(str(tmp_path), "crashy.b200", "rows.bin")
+    with open(rows_p, "r+b") as f:
+        f.truncate(os.path.getsize(rows_p) - 1536 * 3)
+    with pytest.raises(RuntimeError, match="damaged"):
+        frb.get_child_vector_store(collection="crashy")
+    frb.reset_registry()
+
+
+def test_collection_directory_is_single_writer(frb, tmp_path, monkeypatch):
+    """A second PROCESS on the same persist directory (ingest_all.py next to the API server) is refused with a clear
+    error; it used to truncate the rows the first one had appended."""
+    import subprocess
+
+    monkeypatch.setenv("CHROMA_CHILD_PERSIST_DIR", str(tmp_path))
+    frb.reset_registry()
+    store = frb.get_child_vector_store(collection="locked")
+    store.upsert_children([_Child(1, 1, "x", make_corpus(1, 384, seed=1)[0].tolist())])
+    code = ("import os, sys; sys.path.insert(0, %r); import financial_rag_b200 as f\n"
+            "try:\n    f.get_child_vector_store(collection='locked').count(); print('OPENED')\n"
+            "except RuntimeError as e:\n    print('REFUSED', e)\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ), timeout=300).stdout
+    assert "REFUSED" in out and "another process" in out, out
+    frb.reset_registry()  # closing releases the lock
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ), timeout=300).stdout
+    assert "OPENED" in out, out
+
+
+@pytest.mark.parametrize("L,B,kp,k_out", [(1, 1, 1, 1), (2, 3, 5, 10), (6, 4, 30, 24), (3, 2, 50, 200)])
+def test_score_fuse_kernel_bit_exact(frb, L, B, kp, k_out):
+    """K5b == rag_backend.py:732-754 (per-list min-max normalised scores, mean over lists) in fp64, bit for bit:
+    constant lists, empty lists, short lists, keys shared between lists."""
+    rng = np.random.default_rng(L * 100 + kp)
+    dist = rng.random((L, B, kp)).astype(np.float32)
+    keys = rng.integers(0, max(2, kp * 2), size=(L, B, kp)).astype(np.int64)
+    for l in range(L):
+        for b in range(B):
+            keys[l, b] = rng.permutation(max(2, kp * 2))[:kp]   # ids are unique inside one list
+    if L > 1:
+        dist[1, 0, :] = 0.25         # a constant list contributes 0 for every member
+        keys[0, B - 1, kp // 2:] = -1  # a short list
+    if L > 2:
+        keys[2, 0, :] = -1           # an empty list still counts in the divisor
+    sc, fused = frb.score_fuse_host(dist, keys, k_out)
+    for b in range(B):
+        lists = []
+        for l in range(L):
+            n = int((keys[l, b] != -1).sum())
+            lists.append([(str(int(k)), 1.0 - float(d)) for k, d in zip(keys[l, b, :n], dist[l, b, :n])])
+        want = ofusion.avg_fuse(lists, k_out)
+        got_ids = [str(int(k)) for k in fused[b] if k != -1]
+        assert got_ids == [c for c, _ in want], f"query {b}"
+        assert [float(s) for s, k in zip(sc[b], fused[b]) if k != -1] == [s for _, s in want]
+
+
+@pytest.mark.parametrize("fusion", ["rrf", "avg"])
+@pytest.mark.parametrize("sharded", [False, True])
+def test_ensemble_searcher_device_resident(frb, fusion, sharded):
+    """EnsembleSearcher = cfg3 as a product call: every collection scanned, the lists fused on the device, the same
+    answer whether the collections are one shard or row-sharded groups, equal to the oracle pipeline."""
+    n, B, kp = 40000, 20, 50
+    corp = [make_corpus(n, 384, seed=s) for s in (81, 82)]
+    corp[1][:1500] = corp[0][:1500] + 0.05 * make_corpus(1500, 384, seed=83)
+    qs = [make_queries(B, c, seed=90) for c in corp]
+    cols = []
+    for c in corp:
+        ix = frb.ShardGroup(dim=384, dtype="bf16", devices=[0, 0, 0]) if sharded else frb.ShardIndex(dim=384, dtype="bf16")
+        ix.upsert(c, np.arange(n, dtype=np.int64))
+        cols.append(ix)
+    ens = frb.EnsembleSearcher(cols, k_each=kp, k_rrf=60, k_out=10, fusion=fusion)
+    sc, fused = ens.search(qs)
+    lists_d, lists_k = [], []
+    for ix, q in zip(cols, qs):
+        d, kk = ix.search(q, kp)
+        lists_d.append(d)
+        lists_k.append(kk)
+    for b in range(B):
+        if fusion == "rrf":
+            want = ofusion.rrf_fuse([[str(int(x)) for x in lk[b]] for lk in lists_k], 60, 10)
+        else:
+            want = ofusion.avg_fuse([[(str(int(x)), 1.0 - float(dd)) for x, dd in zip(lk[b], ld[b])]
+                                     for lk, ld in zip(lists_k, lists_d)], 10)
+        assert [str(int(x)) for x in fused[b]] == [c for c, _ in want], f"query {b}"
+        assert [float(s) for s in sc[b]] == [s for _, s in want]
+    for ix in cols:
+        ix.close()

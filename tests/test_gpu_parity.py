@@ -486,7 +486,7 @@ def test_small_batch_swapped_operand_kernel_equals_k2(frb, B, k):
     n = 45000
     corpus = make_corpus(n, 384, seed=900 + B, dup_pairs=[(11, 30000)])
     queries = make_queries(B, corpus, seed=901 + k)
-    queries[1] = corpus[11]
+    queries[int(B > 1)] = corpus[11]
     ix = build_index(frb, corpus, "cosine", "bf16")
     ix.set_path("mma")
     for round_ in range(2):
@@ -503,7 +503,7 @@ def test_small_batch_swapped_operand_kernel_equals_k2(frb, B, k):
         assert_matches_oracle(d_s, keys_to_rows(k_s, KEY_BASE), queries, corpus, k, "cosine", "bf16",
                               stored=stored_rows(ix), live=live, label=f"k2s B={B} k={k} round {round_}")
         if round_ == 0:
-            assert keys_to_rows(k_s[1], KEY_BASE)[0] == 11 and (k < 2 or keys_to_rows(k_s[1], KEY_BASE)[1] == 30000)
+            assert keys_to_rows(k_s[int(B > 1)], KEY_BASE)[0] == 11 and (k < 2 or keys_to_rows(k_s[int(B > 1)], KEY_BASE)[1] == 30000)
             victims = np.unique(k_s[:, 0])
             ix.delete(victims)
     ix.close()
