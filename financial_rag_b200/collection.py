@@ -518,6 +518,14 @@ class B200Collection:
         col = cls(meta["name"], meta.get("metadata") or {"hnsw:space": meta["space"]}, dtype=meta["dtype"],
                   device=device, directory=directory, devices=devices)
         col._lock_directory()
+        try:
+            return cls._load_locked(col, directory, meta)
+        except BaseException:
+            col.close()  # releases the directory lock
+            raise
+
+    @classmethod
+    def _load_locked(cls, col: "B200Collection", directory: str, meta: dict) -> "B200Collection":
         _, rows_p, keys_p, pay_p = col._paths()
         journal_p = os.path.join(directory, "patch.journal")
         state: Dict[str, str] = {}
