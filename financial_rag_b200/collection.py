@@ -492,6 +492,22 @@ class B200Collection:
                 os.remove(journal_p)
                 _fsync_file(self.directory)
 
+    @staticmethod
+    def committed_state(directory: str) -> Dict[str, Any]:
+        """What the last committed flush of the collection at ``directory`` recorded (tools, tests): meta.json's static
+        description plus rows / generation / next_synthetic / dim and the names of the row files."""
+        with open(os.path.join(directory, "meta.json")) as f:
+            out = dict(json.load(f))
+        db = sqlite3.connect(os.path.join(directory, "payload.sqlite3"))
+        try:
+            for name, value in db.execute("SELECT name, value FROM state"):
+                out[name] = value if name.endswith("_file") else int(value)
+        finally:
+            db.close()
+        out.setdefault("rows_file", "rows.bin")
+        out.setdefault("keys_file", "keys.bin")
+        return out
+
     def _apply_patches(self, patches, rb: int) -> None:
         _, rows_p, keys_p, _ = self._paths()
         with open(rows_p, "r+b") as fr, open(keys_p, "r+b") as fk:

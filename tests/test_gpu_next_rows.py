@@ -59,10 +59,11 @@ def test_persisted_collection_reloads_bit_identical(frb, tmp_path, monkeypatch, 
     assert store.count() == n - 2
     before = [store.search(q, top_k=10) for q in queries]
     d = os.path.join(str(tmp_path), "children_persist.b200")
-    meta = json.load(open(os.path.join(d, "meta.json")))
+    meta = frb.B200Collection.committed_state(d)
     assert meta["rows"] == n + 1 and meta["dtype"] == dtype and meta["dim"] == 384 and meta["space"] == "cosine"
     assert os.path.getsize(os.path.join(d, "rows.bin")) == (n + 1) * 384 * (2 if dtype == "bf16" else 4)
     assert os.path.getsize(os.path.join(d, "keys.bin")) == (n + 1) * 8
+    assert not os.path.exists(os.path.join(d, "patch.journal"))
 
     frb.reset_registry()  # "restart": the GPU index is gone, the next store object reloads the shard files
     store2 = frb.get_child_vector_store(collection="children_persist")
@@ -71,9 +72,10 @@ def test_persisted_collection_reloads_bit_identical(frb, tmp_path, monkeypatch, 
     assert after == before  # ids, payloads and scores, bit for bit
     assert after[0][0]["child_id"] == "10007" and after[0][1]["child_id"] == "12500"  # tie in insertion order
     # the reload dropped the two deleted rows and rewrote the files to match
-    meta = json.load(open(os.path.join(d, "meta.json")))
+    meta = frb.B200Collection.committed_state(d)
     assert meta["rows"] == n - 2
-    assert os.path.getsize(os.path.join(d, "keys.bin")) == (n - 2) * 8
+    assert os.path.getsize(os.path.join(d, meta["keys_file"])) == (n - 2) * 8
+    assert sorted(f for f in os.listdir(d) if f.endswith(".bin")) == sorted([meta["rows_file"], meta["keys_file"]])
     # the reloaded collection keeps working: upsert after reload, restart again
     store2.upsert_children([_Child(77, 1, "late arrival", corpus[7].tolist())])
     frb.reset_registry()
