@@ -67,6 +67,13 @@ SYMBOLS = {
     "fr_group_lookup_rows": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "fr_group_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "fr_group_search_device": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "fr_encoder_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, POINTER(c_void_p)]),
+    "fr_encoder_destroy": (c_int, [c_void_p]),
+    "fr_encoder_set_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, POINTER(c_int)]),
+    "fr_encoder_finalize": (c_int, [c_void_p]),
+    "fr_encoder_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "fr_encoder_forward_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                          c_void_p]),
     "fr_rrf_fuse": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "fr_rrf_fuse_device": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p]),

@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libfrb200.so")
 SOURCES = ["api.cu", "scan_stream.cu", "scan_mma.cu", "scan_mma_small.cu", "merge_topk.cu", "ingest.cu", "rrf.cu", "maxsim.cu",
-           "group.cu"]
+           "group.cu", "encoder.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -92,17 +92,7 @@ __device__ __forceinline__ uint64_t compact_query(uint64_t *list, const uint64_t
     uint64_t L[KPL];
 #pragma unroll
     for (int j = 0; j < KPL; ++j) L[j] = list[j * 32 + lane];
-    // Push the sorted pending block down the list, 32 entries at a time: the elementwise max / min of a
-    // descending block and the reversed carry are bitonic sequences holding the top / bottom 32 of their
-    // union; the bottom half carries on to the next block and what falls off the end is dropped.
-    uint64_t carry = p;
-#pragma unroll
-    for (int j = 0; j < KPL; ++j) {
-        const uint64_t r = reverse32(carry, lane);
-        const uint64_t hi = bitonic_merge32_desc(umax64(L[j], r), lane);
-        if (j + 1 < KPL) carry = bitonic_merge32_desc(umin64(L[j], r), lane);
-        L[j] = hi;
-    }
+    fold_sorted32<KPL>(L, p, lane);  // push the sorted pending block down the list, 32 entries at a time
 #pragma unroll
     for (int j = 0; j < KPL; ++j) list[j * 32 + lane] = L[j];
     const uint32_t lo = __shfl_sync(FULL_MASK, static_cast<uint32_t>(L[KPL - 1]), 31);

@@ -41,12 +41,22 @@ constexpr int S_TMEM_BUFS = 4;
 // bge-small / gte-small embeddings, 12 for 768-d bert-base token vectors of the multi-vector store), so the
 // offsets are computed, identically, on the host (launch size) and in the kernel.
 constexpr int S_MAX_STAGES = 8;
-// GL: the candidate lists live in global memory (list_scratch, L2-resident) instead of shared memory.  k' = 128 / 256
-// (k up to 100: cfg3's per-collection top-50, cfg5's top-100) times 64 queries times four lane quarters is 256 KB+ of
-// lists; they are only touched on inserts, which the thresholds shared between CTAs make rare after the first tiles
-// (K2 keeps its k' >= 128 lists the same way).
-template <int NQ, int KPL, int SPLIT, bool GL = (KPL >= 4)>
+// Where the candidate lists live (k' = 32 KPL entries per query):
+//   LM_WARP   k' <= 64: one list per (epilogue warp, query) in shared memory, merged at the end -- no sharing, no locks;
+//   LM_SHARED k' = 128 / 256 (k up to 100: cfg3's per-collection top-50, cfg5's top-100): per-warp lists would be 256 KB+,
+//             so the four lane-quarter warps that serve a query share ONE list per query in shared memory (<= 64 KB)
+//             under a per-query spin lock; a warp folds all its passing rows of a tile into it in one bitonic network;
+//   LM_GLOBAL 64 queries x k' = 256 (128 KB even when shared): per-warp lists in global memory (list_scratch).  Measured
+//             with k' = 128 (profiles/r02_ncu_full_scan_mma_small_64q_k128_10m.txt): the corpus stream evicts the lists
+//             from L2, every insert is a DRAM round trip and the scan drops to 0.75 of the copy peak -- hence LM_SHARED
+//             wherever it fits.
+enum { LM_WARP = 0, LM_SHARED = 1, LM_GLOBAL = 2 };
+__host__ __device__ constexpr int small_list_mode(int nq, int kpl) {
+    return kpl <= 2 ? LM_WARP : (nq * 32 * kpl * 8 <= 65536 ? LM_SHARED : LM_GLOBAL);
+}
+template <int NQ, int KPL, int SPLIT>
 struct SmallPlan {
+    static constexpr int LMODE = small_list_mode(NQ, KPL);
     static constexpr int CAP = 32 * KPL;
     static constexpr int N_MMA = NQ * (1 + SPLIT);                               // operand rows: hi terms, then lo terms
     static_assert(N_MMA <= 64, "an accumulator is 64 TMEM columns");
@@ -54,8 +64,9 @@ struct SmallPlan {
     static constexpr int EW = small_epilogue_warps(NQ);                          // epilogue warps
     static constexpr int NQH = NQ * 4 / EW;                                      // queries per epilogue warp
     static constexpr int THREADS = 64 + 32 * EW;
-    static constexpr size_t LIST_ELEMS = size_t(EW) * NQH * CAP;                 // [EW warps][NQH][CAP] per CTA
-    static constexpr size_t LIST_BYTES = GL ? 0 : LIST_ELEMS * 8;
+    static constexpr size_t LIST_ELEMS = LMODE == LM_SHARED ? size_t(NQ) * CAP          // [NQ][CAP] per CTA
+                                                            : size_t(EW) * NQH * CAP;   // [EW warps][NQH][CAP] per CTA
+    static constexpr size_t LIST_BYTES = LMODE == LM_GLOBAL ? 0 : LIST_ELEMS * 8 + (LMODE == LM_SHARED ? size_t(NQ) * 4 : 0);
     static constexpr size_t STASH_BYTES = size_t(EW) * NQH * 32 * 4;             // [EW warps][NQH][32 rows] fp32
     static_assert(Q_CHUNK % 1024 == 0, "query chunks must keep the 1024-byte swizzle alignment");
     size_t q_bytes, ring_off, list_off, stash_off, bar_off, alloc;
@@ -113,9 +124,10 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_q = smem;
     uint8_t *smem_ring = smem + plan.ring_off;
-    constexpr bool GL = KPL >= 4;
-    uint64_t *lists = GL ? list_scratch + static_cast<size_t>(blockIdx.x) * Plan::LIST_ELEMS
-                         : reinterpret_cast<uint64_t *>(smem + plan.list_off);
+    constexpr int LMODE = Plan::LMODE;
+    uint64_t *lists = LMODE == LM_GLOBAL ? list_scratch + static_cast<size_t>(blockIdx.x) * Plan::LIST_ELEMS
+                                         : reinterpret_cast<uint64_t *>(smem + plan.list_off);
+    int *locks = reinterpret_cast<int *>(lists + Plan::LIST_ELEMS);  // LM_SHARED only: one spin lock per query
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + plan.bar_off);
     // barrier slots: full[8] | empty[8] | tmem_full[4] | tmem_empty[4] | q_full | tmem_ptr
     const uint32_t bar_full = smem_u32(bars);
@@ -149,7 +161,9 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < EW * NQH * CAP; i += 32 * EW) lists[i] = 0ull;
+        for (int i = threadIdx.x - 64; i < static_cast<int>(Plan::LIST_ELEMS); i += 32 * EW) lists[i] = 0ull;
+        if (LMODE == LM_SHARED)
+            for (int i = threadIdx.x - 64; i < NQ; i += 32 * EW) locks[i] = 0;
     }
     tc_fence_before();
     __syncthreads();
@@ -243,7 +257,10 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         const int ew = warp - 2;       // epilogue warp index; warps ew and ew + 4 share a quarter and split the queries
         const int qbase = (ew >> 2) * NQH;  // first query (of the launch's block) this warp serves
         const int nqw = max(0, min(NQH, nq - qbase));  // live queries of this warp
-        uint64_t *my_lists = lists + static_cast<size_t>(ew) * NQH * CAP;  // [NQH][CAP], sorted descending
+        // [NQH][CAP], sorted descending: this warp's own lists, or (LM_SHARED) the CTA's lists of the queries it serves
+        uint64_t *my_lists = LMODE == LM_SHARED ? lists + static_cast<size_t>(qbase) * CAP
+                                                : lists + static_cast<size_t>(ew) * NQH * CAP;
+        int *my_locks = locks + qbase;
         float *my_stash = reinterpret_cast<float *>(smem + plan.stash_off) + static_cast<size_t>(ew) * NQH * 32;
         float tau[NQH];
 #pragma unroll
@@ -305,7 +322,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             float v[NQH];
 #pragma unroll
             for (int q = 0; q < NQH; ++q) v[q] = SPLIT ? __uint_as_float(r[q]) + __uint_as_float(r[NQH + q]) : __uint_as_float(r[q]);
-            if (it == 0u) {
+            if (it == 0u && LMODE != LM_SHARED) {
                 // first tile of this warp: every list is empty and every row would pass one by one (32 x NQ sorted
                 // inserts).  Load the lists in bulk instead: per query one 32-key bitonic sort of the tile's scores.
                 const uint32_t row = static_cast<uint32_t>(t * TILE_ROWS_CTA) + quarter * 32 + lane;
@@ -380,23 +397,42 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     const int qb = __ffs(qm) - 1;
                     qm &= qm - 1;
                     const int q = h * 32 + qb;
-                    unsigned mask = __ballot_sync(FULL_MASK, (pm[h] >> qb) & 1u);
+                    const bool has = ((pm[h] >> qb) & 1u) != 0u;
+                    unsigned mask = __ballot_sync(FULL_MASK, has);
                     uint64_t *lp = my_lists + q * CAP;
+                    if (LMODE == LM_SHARED) {  // the other lane quarters' warps fold into the same list
+                        if (lane == 0)
+                            while (atomicCAS(my_locks + q, 0, 1) != 0) __nanosleep(32);
+                        __syncwarp();
+                        __threadfence_block();
+                    }
                     WarpTopK<KPL> lst;
 #pragma unroll
-                    for (int j = 0; j < KPL; ++j) lst.e[j] = lp[j * 32 + lane];
+                    for (int j = 0; j < KPL; ++j) lst.e[j] = LMODE == LM_SHARED ? *(volatile uint64_t *)(lp + j * 32 + lane) : lp[j * 32 + lane];
                     const uint64_t mine = pack_key(my_stash[q * 32 + lane], row);
                     uint32_t best = 0;
-                    while (mask) {
-                        const int src = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const uint32_t lo = __shfl_sync(FULL_MASK, static_cast<uint32_t>(mine), src);
-                        const uint32_t hi = __shfl_sync(FULL_MASK, static_cast<uint32_t>(mine >> 32), src);
-                        lst.insert((static_cast<uint64_t>(hi) << 32) | lo, CAP, lane);
-                        best = max(best, hi);
+                    if (KPL >= 4 && __popc(mask) > 3) {
+                        // many rows at once (the first tiles, before the thresholds bite): one sort + one fold network
+                        const uint64_t p = bitonic_sort32_desc(has ? mine : 0ull, lane);
+                        best = __shfl_sync(FULL_MASK, static_cast<uint32_t>(p >> 32), 0);
+                        fold_sorted32<KPL>(lst.e, p, lane);
+                    } else {
+                        while (mask) {
+                            const int src = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const uint32_t lo = __shfl_sync(FULL_MASK, static_cast<uint32_t>(mine), src);
+                            const uint32_t hi = __shfl_sync(FULL_MASK, static_cast<uint32_t>(mine >> 32), src);
+                            lst.insert((static_cast<uint64_t>(hi) << 32) | lo, CAP, lane);
+                            best = max(best, hi);
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < KPL; ++j) lp[j * 32 + lane] = lst.e[j];
+                    if (LMODE == LM_SHARED) {
+                        __threadfence_block();
+                        __syncwarp();
+                        if (lane == 0) atomicExch(my_locks + q, 0);
+                    }
                     const float nt = key_threshold(lst.kth(CAP));
                     // tau lives in registers: a jump table of NQ one-line cases instead of NQ predicated updates
                     switch (q) {
@@ -419,9 +455,14 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         for (int q = ew; q < nq; q += EW) {
             const int first = (q / NQH) * 4, ql = q % NQH;  // the four warps (one per lane quarter) that served query q
             WarpTopK<KPL> lst;
+            if (LMODE == LM_SHARED) {  // already one list per query
 #pragma unroll
-            for (int j = 0; j < KPL; ++j) lst.e[j] = lists[(static_cast<size_t>(first) * NQH + ql) * CAP + j * 32 + lane];
-            for (int w = 1; w < 4; ++w) lst.merge_sorted(lists + (static_cast<size_t>(first + w) * NQH + ql) * CAP, CAP, CAP, lane);
+                for (int j = 0; j < KPL; ++j) lst.e[j] = lists[static_cast<size_t>(q) * CAP + j * 32 + lane];
+            } else {
+#pragma unroll
+                for (int j = 0; j < KPL; ++j) lst.e[j] = lists[(static_cast<size_t>(first) * NQH + ql) * CAP + j * 32 + lane];
+                for (int w = 1; w < 4; ++w) lst.merge_sorted(lists + (static_cast<size_t>(first + w) * NQH + ql) * CAP, CAP, CAP, lane);
+            }
             uint64_t *dst = partials + (static_cast<size_t>(cta) * nq_total + q0 + q) * ksel;
 #pragma unroll
             for (int j = 0; j < KPL; ++j) dst[j * 32 + lane] = lst.e[j];
@@ -445,11 +486,12 @@ cudaError_t launch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CUte
     const mma::SmallPlan<NQ, KPL, SPLIT> plan(k_chunks);
     if (alloc_out) {  // planning only: does this instance fit, and with how deep a ring?
         *alloc_out = plan.stages >= mma::S_MIN_STAGES ? plan.alloc : 0;
-        if (list_elems_out) *list_elems_out = KPL >= 4 ? mma::SmallPlan<NQ, KPL, SPLIT>::LIST_ELEMS : 0;
+        if (list_elems_out)
+            *list_elems_out = mma::SmallPlan<NQ, KPL, SPLIT>::LMODE == mma::LM_GLOBAL ? mma::SmallPlan<NQ, KPL, SPLIT>::LIST_ELEMS : 0;
         return cudaSuccess;
     }
     if (plan.stages < mma::S_MIN_STAGES) return cudaErrorInvalidValue;
-    if (KPL >= 4 && a.list_scratch == nullptr) return cudaErrorInvalidValue;
+    if (mma::SmallPlan<NQ, KPL, SPLIT>::LMODE == mma::LM_GLOBAL && a.list_scratch == nullptr) return cudaErrorInvalidValue;
     auto kern = mma::scan_mma_small_kernel<NQ, KPL, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.alloc));
     if (e != cudaSuccess) return e;

@@ -250,6 +250,30 @@ int fr_maxsim_aggregate_device(int device, const float *d_dist, const int64_t *d
                                int kp, int group_shift, int k_out, double *d_out_score,
                                int64_t *d_out_group, void *stream);
 
+/* ---- query-side encoder ---------------------------------------------------------------------
+ * Replaces the per-query BERT forward pass the reference runs on the CPU before every search:
+ * SentenceTransformer(...).encode(q) at rag_backend.py:677 / parent_child/retriever.py:87, i.e. the computation
+ * local_embedder.py:155-191 spells out (embeddings -> 12 transformer layers -> pooling :171-179 -> L2 normalisation :182)
+ * for the two 12-layer BERT-384 encoders of the ensemble (local_models/BAAI-bge-small-en-v1.5: CLS pooling,
+ * local_models/thenlper-gte-small: mean pooling; local_models/<model>/1_Pooling/config.json).  Tokenisation stays on the
+ * host; the output block is laid out as fr_index_search_device / fr_group_search_device read their queries, so a
+ * query batch goes from token ids to results without leaving the device.
+ * Weights are handed over tensor by tensor under the key names of a Hugging Face BertModel state dict (fp32, host
+ * memory); fr_encoder_finalize fails, naming what is missing, until the model is complete.
+ * ids: [B][T] int32 token ids, right-padded; lens: [B] valid tokens per sequence (the attention mask);
+ * pooling: 0 = [CLS] token, 1 = mean over the valid tokens; normalize: divide by max(|x|, 1e-12);
+ * out: [B][hidden] fp32; hidden_or_null: optionally the last hidden state [B][T][hidden] (tests). */
+typedef struct fr_encoder fr_encoder;
+int fr_encoder_create(int device, int vocab_size, int hidden_size, int num_layers, int num_heads, int intermediate_size,
+                      int max_position_embeddings, int type_vocab_size, float layer_norm_eps, fr_encoder **out);
+int fr_encoder_destroy(fr_encoder *enc);
+int fr_encoder_set_tensor(fr_encoder *enc, const char *name, const float *data, int64_t n, int *out_used);
+int fr_encoder_finalize(fr_encoder *enc);
+int fr_encoder_forward(fr_encoder *enc, const int32_t *ids, const int32_t *lens, int B, int T, int pooling, int normalize,
+                       float *out, float *hidden_or_null);
+int fr_encoder_forward_device(fr_encoder *enc, const int32_t *d_ids, const int32_t *d_lens, int B, int T, int pooling,
+                              int normalize, float *d_out, float *d_hidden_or_null, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
