@@ -84,6 +84,22 @@ __device__ __forceinline__ uint64_t reverse32(uint64_t x, int lane) {
     return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
+// Fold 32 keys sorted descending (one per lane, 0 = none) into a sorted list of 32 KPL entries held in registers
+// (entry i in lane i & 31, slot i >> 5): the elementwise max / min of a descending block and the reversed carry are
+// bitonic sequences holding the top / bottom 32 of their union; the bottom half carries on to the next block and what
+// falls off the end is dropped.
+template <int KPL>
+__device__ __forceinline__ void fold_sorted32(uint64_t (&L)[KPL], uint64_t p_sorted, int lane) {
+    uint64_t carry = p_sorted;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+        const uint64_t r = reverse32(carry, lane);
+        const uint64_t hi = bitonic_merge32_desc(umax64(L[j], r), lane);
+        if (j + 1 < KPL) carry = bitonic_merge32_desc(umin64(L[j], r), lane);
+        L[j] = hi;
+    }
+}
+
 // A top-K list held by one warp in registers: entry i lives in lane (i & 31), slot (i >> 5).
 // Entries are sorted descending by packed key.  KPL slots per lane => capacity 32*KPL.
 template <int KPL>

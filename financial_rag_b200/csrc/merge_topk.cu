@@ -47,48 +47,75 @@ __device__ __forceinline__ int64_t shard_key_of(uint64_t key, const uint64_t *__
     return shard_keys[base + lo];
 }
 
+// k in (32, 256]: a partial list is 32-entry blocks sorted descending, block after block.  Folding a block into the
+// running top-(32 KPL) list (registers: entry i in lane i & 31, slot i >> 5) is one bitonic network (fold_sorted32), and a
+// list is abandoned at the first block whose best entry does not beat the running list's last one.  8 warps fold P / 8
+// lists each, then a 3-level tree through shared memory.  (The first version inserted candidates one at a time:
+// 178 us for ONE query's 148 lists of 128 -- cfg3's top-50 -- against ~15 us now; profiles/r02_launches_cfg3_b64.txt.)
+template <int KPL>
+__device__ __forceinline__ uint64_t wide_last(const uint64_t (&R)[KPL]) {
+    const uint32_t lo = __shfl_sync(FULL_MASK, static_cast<uint32_t>(R[KPL - 1]), 31);
+    const uint32_t hi = __shfl_sync(FULL_MASK, static_cast<uint32_t>(R[KPL - 1] >> 32), 31);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+// folds one sorted list (`n` entries readable at src, `load(i)` yields entry i or 0) into R
+template <int KPL, typename Load>
+__device__ __forceinline__ void wide_fold_list(uint64_t (&R)[KPL], int n, int lane, Load load) {
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const uint64_t key = load(i0 + lane);
+        const uint32_t hlo = __shfl_sync(FULL_MASK, static_cast<uint32_t>(key), 0);
+        const uint32_t hhi = __shfl_sync(FULL_MASK, static_cast<uint32_t>(key >> 32), 0);
+        const uint64_t head = (static_cast<uint64_t>(hhi) << 32) | hlo;
+        if (head == 0ull || head <= wide_last<KPL>(R)) break;  // sorted: nothing further in this list can enter
+        fold_sorted32<KPL>(R, key, lane);
+    }
+}
+
 template <int KPL, bool SHARDS>
-__global__ void __launch_bounds__(128)
-merge_topk_kernel(const uint64_t *__restrict__ packed, int P, int64_t shard_stride, int B, int k,
-                  const int64_t *__restrict__ row_keys, const int64_t *__restrict__ shard_keys, bool l2,
-                  float *__restrict__ out_dist, uint64_t *__restrict__ out_packed,
-                  int64_t *__restrict__ out_keys, const uint8_t *__restrict__ only_flagged,
-                  const int *__restrict__ limit, int cyclic_w) {
-    __shared__ uint64_t lists[4 * 32 * KPL];
+__global__ void __launch_bounds__(256)
+merge_topk_wide_kernel(const uint64_t *__restrict__ packed, int P, int64_t shard_stride, int B, int k,
+                       const int64_t *__restrict__ row_keys, const int64_t *__restrict__ shard_keys, bool l2,
+                       float *__restrict__ out_dist, uint64_t *__restrict__ out_packed,
+                       int64_t *__restrict__ out_keys, const uint8_t *__restrict__ only_flagged,
+                       const int *__restrict__ limit, int cyclic_w) {
+    constexpr int CAP = 32 * KPL;
+    __shared__ uint64_t lists[8][CAP];
     const int b = blockIdx.x;
     if (only_flagged != nullptr && only_flagged[b] == 0) return;  // uniform per CTA
     if (limit != nullptr && b >= *limit) return;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int nwarps = blockDim.x >> 5;
-
-    WarpTopK<KPL> tk[1];
-    tk[0].clear();
-    uint64_t thr = 0ull;
-    for (int p = warp; p < P; p += nwarps) {
+    uint64_t R[KPL];
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) R[j] = 0ull;
+    for (int p = warp; p < P; p += 8) {
         const uint64_t *src = packed + static_cast<int64_t>(p) * shard_stride + static_cast<int64_t>(b) * k;
-        for (int i0 = 0; i0 < k; i0 += 32) {
-            const int i = i0 + lane;
-            uint64_t key = (i < k) ? src[i] : 0ull;
+        wide_fold_list<KPL>(R, k, lane, [&](int i) -> uint64_t {
+            uint64_t key = i < k ? src[i] : 0ull;
             if (SHARDS && key != 0ull) key = shard_order_key(key, p, i, k, cyclic_w);
-            unsigned m = __ballot_sync(FULL_MASK, key != 0ull && key > thr);
-            if (m == 0u) break;  // list is sorted: nothing further in it can enter
-            while (m) {
-                const int srcl = __ffs(m) - 1;
-                m &= m - 1;
-                const uint64_t kk = __shfl_sync(FULL_MASK, key, srcl);
-                tk[0].insert(kk, k, lane);
-            }
-            thr = tk[0].kth(k);
+            return key;
+        });
+    }
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) lists[warp][j * 32 + lane] = R[j];
+    for (int stride = 4; stride > 0; stride >>= 1) {
+        __syncthreads();
+        if (warp < stride) {
+            const uint64_t *src = lists[warp + stride];
+            wide_fold_list<KPL>(R, CAP, lane, [&](int i) -> uint64_t { return src[i]; });
+        }
+        __syncthreads();
+        if (warp < stride) {
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) lists[warp][j * 32 + lane] = R[j];
         }
     }
-    cta_merge_lists<KPL, 1>(tk, lists, nwarps, warp, lane, k);
     if (warp != 0) return;
 #pragma unroll
     for (int j = 0; j < KPL; ++j) {
         const int i = j * 32 + lane;
         if (i >= k) continue;
-        const uint64_t key = tk[0].e[j];
+        const uint64_t key = R[j];
         const int64_t o = static_cast<int64_t>(b) * k + i;
         if (key == 0ull) {
             if (out_dist) out_dist[o] = INFINITY;
@@ -96,14 +123,13 @@ merge_topk_kernel(const uint64_t *__restrict__ packed, int P, int64_t shard_stri
             out_keys[o] = -1;
             continue;
         }
-        const uint32_t idx = key_row(key);
         const float s = key_score(key);
         if (out_dist) out_dist[o] = l2 ? -s : 1.0f - s;
         if (out_packed) out_packed[o] = key;
         if (SHARDS) {
             out_keys[o] = shard_key_of(key, packed, shard_keys, shard_stride, b, k, cyclic_w);
         } else {
-            out_keys[o] = row_keys[idx];
+            out_keys[o] = row_keys[key_row(key)];
         }
     }
 }
@@ -166,11 +192,11 @@ merge_topk32_kernel(const uint64_t *__restrict__ packed, int P, int64_t shard_st
 
 cudaError_t launch_merge_topk(const MergeArgs &a) {
     if (a.B <= 0) return cudaSuccess;
-    const dim3 grid(a.B), block(128);
-#define FR_MERGE(KPL, SH)                                                                          \
-    merge_topk_kernel<KPL, SH><<<grid, block, 0, a.stream>>>(a.packed, a.P, a.shard_stride, a.B, a.k, \
-                                                             a.row_keys, a.shard_keys, a.l2, a.out_dist, \
-                                                             a.out_packed, a.out_keys, a.only_flagged, a.limit, a.cyclic_world)
+    const dim3 grid(a.B);
+#define FR_MERGE(KPL, SH)                                                                               \
+    merge_topk_wide_kernel<KPL, SH><<<grid, 256, 0, a.stream>>>(a.packed, a.P, a.shard_stride, a.B, a.k, a.row_keys,      \
+                                                                a.shard_keys, a.l2, a.out_dist, a.out_packed, a.out_keys, \
+                                                                a.only_flagged, a.limit, a.cyclic_world)
     if (a.k <= 32) {
         if (a.shards)
             merge_topk32_kernel<true><<<grid, 256, 0, a.stream>>>(a.packed, a.P, a.shard_stride, a.B, a.k, a.row_keys,
@@ -180,10 +206,12 @@ cudaError_t launch_merge_topk(const MergeArgs &a) {
             merge_topk32_kernel<false><<<grid, 256, 0, a.stream>>>(a.packed, a.P, a.shard_stride, a.B, a.k, a.row_keys,
                                                                   a.shard_keys, a.l2, a.out_dist, a.out_packed, a.out_keys,
                                                                   a.only_flagged, a.limit, a.cyclic_world);
+    } else if (a.k <= 64) {
+        if (a.shards) FR_MERGE(2, true); else FR_MERGE(2, false);
     } else if (a.k <= 128) {
         if (a.shards) FR_MERGE(4, true); else FR_MERGE(4, false);
     } else if (a.k <= 256 && !a.shards) {
-        FR_MERGE(8, false);  // K2 second-chance lists
+        FR_MERGE(8, false);  // K2 second-chance lists, k' = 256
     } else {
         return cudaErrorInvalidValue;
     }

@@ -167,22 +167,6 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
            (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-// Fold 32 keys sorted descending (one per lane, 0 = none) into a sorted list of 32 KPL entries held in registers
-// (entry i in lane i & 31, slot i >> 5): the elementwise max / min of a descending block and the reversed carry are
-// bitonic sequences holding the top / bottom 32 of their union; the bottom half carries on to the next block and what
-// falls off the end is dropped.
-template <int KPL>
-__device__ __forceinline__ void fold_sorted32(uint64_t (&L)[KPL], uint64_t p_sorted, int lane) {
-    uint64_t carry = p_sorted;
-#pragma unroll
-    for (int j = 0; j < KPL; ++j) {
-        const uint64_t r = reverse32(carry, lane);
-        const uint64_t hi = bitonic_merge32_desc(umax64(L[j], r), lane);
-        if (j + 1 < KPL) carry = bitonic_merge32_desc(umin64(L[j], r), lane);
-        L[j] = hi;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,

@@ -637,36 +637,55 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
     __syncthreads();
     const uint64_t *s = sel + static_cast<size_t>(j_cta) * ksel;
     const int nwarps = blockDim.x >> 5;
-    for (int j = warp; j < ksel; j += nwarps) {
-        const uint64_t key = s[j];
-        if (key == 0ull) continue;  // warp-uniform
-        const uint32_t row = key_row(key);
-        float acc = 0.0f;
+    // two candidate rows per step and warp: their loads are issued together (a row is 3 x 256 B per warp at width 384;
+    // one row at a time left the warp waiting a full DRAM latency per candidate -- 41 us for 128 candidates)
+    for (int j = warp; j < ksel; j += 2 * nwarps) {
+        const int j1 = j + nwarps;
+        const uint64_t key0 = s[j], key1 = j1 < ksel ? s[j1] : 0ull;  // warp-uniform
+        if (key0 == 0ull && key1 == 0ull) continue;
+        const uint32_t row0 = key_row(key0 != 0ull ? key0 : key1), row1 = key_row(key1 != 0ull ? key1 : key0);
+        float acc0 = 0.0f, acc1 = 0.0f;
         if constexpr (F32ROWS) {  // fp32 collection: the exact score is taken from the fp32 row, 16 bytes per lane and step
-            const float4 *rp = reinterpret_cast<const float4 *>(corpus + static_cast<size_t>(row) * (static_cast<size_t>(dim) * 4));
+            const float4 *rp0 = reinterpret_cast<const float4 *>(corpus + static_cast<size_t>(row0) * (static_cast<size_t>(dim) * 4));
+            const float4 *rp1 = reinterpret_cast<const float4 *>(corpus + static_cast<size_t>(row1) * (static_cast<size_t>(dim) * 4));
             for (int c = lane; c < dim / 4; c += 32) {
-                const float4 w = rp[c];
+                const float4 w0 = rp0[c], w1 = rp1[c];
                 const float *qq = sq + c * 4;
-                acc = fmaf(w.x, qq[0], acc);
-                acc = fmaf(w.y, qq[1], acc);
-                acc = fmaf(w.z, qq[2], acc);
-                acc = fmaf(w.w, qq[3], acc);
+                acc0 = fmaf(w0.x, qq[0], acc0);
+                acc0 = fmaf(w0.y, qq[1], acc0);
+                acc0 = fmaf(w0.z, qq[2], acc0);
+                acc0 = fmaf(w0.w, qq[3], acc0);
+                acc1 = fmaf(w1.x, qq[0], acc1);
+                acc1 = fmaf(w1.y, qq[1], acc1);
+                acc1 = fmaf(w1.z, qq[2], acc1);
+                acc1 = fmaf(w1.w, qq[3], acc1);
             }
         } else {
             // 8-byte pieces (4 bf16) of the row, lane-strided: coalesced 256 bytes per warp step
-            const uint2 *rp = reinterpret_cast<const uint2 *>(corpus + static_cast<size_t>(row) * (static_cast<size_t>(dim) * 2));
+            const uint2 *rp0 = reinterpret_cast<const uint2 *>(corpus + static_cast<size_t>(row0) * (static_cast<size_t>(dim) * 2));
+            const uint2 *rp1 = reinterpret_cast<const uint2 *>(corpus + static_cast<size_t>(row1) * (static_cast<size_t>(dim) * 2));
             for (int c = lane; c < dim / 4; c += 32) {
-                const uint2 w = rp[c];
+                const uint2 w0 = rp0[c], w1 = rp1[c];
                 const float *qq = sq + c * 4;
-                acc = fmaf(__uint_as_float(w.x << 16), qq[0], acc);
-                acc = fmaf(__uint_as_float(w.x & 0xffff0000u), qq[1], acc);
-                acc = fmaf(__uint_as_float(w.y << 16), qq[2], acc);
-                acc = fmaf(__uint_as_float(w.y & 0xffff0000u), qq[3], acc);
+                acc0 = fmaf(__uint_as_float(w0.x << 16), qq[0], acc0);
+                acc0 = fmaf(__uint_as_float(w0.x & 0xffff0000u), qq[1], acc0);
+                acc0 = fmaf(__uint_as_float(w0.y << 16), qq[2], acc0);
+                acc0 = fmaf(__uint_as_float(w0.y & 0xffff0000u), qq[3], acc0);
+                acc1 = fmaf(__uint_as_float(w1.x << 16), qq[0], acc1);
+                acc1 = fmaf(__uint_as_float(w1.x & 0xffff0000u), qq[1], acc1);
+                acc1 = fmaf(__uint_as_float(w1.y << 16), qq[2], acc1);
+                acc1 = fmaf(__uint_as_float(w1.y & 0xffff0000u), qq[3], acc1);
             }
         }
 #pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, sft);
-        if (lane == 0) exact[j] = pack_key(acc, row);
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            acc0 += __shfl_xor_sync(FULL_MASK, acc0, sft);
+            acc1 += __shfl_xor_sync(FULL_MASK, acc1, sft);
+        }
+        if (lane == 0) {
+            if (key0 != 0ull) exact[j] = pack_key(acc0, row0);
+            if (key1 != 0ull) exact[j1] = pack_key(acc1, row1);
+        }
     }
     __syncthreads();
     if (warp != 0) return;
@@ -676,13 +695,13 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
         const uint64_t key = exact[lane];
         n_valid = __popc(__ballot_sync(FULL_MASK, key != 0ull));
         lst.e[0] = bitonic_sort32_desc(key, lane);
-    } else {
+    } else {  // sort the candidates block by block and fold the blocks together (bitonic networks, no serial inserts)
         lst.clear();
-        for (int j = 0; j < ksel; ++j) {
-            const uint64_t key = exact[j];
-            if (key == 0ull) continue;
-            ++n_valid;
-            lst.insert(key, 32 * KPL, lane);
+#pragma unroll
+        for (int blk = 0; blk < KPL; ++blk) {
+            const uint64_t key = blk * 32 + lane < ksel ? exact[blk * 32 + lane] : 0ull;
+            n_valid += __popc(__ballot_sync(FULL_MASK, key != 0ull));
+            fold_sorted32<KPL>(lst.e, bitonic_sort32_desc(key, lane), lane);
         }
     }
     // certification: a row outside the candidate set has a selection score <= ceiling (the k'-th selection score of
