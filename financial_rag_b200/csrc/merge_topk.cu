@@ -58,11 +58,12 @@ __device__ __forceinline__ uint64_t wide_last(const uint64_t (&R)[KPL]) {
     const uint32_t hi = __shfl_sync(FULL_MASK, static_cast<uint32_t>(R[KPL - 1] >> 32), 31);
     return (static_cast<uint64_t>(hi) << 32) | lo;
 }
-// folds one sorted list (`n` entries readable at src, `load(i)` yields entry i or 0) into R
+// folds one sorted list (`n` entries, `load(i)` yields entry i or 0; `first` = its block 0, loaded by the caller ahead
+// of time so that the next list's load overlaps this list's networks) into R
 template <int KPL, typename Load>
-__device__ __forceinline__ void wide_fold_list(uint64_t (&R)[KPL], int n, int lane, Load load) {
+__device__ __forceinline__ void wide_fold_list(uint64_t (&R)[KPL], int n, int lane, uint64_t first, Load load) {
     for (int i0 = 0; i0 < n; i0 += 32) {
-        const uint64_t key = load(i0 + lane);
+        const uint64_t key = i0 == 0 ? first : load(i0 + lane);
         const uint32_t hlo = __shfl_sync(FULL_MASK, static_cast<uint32_t>(key), 0);
         const uint32_t hhi = __shfl_sync(FULL_MASK, static_cast<uint32_t>(key >> 32), 0);
         const uint64_t head = (static_cast<uint64_t>(hhi) << 32) | hlo;
@@ -88,13 +89,17 @@ merge_topk_wide_kernel(const uint64_t *__restrict__ packed, int P, int64_t shard
     uint64_t R[KPL];
 #pragma unroll
     for (int j = 0; j < KPL; ++j) R[j] = 0ull;
+    auto entry = [&](int p, int i) -> uint64_t {
+        if (p >= P || i >= k) return 0ull;
+        uint64_t key = packed[static_cast<int64_t>(p) * shard_stride + static_cast<int64_t>(b) * k + i];
+        if (SHARDS && key != 0ull) key = shard_order_key(key, p, i, k, cyclic_w);
+        return key;
+    };
+    uint64_t next = entry(warp, lane);
     for (int p = warp; p < P; p += 8) {
-        const uint64_t *src = packed + static_cast<int64_t>(p) * shard_stride + static_cast<int64_t>(b) * k;
-        wide_fold_list<KPL>(R, k, lane, [&](int i) -> uint64_t {
-            uint64_t key = i < k ? src[i] : 0ull;
-            if (SHARDS && key != 0ull) key = shard_order_key(key, p, i, k, cyclic_w);
-            return key;
-        });
+        const uint64_t cur = next;
+        next = entry(p + 8, lane);
+        wide_fold_list<KPL>(R, k, lane, cur, [&](int i) -> uint64_t { return entry(p, i); });
     }
 #pragma unroll
     for (int j = 0; j < KPL; ++j) lists[warp][j * 32 + lane] = R[j];
@@ -102,7 +107,7 @@ merge_topk_wide_kernel(const uint64_t *__restrict__ packed, int P, int64_t shard
         __syncthreads();
         if (warp < stride) {
             const uint64_t *src = lists[warp + stride];
-            wide_fold_list<KPL>(R, CAP, lane, [&](int i) -> uint64_t { return src[i]; });
+            wide_fold_list<KPL>(R, CAP, lane, src[lane], [&](int i) -> uint64_t { return src[i]; });
         }
         __syncthreads();
         if (warp < stride) {
