@@ -51,6 +51,24 @@ def parse_devices(spec: Optional[str]) -> Optional[List[int]]:
     return [int(x) for x in spec.split(",") if x.strip()]
 
 
+def exchange_nccl_id(device: Optional[int] = None, group=None) -> bytes:
+    """Rank 0 of an initialised torch.distributed group creates an NCCL unique id (fr_nccl_unique_id) and every rank
+    receives it: the only thing torch.distributed carries for a multi-process ShardGroup.  ``device``: CUDA ordinal
+    when the process group's backend is NCCL (its broadcast wants device tensors); None for gloo."""
+    import torch
+    import torch.distributed as dist
+
+    _lib.ensure_nccl()
+    buf = ctypes.create_string_buffer(128)
+    if dist.get_rank(group) == 0:
+        check(_lib.load().fr_nccl_unique_id(buf, 128))
+    t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+    if dist.get_backend(group) == "nccl":
+        t = t.to(torch.device("cuda", device))
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return bytes(t.cpu().numpy().tobytes())
+
+
 class ShardGroup:
     def __init__(self, dim: int = 384, space: str = "cosine", dtype: str = "bf16", devices: Sequence[int] = (0,),
                  reserve_rows: int = 0, exchange: str = "auto", world_shards: Optional[int] = None,
@@ -90,22 +108,13 @@ class ShardGroup:
                                reserve_rows: int = 0, group=None) -> "ShardGroup":
         """One shard per rank of an initialised torch.distributed group (torchrun); rank r owns world shard r.
         The only thing torch.distributed moves is rank 0's NCCL unique id."""
-        import torch
         import torch.distributed as dist
 
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if world == 1:
             return cls(dim, space, dtype, [device], reserve_rows)
-        _lib.ensure_nccl()
-        buf = ctypes.create_string_buffer(128)
-        if rank == 0:
-            check(_lib.load().fr_nccl_unique_id(buf, 128))
-        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-        if dist.get_backend(group) == "nccl":
-            t = t.to(torch.device("cuda", device))
-        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         return cls(dim, space, dtype, [device], reserve_rows, exchange="nccl", world_shards=world, first_shard=rank,
-                   nccl_id=bytes(t.cpu().numpy().tobytes()))
+                   nccl_id=exchange_nccl_id(device, group))
 
     # -- lifecycle / introspection -------------------------------------------------------------------------
     def close(self) -> None:
@@ -272,4 +281,4 @@ class ShardGroup:
         return out_dist, out_keys
 
 
-__all__ = ["ShardGroup", "shard_of_row", "rows_of_shard", "parse_devices"]
+__all__ = ["ShardGroup", "exchange_nccl_id", "shard_of_row", "rows_of_shard", "parse_devices"]
