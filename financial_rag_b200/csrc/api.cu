@@ -110,6 +110,8 @@ struct fr_index {
     cudaEvent_t last_use = nullptr;  // orders scratch reuse across caller streams
     DevBuf q_raw, q_prep, q_keys, partials, out_dist, out_keys, stage_vecs, stage_keys, stage_rows;
     DevBuf q_bf16, err_bound, sel, sel_keys, flags, fail, fb_partials, tau, progress, s_lists;  // K2 path
+    DevBuf cmax;             // inner-product collections: largest row norm (device float), the scale of the error bounds
+    int64_t cmax_rows = 0;   // rows it covers; an in-place overwrite resets it
     DevBuf kth_exact, r_q, r_misc, r_tau, r_partials, r_sel, r_sel_keys;     // K2 second-chance pass
     int mma_min_batch = 2;  // FR_PATH_AUTO: batches at least this large go to the tensor-core scans; smaller ones
                             // too when the swapped-operand kernel K2s serves them (it out-streams K1: TMA ring)
@@ -266,7 +268,24 @@ struct ProfScope {
 // K2s reads the queries as ONE bf16 term (selection error up to |q - bf16(q)|, ~1e-3) or as TWO (hi + lo, error
 // ~1e-5: nearly every query certified at once even where thousands of rows score within 1e-2 of the best).
 bool shadow_serves(const fr_index *ix) {
-    return ix->dtype == FR_F32 && ix->mma_f32_shadow && ix->metric == FR_COSINE && ix->dim == 384;
+    return ix->dtype == FR_F32 && ix->mma_f32_shadow && (ix->metric == FR_COSINE || ix->metric == FR_IP) && ix->dim == 384;
+}
+
+// inner-product collections: bring the largest row norm up to date (stream-ordered on `s`)
+int ensure_cmax(fr_index *ix, cudaStream_t s) {
+    if (ix->metric != FR_IP) return FR_OK;
+    if (!ix->cmax.p) {
+        FR_CUDA(ix->cmax.need(64));
+        ix->cmax_rows = 0;
+    }
+    if (ix->cmax_rows == 0) FR_CUDA(cudaMemsetAsync(ix->cmax.p, 0, 64, s));
+    if (ix->cmax_rows < ix->rows) {
+        const size_t rb = ix->row_bytes();
+        FR_CUDA(fr::launch_row_norm_max(ix->corpus + static_cast<size_t>(ix->cmax_rows) * rb, ix->dtype == FR_BF16,
+                                        ix->rows - ix->cmax_rows, ix->dim, static_cast<float *>(ix->cmax.p), s));
+        ix->cmax_rows = ix->rows;
+    }
+    return FR_OK;
 }
 
 // bring the bf16 selection copy of an fp32 collection up to date (stream-ordered on `s`)
@@ -314,7 +333,7 @@ bool small_serves(const fr_index *ix, int B, int ksel) {
 }
 int mma_slice(const fr_index *ix, int k) {  // 0 = not eligible, else the largest batch one pass may take
     const int ksel = fr::scan_mma_ksel(k, ix->mma_wide_lists);
-    if (ix->metric != FR_COSINE || ksel == 0 || ix->rows <= 0) return 0;
+    if ((ix->metric != FR_COSINE && ix->metric != FR_IP) || ksel == 0 || ix->rows <= 0) return 0;
     if (ix->dtype != FR_BF16) return shadow_serves(ix) ? 1 << 30 : 0;  // fp32 rows: selection on a bf16 copy
     if (ix->dim == 384) return 1 << 30;
     if (ix->dim != 768) return 0;  // the re-scan safety net exists for 384 and 768 only
@@ -405,7 +424,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
         }
     }
     FR_CUDA(ix->q_bf16.need(static_cast<size_t>(nq_pad) * ix->dim * 2 * (1 + split)));
-    FR_CUDA(ix->err_bound.need(4 * static_cast<size_t>(B) * sizeof(float)));  // |e| one-term | two-term | |e.q| one-term | two-term
+    FR_CUDA(ix->err_bound.need(5 * static_cast<size_t>(B) * sizeof(float)));  // |e| one-term | two-term | |e.q| one-term | two-term | 1/scale
     FR_CUDA(ix->partials.need(static_cast<size_t>(grid) * B * ksel * sizeof(uint64_t)));
     FR_CUDA(ix->sel.need(static_cast<size_t>(B) * ksel * sizeof(uint64_t)));
     FR_CUDA(ix->sel_keys.need(static_cast<size_t>(B) * ksel * sizeof(int64_t)));
@@ -442,6 +461,14 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     pa.ksel = ksel;
     pa.counters = counters;
     pa.n_counters = 2;
+    pa.normalize = ix->metric == FR_COSINE;
+    float *inv_scale = eb_one + 4 * static_cast<size_t>(B);
+    if (ix->metric == FR_IP) {
+        int rcm = ensure_cmax(ix, s);
+        if (rcm != FR_OK) return rcm;
+        pa.cmax = static_cast<const float *>(ix->cmax.p);
+    }
+    pa.inv_scale = inv_scale;
     pa.stream = s;
     FR_CUDA(fr::launch_prep_queries(pa));
     const float *q = pa.q_prep;
@@ -523,6 +550,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     ra.row_keys = ix->keys;
     ra.err_bound = split ? eb_two : eb_one;
     ra.err_alpha = split ? ea_two : ea_one;
+    ra.inv_scale = inv_scale;
     ra.split = split;
     ra.B = B;
     ra.k = k;
@@ -559,6 +587,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
         rp.err_bound = eb_one;  // the second-chance scan reads one-term bf16 queries
         rp.err_alpha = ea_one;
         rp.extra_bound = extra_bound;
+        rp.inv_scale = inv_scale;
         rp.kth_exact = ra.kth_exact;
         rp.fail_count = fail_count;
         rp.fail_list = fail_list;
@@ -687,7 +716,7 @@ int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *
     const bool eligible = mma_eligible(ix, k);
     if (ix->path == FR_PATH_MMA && !eligible)
         return fail(FR_EUNSUP,
-                    "FR_PATH_MMA serves cosine collections of width 384 (bf16 or fp32 rows, k <= 100) or 768 (bf16, k <= 32) with at least one row "
+                    "FR_PATH_MMA serves cosine and inner-product collections of width 384 (bf16 or fp32 rows, k <= 100) or 768 (bf16) with at least one row "
                     "(this one: dtype %d, dim %d, metric %d, k %d, rows %lld)",
                     ix->dtype, ix->dim, ix->metric, k, (long long)ix->rows);
     const bool k2s = eligible && small_serves(ix, B, fr::scan_mma_ksel(k, ix->mma_wide_lists));
@@ -736,7 +765,7 @@ uint64_t state_hash(const fr_index *ix) {
     };
     const DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist, &ix->out_keys, &ix->q_bf16,
                             &ix->err_bound, &ix->sel, &ix->sel_keys, &ix->flags, &ix->fail, &ix->fb_partials, &ix->tau,
-                            &ix->progress, &ix->s_lists, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau, &ix->r_partials, &ix->r_sel,
+                            &ix->progress, &ix->s_lists, &ix->cmax, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau, &ix->r_partials, &ix->r_sel,
                             &ix->r_sel_keys};
     for (const DevBuf *b : bufs) mix(reinterpret_cast<uintptr_t>(b->p));
     mix(reinterpret_cast<uintptr_t>(ix->pin.p));
@@ -746,6 +775,7 @@ uint64_t state_hash(const fr_index *ix) {
     mix(static_cast<uint64_t>(ix->shadow_rows) * 2u + (ix->shadow_dirty ? 1u : 0u));
     mix(reinterpret_cast<uintptr_t>(ix->keys));
     mix(static_cast<uint64_t>(ix->rows));
+    mix(static_cast<uint64_t>(ix->cmax_rows));
     mix(ix->n_deleted > 0 ? 1u : 0u);
     for (int v : {ix->path, ix->mma_min_batch, ix->mma_small_max, ix->mma_co_groups, ix->mma_split, ix->mma_split_max,
                   ix->mma_debug, ix->mma_bound_scale_pct, ix->mma_max_lead, ix->mma_wide_lists, ix->mma_f32_shadow,
@@ -860,7 +890,7 @@ int fr_index_destroy(fr_index *ix) {
         DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist,
                           &ix->out_keys, &ix->stage_vecs, &ix->stage_keys, &ix->stage_rows,
                           &ix->q_bf16, &ix->err_bound, &ix->sel, &ix->sel_keys, &ix->flags, &ix->fail,
-                          &ix->fb_partials, &ix->tau, &ix->progress, &ix->s_lists, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau,
+                          &ix->fb_partials, &ix->tau, &ix->progress, &ix->s_lists, &ix->cmax, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau,
                           &ix->r_partials, &ix->r_sel, &ix->r_sel_keys};
         for (DevBuf *b : bufs) b->release();
         ix->pin.release();
@@ -1077,7 +1107,10 @@ int fr_index_upsert(fr_index *ix, const float *vecs, const int64_t *keys, int64_
         ix->keymap_valid = false;
         return fail(FR_EUNSUP, "a shard holds at most 2^32-16 rows");
     }
-    if (static_cast<int64_t>(last_writer.size()) != new_rows - ix->rows) ix->shadow_dirty = true;  // an existing row is overwritten
+    if (static_cast<int64_t>(last_writer.size()) != new_rows - ix->rows) {  // an existing row is overwritten
+        ix->shadow_dirty = true;
+        ix->cmax_rows = 0;  // (the maximum is recomputed over all rows: an overwrite may have raised it)
+    }
     rc = grow(ix, new_rows, false);
     if (rc != FR_OK) {
         ix->keymap_valid = false;  // the map now names rows that were never written

@@ -87,8 +87,13 @@ struct PrepArgs {
     float bound_scale;  // >= 1: inflates the error bounds (diagnostics: forces second-chance passes; never unsafe)
     int *counters;      // n_counters ints zeroed here (failure counters of the call)
     int n_counters;
+    bool normalize;     // cosine collections; inner-product collections read the raw query
+    const float *cmax;  // device scalar: largest row norm (inner product), null = rows of norm <= 1.004 (cosine)
+    float *inv_scale;   // [nq] out: 1 / (|q| * max row norm) -- 1 for cosine -- the scale of the absolute error slacks
     cudaStream_t stream;
 };
+// largest row norm of rows [0, n) folded into *out by atomicMax (a float >= 0 stored as its bits)
+cudaError_t launch_row_norm_max(const void *rows, bool bf16, int64_t n, int dim, float *out, cudaStream_t s);
 cudaError_t launch_prep_queries(const PrepArgs &a);
 cudaError_t launch_scan_mma(const MmaScanArgs &a);
 // K2s (scan_mma_small.cu): operands swapped for 1..64 queries, k' <= 64.  Uses plan.lists CTAs per launch;
@@ -106,6 +111,7 @@ struct RescoreArgs {
     const uint8_t *corpus;   // the rows the collection stores: bf16, or fp32 when f32_rows
     int f32_rows;            // the scan read a bf16 copy of fp32 rows: exact scores come from the fp32 rows, and
     float extra_bound;       // the copy's rounding (<= 2^-9 sum|q_i c_i| <= 2^-9) widens the certification bound
+    const float *inv_scale;  // [B] or null: see PrepArgs (absolute slacks are divided by it)
     const int64_t *row_keys;
     const float *err_bound;  // [B] |e|_2, e = q - (what the scan read)
     const float *err_alpha;  // [B] |e . q|
@@ -135,6 +141,7 @@ struct RetryPrepArgs {
     const float *err_bound;   // [B] |q - bf16(q)|_2 (the second-chance scan reads plain bf16 queries)
     const float *err_alpha;   // [B] |(q - bf16(q)) . q|
     float extra_bound;        // see RescoreArgs
+    const float *inv_scale;   // [B] or null
     const float *kth_exact;   // [B]
     const int *fail_count;    // first-pass failures
     const int *fail_list;

@@ -507,7 +507,8 @@ __global__ void prep_queries_kernel(const float *__restrict__ raw, int nq, int n
                                     __nv_bfloat16 *__restrict__ qb, float *__restrict__ err_bound,
                                     float *__restrict__ err_bound_split, float *__restrict__ err_alpha,
                                     float *__restrict__ err_alpha_split, int split, uint32_t *__restrict__ tau_g, int ksel,
-                                    int *__restrict__ counters, int n_counters, float bound_scale) {
+                                    int *__restrict__ counters, int n_counters, float bound_scale, int normalize,
+                                    const float *__restrict__ cmax, float *__restrict__ inv_scale) {
     const int row = blockIdx.x;
     const int lane = threadIdx.x;  // 32 threads
     if (row == 0 && lane < n_counters) counters[lane] = 0;
@@ -532,7 +533,9 @@ __global__ void prep_queries_kernel(const float *__restrict__ raw, int nq, int n
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, s);
-    const float inv = 1.0f / (sqrtf(ss) + 1e-30f);
+    // cosine: the query is normalised (K0's arithmetic).  Inner-product collections (FR_IP) score the raw query against
+    // raw rows: nothing is normalised, and every absolute error bound below scales with |q| * (largest row norm).
+    const float inv = normalize ? 1.0f / (sqrtf(ss) + 1e-30f) : 1.0f;
     float4 *p4 = reinterpret_cast<float4 *>(q_prep + static_cast<size_t>(row) * dim);
     float es = 0.0f, es2 = 0.0f, al = 0.0f, al2 = 0.0f;  // |e|^2 and e . q of the one-term / two-term residual e
     for (int c = lane; c < c4; c += 32) {
@@ -582,11 +585,19 @@ __global__ void prep_queries_kernel(const float *__restrict__ raw, int nq, int n
     }
     if (lane == 0) {
         // bound_scale > 1 (option "mma_bound_scale_pct", tests) only makes the certification stricter
-        err_bound[row] = sqrtf(es) * bound_scale;
-        err_alpha[row] = fabsf(al) * bound_scale;
+        // selection_error_bound() is written for |q| = 1 and rows of norm <= L.  In general, with C the largest row norm,
+        // e . c = (e . q^)(c . q^) + e_perp . c_perp, q^ = q / |q|: evaluated at the NORMALISED score t / (|q| C) with
+        // E = |e| C and A = |e . q| C / |q| the same formula bounds the selection error in absolute score units.
+        const float qn = normalize ? 1.0f : sqrtf(ss);
+        const float cm = cmax != nullptr ? *cmax : 1.0f;
+        const float scale = fmaxf(qn * cm, 1e-30f);
+        const float a_scale = cm / fmaxf(qn, 1e-30f);
+        if (inv_scale) inv_scale[row] = 1.0f / scale;
+        err_bound[row] = sqrtf(es) * bound_scale * cm;
+        err_alpha[row] = fabsf(al) * bound_scale * a_scale;
         if (split) {
-            err_bound_split[row] = sqrtf(es2) * bound_scale;
-            err_alpha_split[row] = fabsf(al2) * bound_scale;
+            err_bound_split[row] = sqrtf(es2) * bound_scale * cm;
+            err_alpha_split[row] = fabsf(al2) * bound_scale * a_scale;
         }
     }
     (void)nq_pad;
@@ -625,7 +636,7 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
                int *__restrict__ fail_count, int *__restrict__ fail_list, unsigned long long *__restrict__ fail_total,
                float *__restrict__ kth_exact_out, const int *__restrict__ idx_list, const int *__restrict__ limit,
                const float *__restrict__ tau0, int dim, unsigned long long *__restrict__ fail_total2, float acc_slack,
-               float extra_bound) {
+               float extra_bound, const float *__restrict__ inv_scale) {
     __shared__ float sq[RESCORE_MAX_DIM];
     __shared__ uint64_t exact[32 * KPL];
     const int j_cta = blockIdx.x;
@@ -712,8 +723,11 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
     const float kth_exact = n_valid >= k ? key_score(lst.kth(k)) : -INFINITY;
     // (extra_bound: the scan scored a bf16 copy c16 of an fp32 row c; q . (c - c16) is at most 2^-9 sum|q_i c_i|, so a
     //  row whose exact score reaches t scores at least t - extra_bound against the query on the copy)
-    const float t_copy = kth_exact - extra_bound;
-    const float floor_sel = t_copy - selection_error_bound(t_copy, err_bound[b], err_alpha[b]) - acc_slack;
+    // (inner-product collections: the absolute slacks scale with |q| * max row norm = 1 / inv_scale, and the bound is
+    //  evaluated at the normalised score -- see prep_queries_kernel; cosine: inv_scale = 1)
+    const float isc = inv_scale != nullptr ? inv_scale[b] : 1.0f;
+    const float t_copy = kth_exact - extra_bound / isc;
+    const float floor_sel = t_copy - selection_error_bound(t_copy * isc, err_bound[b], err_alpha[b]) - acc_slack / isc;
     bool certified = true;
     if (last_sel != 0ull) {                       // list full: ceiling = the k'-th selection score
         certified = n_valid >= k && floor_sel > key_score(last_sel);
@@ -764,7 +778,7 @@ __global__ void retry_prep_kernel(const float *__restrict__ queries, const float
                                   float *__restrict__ tau0, int *__restrict__ retry_n, uint32_t *__restrict__ tau_g_retry,
                                   int ksel, uint8_t *__restrict__ flags, int slices, int *__restrict__ fail_count2,
                                   int *__restrict__ fail_list2, unsigned long long *__restrict__ rescanned_total,
-                                  int *__restrict__ host_mirror) {
+                                  int *__restrict__ host_mirror, const float *__restrict__ inv_scale) {
     const int j = blockIdx.x;  // retry slot
     const int slice = j / RETRY_MAX, jj = j % RETRY_MAX;
     const int lane = threadIdx.x;
@@ -791,13 +805,50 @@ __global__ void retry_prep_kernel(const float *__restrict__ queries, const float
     for (int e = lane; e < DIM; e += 32)
         qb_retry[static_cast<size_t>(j) * DIM + e] = __float2bfloat16_rn(on ? queries[static_cast<size_t>(b) * DIM + e] : 0.0f);
     if (lane == 0) {
-        const float t_copy = on ? kth_exact[b] - extra_bound : 0.0f;
-        tau0[j] = on ? t_copy - selection_error_bound(t_copy, err_bound[b], err_alpha[b]) - 2e-5f : INFINITY;
+        const float isc = (on && inv_scale != nullptr) ? inv_scale[b] : 1.0f;
+        const float t_copy = on ? kth_exact[b] - extra_bound / isc : 0.0f;
+        tau0[j] = on ? t_copy - selection_error_bound(t_copy * isc, err_bound[b], err_alpha[b]) - 2e-5f / isc : INFINITY;
         if (on) flags[b] = 1;  // stays flagged until the second rescore pass certifies it
     }
 }
 
+// Largest row norm of rows [0, n) (inner-product collections: the scale of every selection error bound).  Warp per row.
+template <bool BF16>
+__global__ void row_norm_max_kernel(const uint8_t *__restrict__ rows, int64_t n, int dim, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    float mx = 0.0f;
+    for (int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); r < n;
+         r += static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5)) {
+        float ss = 0.0f;
+        if (BF16) {
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(rows + static_cast<size_t>(r) * dim * 2);
+            for (int c = lane; c < dim / 2; c += 32) {
+                const uint32_t w = p[c];
+                const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
+                ss = fmaf(a, a, fmaf(b, b, ss));
+            }
+        } else {
+            const float *p = reinterpret_cast<const float *>(rows + static_cast<size_t>(r) * dim * 4);
+            for (int c = lane; c < dim; c += 32) ss = fmaf(p[c], p[c], ss);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, o);
+        mx = fmaxf(mx, ss);
+    }
+    // (1 + 2^-7): fp32 summation noise, and for fp32 rows the bf16 copy the scan reads may be 2^-9 longer
+    if (lane == 0 && mx > 0.0f) atomicMax(reinterpret_cast<unsigned int *>(out), __float_as_uint(sqrtf(mx) * 1.0078125f));
+}
+
 }  // namespace mma
+
+cudaError_t launch_row_norm_max(const void *rows, bool bf16, int64_t n, int dim, float *out, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    const int grid = static_cast<int>(n / 8 + 1 < 148 * 8 ? n / 8 + 1 : 148 * 8);
+    if (bf16) mma::row_norm_max_kernel<true><<<grid, 256, 0, s>>>(static_cast<const uint8_t *>(rows), n, dim, out);
+    else mma::row_norm_max_kernel<false><<<grid, 256, 0, s>>>(static_cast<const uint8_t *>(rows), n, dim, out);
+    count_launch();
+    return cudaGetLastError();
+}
 
 // ---- host launchers ---------------------------------------------------------------------------
 // candidates kept per query: k' > k leaves the certification a margin (k' - k rows may overtake)
@@ -815,7 +866,8 @@ cudaError_t launch_prep_queries(const PrepArgs &a) {
     mma::prep_queries_kernel<<<a.nq_pad, 32, 0, a.stream>>>(a.raw, a.nq, a.nq_pad, a.dim, a.q_prep,
                                                            static_cast<__nv_bfloat16 *>(a.qb), a.err_bound, a.err_bound_split,
                                                            a.err_alpha, a.err_alpha_split, a.split, a.tau_g, a.ksel,
-                                                           a.counters, a.n_counters, a.bound_scale >= 1.0f ? a.bound_scale : 1.0f);
+                                                           a.counters, a.n_counters, a.bound_scale >= 1.0f ? a.bound_scale : 1.0f,
+                                                           a.normalize ? 1 : 0, a.cmax, a.inv_scale);
     count_launch();
     return cudaGetLastError();
 }
@@ -915,7 +967,7 @@ cudaError_t launch_rescore(const RescoreArgs &a) {
                                                             a.fail_total, a.kth_exact, a.idx_list, a.limit, a.tau0, \
                                                             a.dim, a.fail_total2,                                   \
                                                             1e-5f * static_cast<float>(((a.dim + 383) / 384) * (1 + a.split)), \
-                                                            a.extra_bound)
+                                                            a.extra_bound, a.inv_scale)
 #define FR_RESCORE(KPL)                  \
     do {                                 \
         if (a.f32_rows) FR_RESCORE_T(KPL, true); \
@@ -941,7 +993,7 @@ cudaError_t launch_retry_prep(const RetryPrepArgs &a) {
     mma::retry_prep_kernel<<<a.slices * mma::RETRY_MAX, 32, 0, a.stream>>>(a.queries, a.err_bound, a.err_alpha, a.extra_bound, a.kth_exact, a.fail_count,
                                                                          a.fail_list, static_cast<__nv_bfloat16 *>(a.qb_retry),
                                                                          a.tau0, a.retry_n, a.tau_g_retry, a.ksel, a.flags, a.slices, a.fail_count2,
-                                                                         a.fail_list2, a.rescanned_total, a.host_mirror);
+                                                                         a.fail_list2, a.rescanned_total, a.host_mirror, a.inv_scale);
     count_launch();
     return cudaGetLastError();
 }

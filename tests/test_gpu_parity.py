@@ -379,8 +379,10 @@ def test_multivector_caller_shape(frb, tmp_path):
     frb.reset_registry()
 
 
-def test_million_rows_strict_gate(frb):
-    """1M x 384 bf16, planted neighbours: high scores, so the north-star gate applies verbatim."""
+def test_million_rows_gate_with_storage_bound(frb):
+    """1M x 384 bf16 Gaussian rows with planted neighbours.  Top scores of the random queries are ~0.25, where a
+    RELATIVE 1e-3 is finer than bf16 storage rounding itself, so the gate carries the rigorous storage bound
+    (strict=False); the literal gate is applied below on a clustered corpus and measured by bench.py (``parity``)."""
     n, B, k = 1_000_000, 8, 10
     g = torch.Generator(device="cuda").manual_seed(1234)
     c = torch.randn((n, 384), generator=g, device="cuda", dtype=torch.float32)
@@ -393,6 +395,24 @@ def test_million_rows_strict_gate(frb):
     # planted queries (even indices): their source row is top-1 with a score near 1/sqrt(1+0.01*384)...
     s = scores_from_dist(d, "cosine")
     assert (s[0::2, 0] > 0.4).all() and (s[1::2, 0] < 0.4).all()
+    ix.close()
+
+
+@pytest.mark.parametrize("B,path", [(1, "auto"), (8, "mma"), (64, "mma"), (300, "mma"), (5, "stream")])
+def test_clustered_corpus_literal_north_star_gate(frb, B, path):
+    """The north-star gate taken literally (strict=True: ids equal except where the fp32 scores tie within 1e-3
+    relative, scores within 1e-3 relative, NO storage-bound slack) on the kind of data the reference holds: dense
+    neighbourhoods with top scores around 0.9, bf16 storage, every kernel."""
+    n, k = 300_000, 10
+    corpus, centres = make_clustered(n, 60, 0.35, seed=4100)
+    rng = np.random.default_rng(4101 + B)
+    queries = (centres[rng.integers(0, 60, B)] + 0.35 / np.sqrt(384.0) * rng.standard_normal((B, 384), dtype=np.float32)).astype(np.float32)
+    ix = build_index(frb, corpus, "cosine", "bf16")
+    ix.set_path(path)
+    d, kk = ix.search(queries, k)
+    assert scores_from_dist(d, "cosine")[:, 0].min() > 0.75
+    assert_matches_oracle(d, keys_to_rows(kk, KEY_BASE), queries, corpus, k, "cosine", "bf16", strict=True,
+                          stored=stored_rows(ix), label=f"literal gate B={B} {path}")
     ix.close()
 
 
@@ -448,6 +468,44 @@ def test_mma_path_matches_oracle_and_stream(frb, n, B, k):
         assert np.abs(d_m[mism] - d_s[mism]).max() <= 2e-6
     if dups and k >= 2:
         assert rows[0, 0] == 5 and rows[0, 1] == n - 3
+    ix.close()
+
+
+@pytest.mark.parametrize("n,B,k,dtype", [(300, 3, 10, "bf16"), (70001, 1, 10, "bf16"), (70001, 40, 32, "bf16"),
+                                         (50000, 200, 10, "bf16"), (40000, 600, 50, "bf16"), (30000, 130, 100, "bf16"),
+                                         (60000, 24, 10, "f32"), (60000, 300, 10, "f32")])
+def test_inner_product_collections_on_the_tensor_cores(frb, n, B, k, dtype):
+    """The metric vocabulary of the reference (pgvector_child_store.py:7-26: cosine | l2 | ip): inner-product
+    collections take the same tensor-core selection + exact rescoring as cosine ones.  Nothing is normalised, so the
+    certification bounds scale with |q| * (largest row norm) -- rows of very different lengths, long queries."""
+    rng = np.random.default_rng(n + B)
+    corpus = make_corpus(n, 384, seed=7000 + n) * rng.uniform(0.05, 3.0, size=(n, 1)).astype(np.float32)
+    queries = make_queries(B, corpus, seed=B + k) * rng.uniform(0.2, 5.0, size=(B, 1)).astype(np.float32)
+    ix = build_index(frb, corpus, "ip", dtype)
+    ix.set_path("stream")
+    d_s, k_s = ix.search(queries, k)
+    ix.set_path("mma")
+    d_m, k_m = ix.search(queries, k)
+    assert ix.stat("mma_queries") == B
+    rows = keys_to_rows(k_m, KEY_BASE)
+    assert_matches_oracle(d_m, rows, queries, corpus, k, "ip", dtype, stored=stored_rows(ix), label=f"ip n={n} B={B} k={k}")
+    # same definition in both kernels: scores agree to fp32 summation noise (relative to their size), ids up to such ties
+    tol = 3e-6 * np.maximum(np.abs(d_s), 1.0)
+    assert (np.abs(d_m - d_s) <= tol)[np.isfinite(d_s)].all()
+    mism = (k_m != k_s) & np.isfinite(d_s)
+    if mism.any():
+        assert (np.abs(d_m - d_s) <= tol)[mism].all()
+    ix.set_path("auto")
+    d_a, k_a = ix.search(queries, k)
+    np.testing.assert_array_equal(k_a, k_m) if n > 2_000_000 or B > 4 else None
+    # an overwrite with a much longer row must widen the bounds (the maximum norm is recomputed), never break exactness
+    ix.upsert(corpus[:1] * 40.0, np.array([KEY_BASE + 7]))
+    corpus2 = corpus.copy()
+    corpus2[7] = corpus[0] * 40.0
+    ix.set_path("mma")
+    d_2, k_2 = ix.search(queries, k)
+    assert_matches_oracle(d_2, keys_to_rows(k_2, KEY_BASE), queries, corpus2, k, "ip", dtype, stored=stored_rows(ix),
+                          label=f"ip after overwrite n={n} B={B} k={k}")
     ix.close()
 
 
