@@ -221,7 +221,7 @@ def scan_kernel_of(batch, path, k, dtype="bf16", rows_local=None):
             use_mma = False
     if not use_mma:
         return "scan_stream_kernel", "stream", min(batch, 4)
-    if batch <= 64 and k <= 100:
+    if batch <= 64 and (k <= 64 or batch <= 32):  # (64 queries x 256 candidates do not fit K2s's shared-memory lists)
         nq = 16 if batch <= 16 else (32 if batch <= 32 else 64)
         return f"scan_mma_small_kernel<{nq},*> (tcgen05, corpus rows as M, queries as N)", "mma_small", batch
     if batch <= 128:

@@ -7,6 +7,7 @@
 // plus grow-only scratch (query staging, per-CTA partial lists, result staging, pinned mirror).
 // Mirrors what ChromaChildStore asks of chromadb (parent_child/chroma_child_store.py:32-80).
 #include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -134,7 +135,18 @@ struct fr_index {
     int *fail_mirror = nullptr;  // pinned: first-pass failure count of the last finished search (written by retry_prep_kernel)
     DevBuf stats;           // [0] queries K2 could not certify (re-scanned by the stream kernel), cumulative
     int64_t n_searches = 0, n_queries = 0, n_mma_queries = 0;
-    PinBuf pin;
+    // Host entry point fr_index_search: concurrent callers (Flask threads, api_server.py:1366-1371) hold `mu` only while
+    // their call is ENQUEUED on the shard's stream; each then waits for its own event and copies its results out of its own
+    // pinned slot, so the host copies and waits of one search overlap the GPU work of the next.
+    struct HostSlot {
+        PinBuf pin;
+        cudaEvent_t done = nullptr;
+        bool busy = false;
+    };
+    static constexpr int N_SLOTS = 4;
+    HostSlot slots[N_SLOTS];
+    std::mutex slot_mu;
+    std::condition_variable slot_cv;
     std::mutex mu;
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;  // one pair per profiled search
@@ -498,13 +510,6 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     }
     ms.tau_g = static_cast<uint32_t *>(ix->tau.p);
     ms.stream = s;
-    if (small) {  // k' >= 128: K2s keeps its candidate lists in global memory
-        const size_t le = fr::scan_mma_small_list_elems(B, ksel, ix->dim, split);
-        if (le > 0) {
-            FR_CUDA(ix->s_lists.need(static_cast<size_t>(plan.lists) * le * sizeof(uint64_t)));
-            ms.list_scratch = static_cast<uint64_t *>(ix->s_lists.p);
-        }
-    }
     ProfScope prof{ix, s};
     int rc = prof.begin();
     if (rc != FR_OK) return rc;
@@ -768,7 +773,6 @@ uint64_t state_hash(const fr_index *ix) {
                             &ix->progress, &ix->s_lists, &ix->cmax, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau, &ix->r_partials, &ix->r_sel,
                             &ix->r_sel_keys};
     for (const DevBuf *b : bufs) mix(reinterpret_cast<uintptr_t>(b->p));
-    mix(reinterpret_cast<uintptr_t>(ix->pin.p));
     mix(reinterpret_cast<uintptr_t>(ix->fail_mirror));
     mix(reinterpret_cast<uintptr_t>(ix->corpus));
     mix(reinterpret_cast<uintptr_t>(ix->shadow));
@@ -893,7 +897,10 @@ int fr_index_destroy(fr_index *ix) {
                           &ix->fb_partials, &ix->tau, &ix->progress, &ix->s_lists, &ix->cmax, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau,
                           &ix->r_partials, &ix->r_sel, &ix->r_sel_keys};
         for (DevBuf *b : bufs) b->release();
-        ix->pin.release();
+        for (auto &sl : ix->slots) {
+            sl.pin.release();
+            if (sl.done) cudaEventDestroy(sl.done);
+        }
         if (ix->fail_mirror) cudaFreeHost(ix->fail_mirror);
         for (auto &pr : ix->prof_events) {
             cudaEventDestroy(pr.first);
@@ -1323,23 +1330,59 @@ int fr_index_lookup_rows(fr_index *ix, const int64_t *keys, int64_t n, int64_t *
     return FR_OK;
 }
 
+namespace {
+// a pinned staging slot of one host search, held from before the enqueue until the results are copied out
+struct SlotLease {
+    fr_index *ix;
+    int id = -1;
+    explicit SlotLease(fr_index *ix_) : ix(ix_) {
+        std::unique_lock<std::mutex> lk(ix->slot_mu);
+        ix->slot_cv.wait(lk, [&] {
+            for (int i = 0; i < fr_index::N_SLOTS; ++i)
+                if (!ix->slots[i].busy) return true;
+            return false;
+        });
+        for (int i = 0; i < fr_index::N_SLOTS; ++i)
+            if (!ix->slots[i].busy) {
+                ix->slots[i].busy = true;
+                id = i;
+                break;
+            }
+    }
+    ~SlotLease() {
+        {
+            std::lock_guard<std::mutex> lk(ix->slot_mu);
+            ix->slots[id].busy = false;
+        }
+        ix->slot_cv.notify_one();
+    }
+    fr_index::HostSlot &slot() { return ix->slots[id]; }
+};
+}  // namespace
+
 int fr_index_search(fr_index *ix, const float *queries, int B, int k, float *out_dist, int64_t *out_keys) {
     int rc = check_search_args(ix, queries, B, k, out_dist, out_keys);
     if (rc != FR_OK || B == 0) return rc;
-    std::lock_guard<std::mutex> lk(ix->mu);
+    SlotLease lease(ix);
+    fr_index::HostSlot &slot = lease.slot();
     DeviceGuard g(ix->device);
     cudaStream_t s = ix->stream;
     const size_t qb = static_cast<size_t>(B) * ix->dim * sizeof(float);
     const size_t db = static_cast<size_t>(B) * k * sizeof(float);
     const size_t kb = static_cast<size_t>(B) * k * sizeof(int64_t);
     const size_t db_al = (db + 15) & ~static_cast<size_t>(15), kb_al = (kb + 15) & ~static_cast<size_t>(15);
-    FR_CUDA(ix->pin.need(qb + db_al + kb_al));
+    // the slot is ours alone and its previous search has been waited for: growing it needs no lock
+    if (!slot.done) FR_CUDA(cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
+    FR_CUDA(slot.pin.need(qb + db_al + kb_al));
+    uint8_t *pin = static_cast<uint8_t *>(slot.pin.p);
+    // every block 16-byte aligned: the kernels may read the queries as float4 straight from the pinned block
+    uint8_t *pin_keys = pin, *pin_dist = pin + kb_al, *pin_q = pin + kb_al + db_al;
+    std::memcpy(pin_q, queries, qb);
+    {
+    std::lock_guard<std::mutex> lk(ix->mu);
     FR_CUDA(ix->q_raw.need(qb));
     FR_CUDA(ix->out_dist.need(db));
     FR_CUDA(ix->out_keys.need(kb));
-    uint8_t *pin = static_cast<uint8_t *>(ix->pin.p);
-    // every block 16-byte aligned: the kernels may read the queries as float4 straight from the pinned block
-    uint8_t *pin_keys = pin, *pin_dist = pin + kb_al, *pin_q = pin + kb_al + db_al;
     // the whole call as it is enqueued on `s`: H2D of the queries, the search, D2H of the results
     // Small batches of a cosine collection skip the three copy operations: the query-preparation kernel reads the
     // pinned block directly (the only reader of the raw queries) and the last kernel of the chain writes its
@@ -1357,16 +1400,23 @@ int fr_index_search(fr_index *ix, const float *queries, int B, int k, float *out
         FR_CUDA(cudaMemcpyAsync(pin_keys, ix->out_keys.p, kb, cudaMemcpyDeviceToHost, s));
         return FR_OK;
     };
-    // Small collections: replay a captured graph of the call (same shape, nothing it baked in changed).  The first
-    // call of a shape runs eagerly (it sizes the scratch), the second is captured, later ones are replays.
+    // Small collections: replay a captured graph of the call (same shape, same staging slot, nothing it baked in
+    // changed).  The first call of a shape runs eagerly (it sizes the scratch), the second is captured, later ones replay.
     const bool graphable = ix->use_graphs && !ix->profile && B <= 8192 &&
                            static_cast<int64_t>(ix->rows) * static_cast<int64_t>(ix->row_bytes()) <= ix->graph_max_bytes;
     fr_index::SearchGraph *sg = nullptr;
+    auto hash_now = [&]() {  // what a graph bakes in: the shard's state and this slot's pinned block
+        uint64_t h = state_hash(ix);
+        h ^= reinterpret_cast<uintptr_t>(pin);
+        h *= 1099511628211ull;
+        return h;
+    };
     if (graphable) {
         if (ix->graphs.size() > 64) drop_graphs(ix);
         plan_retry_blocks(ix);  // part of what a graph bakes in
-        sg = &ix->graphs[(static_cast<uint64_t>(static_cast<uint32_t>(B)) << 32) | static_cast<uint32_t>(k)];
-        const uint64_t h = state_hash(ix);
+        sg = &ix->graphs[(static_cast<uint64_t>(static_cast<uint32_t>(B)) << 32) | (static_cast<uint64_t>(static_cast<uint32_t>(k)) << 4) |
+                         static_cast<uint64_t>(lease.id)];
+        const uint64_t h = hash_now();
         if (sg->exec && sg->state != h) {
             cudaGraphExecDestroy(sg->exec);
             sg->exec = nullptr;
@@ -1388,7 +1438,7 @@ int fr_index_search(fr_index *ix, const float *queries, int B, int k, float *out
             ix->n_searches = s0;
             ix->n_queries = q0;
             ix->n_mma_queries = m0;
-            if (ok) ok = state_hash(ix) == h;  // the capture must not have moved any scratch
+            if (ok) ok = hash_now() == h;  // the capture must not have moved any scratch
             if (ok) ok = cudaGraphInstantiate(&sg->exec, graph, 0) == cudaSuccess;
             if (graph) cudaGraphDestroy(graph);
             if (!ok) {
@@ -1402,7 +1452,6 @@ int fr_index_search(fr_index *ix, const float *queries, int B, int k, float *out
     }
     rc = begin_use(ix, s);
     if (rc != FR_OK) return rc;
-    std::memcpy(pin_q, queries, qb);
     if (sg && sg->exec) {
         FR_CUDA(cudaGraphLaunch(sg->exec, s));
         g_launches.fetch_add(sg->launches, std::memory_order_relaxed);
@@ -1412,12 +1461,17 @@ int fr_index_search(fr_index *ix, const float *queries, int B, int k, float *out
         ix->n_graph_replays += 1;
     } else {
         rc = enqueue();
-        if (rc != FR_OK) return rc;
-        if (sg) sg->seen = state_hash(ix);
+        if (rc != FR_OK) {
+            cudaStreamSynchronize(s);  // whatever part of the chain was enqueued may still write the slot
+            return rc;
+        }
+        if (sg) sg->seen = hash_now();
     }
     rc = end_use(ix, s);
     if (rc != FR_OK) return rc;
-    FR_CUDA(cudaStreamSynchronize(s));
+    FR_CUDA(cudaEventRecord(slot.done, s));
+    }  // the shard is free for the next caller's enqueue; this call waits for its own results only
+    FR_CUDA(cudaEventSynchronize(slot.done));
     std::memcpy(out_dist, pin_dist, db);
     std::memcpy(out_keys, pin_keys, kb);
     return FR_OK;

@@ -65,7 +65,6 @@ struct MmaScanArgs {
                                 // groups of a stream stay within max_lead tiles of each other (zeroed by the launcher)
     int max_lead;
     int dbg;                    // diagnostics only (option "mma_debug"): 1 = no corpus loads, 2 = no accumulator reads
-    uint64_t *list_scratch;     // K2s with k' >= 128: [plan.lists][scan_mma_small_list_elems()] candidate lists (global memory)
     uint32_t *tau_g;            // ksel * nq_total shared threshold slots (order_bits of a score), zeroed before the launches;
                                 // K2 lays them out [ksel][nq_total], K2s [nq_total][ksel]
     cudaStream_t stream;
@@ -100,7 +99,6 @@ cudaError_t launch_scan_mma(const MmaScanArgs &a);
 // writes partials [plan.lists][nq_total][ksel] for queries [q0, q0 + nq).
 int scan_mma_small_nq(int nq, int ksel, int dim, int split);  // padded query count (16/32/64), 0 = not served
 int scan_mma_small_max_batch(int ksel, int dim, int split);   // largest batch one K2s launch serves (0 = none)
-size_t scan_mma_small_list_elems(int nq, int ksel, int dim, int split);  // list scratch per CTA, uint64 elements (0 = none)
 cudaError_t launch_scan_mma_small(const MmaScanArgs &a, int q0, int nq);
 
 struct RescoreArgs {

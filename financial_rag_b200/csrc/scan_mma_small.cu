@@ -46,13 +46,13 @@ constexpr int S_MAX_STAGES = 8;
 //   LM_SHARED k' = 128 / 256 (k up to 100: cfg3's per-collection top-50, cfg5's top-100): per-warp lists would be 256 KB+,
 //             so the four lane-quarter warps that serve a query share ONE list per query in shared memory (<= 64 KB)
 //             under a per-query spin lock; a warp folds all its passing rows of a tile into it in one bitonic network;
-//   LM_GLOBAL 64 queries x k' = 256 (128 KB even when shared): per-warp lists in global memory (list_scratch).  Measured
-//             with k' = 128 (profiles/r02_ncu_full_scan_mma_small_64q_k128_10m.txt): the corpus stream evicts the lists
-//             from L2, every insert is a DRAM round trip and the scan drops to 0.75 of the copy peak -- hence LM_SHARED
-//             wherever it fits.
-enum { LM_WARP = 0, LM_SHARED = 1, LM_GLOBAL = 2 };
+//   (not served) 64 queries x k' = 256 is 128 KB even when shared.  Lists in global memory were tried: the corpus stream
+//             evicts them from L2, every insert is a DRAM round trip -- 0.75 of the copy peak at k' = 128
+//             (profiles/r02_ncu_full_scan_mma_small_64q_k128_10m_global_lists.txt) and 8 x the roofline time at k' = 256
+//             (profiles/r02_launches_k100_b1024_25m.txt).  Batches of 33-64 with k > 64 take K2 instead.
+enum { LM_WARP = 0, LM_SHARED = 1, LM_NONE = 2 };
 __host__ __device__ constexpr int small_list_mode(int nq, int kpl) {
-    return kpl <= 2 ? LM_WARP : (nq * 32 * kpl * 8 <= 65536 ? LM_SHARED : LM_GLOBAL);
+    return kpl <= 2 ? LM_WARP : (nq * 32 * kpl * 8 <= 65536 ? LM_SHARED : LM_NONE);
 }
 template <int NQ, int KPL, int SPLIT>
 struct SmallPlan {
@@ -66,7 +66,7 @@ struct SmallPlan {
     static constexpr int THREADS = 64 + 32 * EW;
     static constexpr size_t LIST_ELEMS = LMODE == LM_SHARED ? size_t(NQ) * CAP          // [NQ][CAP] per CTA
                                                             : size_t(EW) * NQH * CAP;   // [EW warps][NQH][CAP] per CTA
-    static constexpr size_t LIST_BYTES = LMODE == LM_GLOBAL ? 0 : LIST_ELEMS * 8 + (LMODE == LM_SHARED ? size_t(NQ) * 4 : 0);
+    static constexpr size_t LIST_BYTES = LIST_ELEMS * 8 + (LMODE == LM_SHARED ? size_t(NQ) * 4 : 0);
     static constexpr size_t STASH_BYTES = size_t(EW) * NQH * 32 * 4;             // [EW warps][NQH][32 rows] fp32
     static_assert(Q_CHUNK % 1024 == 0, "query chunks must keep the 1024-byte swizzle alignment");
     size_t q_bytes, ring_off, list_off, stash_off, bar_off, alloc;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(64 + 32 * small_epilogue_warps(NQ), 1)
 scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                       const int64_t *__restrict__ keys_or_null, int64_t n_rows, int nq, int ksel,
                       uint64_t *__restrict__ partials, int nq_total, uint32_t *__restrict__ tau_g, int k_chunks,
-                      int q0, const int *__restrict__ nq_dev, uint64_t *__restrict__ list_scratch) {
+                      int q0, const int *__restrict__ nq_dev) {
     // q0: first query (row of the query block, index into partials / tau_g) this launch serves; with nq_dev the
     // live count comes from the device (retry slices: *nq_dev queries in all, this slice takes [q0, q0 + nq))
     if (nq_dev != nullptr) {
@@ -125,8 +125,8 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     uint8_t *smem_q = smem;
     uint8_t *smem_ring = smem + plan.ring_off;
     constexpr int LMODE = Plan::LMODE;
-    uint64_t *lists = LMODE == LM_GLOBAL ? list_scratch + static_cast<size_t>(blockIdx.x) * Plan::LIST_ELEMS
-                                         : reinterpret_cast<uint64_t *>(smem + plan.list_off);
+    static_assert(LMODE != LM_NONE, "this instance is not built");
+    uint64_t *lists = reinterpret_cast<uint64_t *>(smem + plan.list_off);
     int *locks = reinterpret_cast<int *>(lists + Plan::LIST_ELEMS);  // LM_SHARED only: one spin lock per query
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + plan.bar_off);
     // barrier slots: full[8] | empty[8] | tmem_full[4] | tmem_empty[4] | q_full | tmem_ptr
@@ -482,28 +482,30 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 namespace {
 template <int NQ, int KPL, int SPLIT>
 cudaError_t launch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CUtensorMap &tc, int k_chunks, int nq, int q0,
-                         size_t *alloc_out, size_t *list_elems_out) {
+                         size_t *alloc_out) {
+    if constexpr (mma::small_list_mode(NQ, KPL) == mma::LM_NONE) {
+        if (alloc_out) *alloc_out = 0;
+        return cudaErrorInvalidValue;
+    } else {
     const mma::SmallPlan<NQ, KPL, SPLIT> plan(k_chunks);
     if (alloc_out) {  // planning only: does this instance fit, and with how deep a ring?
         *alloc_out = plan.stages >= mma::S_MIN_STAGES ? plan.alloc : 0;
-        if (list_elems_out)
-            *list_elems_out = mma::SmallPlan<NQ, KPL, SPLIT>::LMODE == mma::LM_GLOBAL ? mma::SmallPlan<NQ, KPL, SPLIT>::LIST_ELEMS : 0;
         return cudaSuccess;
     }
     if (plan.stages < mma::S_MIN_STAGES) return cudaErrorInvalidValue;
-    if (mma::SmallPlan<NQ, KPL, SPLIT>::LMODE == mma::LM_GLOBAL && a.list_scratch == nullptr) return cudaErrorInvalidValue;
     auto kern = mma::scan_mma_small_kernel<NQ, KPL, SPLIT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.alloc));
     if (e != cudaSuccess) return e;
     kern<<<a.plan.lists, mma::SmallPlan<NQ, KPL, SPLIT>::THREADS, plan.alloc, a.stream>>>(tq, tc, a.keys_or_null, a.n_rows, nq, a.ksel, a.partials,
-                                                                a.nq_total, a.tau_g, k_chunks, q0, a.nq_dev, a.list_scratch);
+                                                                a.nq_total, a.tau_g, k_chunks, q0, a.nq_dev);
     count_launch();
     return cudaGetLastError();
+    }
 }
 
 cudaError_t dispatch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CUtensorMap &tc, int nq_pad, int ksel,
-                           int k_chunks, int split, int nq, int q0, size_t *alloc_out, size_t *list_elems_out = nullptr) {
-#define FR_SMALL(NQ, KPL, SPLIT) launch_small<NQ, KPL, SPLIT>(a, tq, tc, k_chunks, nq, q0, alloc_out, list_elems_out)
+                           int k_chunks, int split, int nq, int q0, size_t *alloc_out) {
+#define FR_SMALL(NQ, KPL, SPLIT) launch_small<NQ, KPL, SPLIT>(a, tq, tc, k_chunks, nq, q0, alloc_out)
 #define FR_SMALL_K(NQ, SPLIT)                                                                      \
     return ksel <= 32 ? FR_SMALL(NQ, 1, SPLIT)                                                     \
                       : (ksel <= 64 ? FR_SMALL(NQ, 2, SPLIT) : (ksel <= 128 ? FR_SMALL(NQ, 4, SPLIT) : FR_SMALL(NQ, 8, SPLIT)))
@@ -538,17 +540,6 @@ int scan_mma_small_nq(int nq, int ksel, int dim, int split) {
     if (dispatch_small(dummy, none, none, nq_pad, ksel, dim / mma::K_CHUNK, split, nq, 0, &alloc) != cudaSuccess || alloc == 0)
         return 0;
     return nq_pad;
-}
-
-// uint64 elements of list scratch per CTA (0: the instance keeps its candidate lists in shared memory)
-size_t scan_mma_small_list_elems(int nq, int ksel, int dim, int split) {
-    const int nq_pad = scan_mma_small_nq(nq, ksel, dim, split);
-    if (nq_pad == 0) return 0;
-    size_t alloc = 0, elems = 0;
-    MmaScanArgs dummy{};
-    CUtensorMap none{};
-    dispatch_small(dummy, none, none, nq_pad, ksel, dim / mma::K_CHUNK, split, nq, 0, &alloc, &elems);
-    return elems;
 }
 
 // largest batch one K2s launch can serve for this width, k' and query precision (0 = none)

@@ -976,3 +976,41 @@ def test_mma_path_with_deletes_and_eligibility(frb):
         jx.set_path("auto")  # auto silently uses the kernel that serves the configuration
         jx.search(make_corpus(8, args["dim"], seed=2), 5)
         jx.close()
+
+
+def test_concurrent_host_searches_share_a_shard(frb):
+    """Flask serves requests from several threads (api_server.py:1366-1371): concurrent fr_index_search calls on one
+    shard hold its lock only while they are enqueued, wait for their own event and read their own pinned slot.
+    Every thread must get exactly the answer of a lone call -- small batches (graph replay, zero-copy), large ones
+    (copies through the staging buffers), more threads than slots."""
+    import threading
+
+    n = 60000
+    corpus = make_corpus(n, 384, seed=9100)
+    ix = build_index(frb, corpus, "cosine", "bf16")
+    jobs = []
+    for t in range(7):
+        b = (1, 3, 8, 40, 70, 200, 300)[t]
+        q = make_queries(b, corpus, seed=9200 + t)
+        jobs.append((q, ix.search(q, 10)))           # the lone answers (also warms the graphs up)
+    errors = []
+
+    def worker(t):
+        q, (want_d, want_k) = jobs[t]
+        try:
+            for _ in range(25):
+                d, kk = ix.search(q, 10)
+                if not ((kk == want_k).all() and (d == want_d).all()):
+                    errors.append(f"thread {t}: answer differs from the lone call")
+                    return
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"thread {t}: {e!r}")
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(7)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    assert ix.stat("searches") >= 7 * 26
+    ix.close()
