@@ -19,6 +19,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -126,7 +127,16 @@ struct fr_group {
     std::vector<cudaEvent_t> ev_local;  // FR_XCHG_COPY: the shard's local lists are complete
     std::vector<cudaEvent_t> ev_done;   // FR_XCHG_COPY: device j has finished reading everybody's lists
     std::vector<DevBuf> q, send, recv, out_dist, out_keys;
-    PinBuf pin;
+    // host searches: `mu` is held only while a call is enqueued; each call owns one pinned slot and waits for its own event
+    struct HostSlot {
+        PinBuf pin;
+        cudaEvent_t done = nullptr;
+        bool busy = false;
+    };
+    static constexpr int N_SLOTS = 4;
+    HostSlot slots[N_SLOTS];
+    std::mutex slot_mu;
+    std::condition_variable slot_cv;
     std::mutex mu;
     int64_t rows = 0;       // global rows, deleted ones included
     int64_t n_deleted = 0;  // global
@@ -289,7 +299,13 @@ int fr_group_destroy(fr_group *g) {
             if (j < static_cast<int>(evs->size()) && (*evs)[j]) cudaEventDestroy((*evs)[j]);
         if (j < static_cast<int>(g->stream.size()) && g->stream[j]) cudaStreamDestroy(g->stream[j]);
     }
-    g->pin.release();
+    if (!g->dev.empty()) {
+        DeviceGuard dg(g->dev[0]);
+        for (auto &sl : g->slots) {
+            sl.pin.release();
+            if (sl.done) cudaEventDestroy(sl.done);
+        }
+    }
     delete g;
     return FR_OK;
 }
@@ -677,59 +693,96 @@ int fr_group_search(fr_group *g, const float *queries, int B, int k, float *out_
     const bool has_root = g->first == 0;  // the process that holds shard 0 feeds the queries
     if (has_root && !queries) return fail(FR_EINVAL, "NULL queries");
     if (!out_dist || !out_keys) return fail(FR_EINVAL, "NULL buffer");
-    std::lock_guard<std::mutex> lk(g->mu);
+    // a pinned staging slot of this call alone (concurrent callers overlap their copies and waits with each other's GPU work)
+    int sid = -1;
+    {
+        std::unique_lock<std::mutex> lk(g->slot_mu);
+        g->slot_cv.wait(lk, [&] {
+            for (auto &sl : g->slots)
+                if (!sl.busy) return true;
+            return false;
+        });
+        for (int i = 0; i < fr_group::N_SLOTS; ++i)
+            if (!g->slots[i].busy) {
+                g->slots[i].busy = true;
+                sid = i;
+                break;
+            }
+    }
+    struct Release {
+        fr_group *g;
+        int sid;
+        ~Release() {
+            {
+                std::lock_guard<std::mutex> lk(g->slot_mu);
+                g->slots[sid].busy = false;
+            }
+            g->slot_cv.notify_one();
+        }
+    } release{g, sid};
+    fr_group::HostSlot &slot = g->slots[sid];
     const size_t qb = static_cast<size_t>(B) * g->dim * sizeof(float);
     const size_t db = static_cast<size_t>(B) * k * sizeof(float), kb = static_cast<size_t>(B) * k * sizeof(int64_t);
     const size_t db_al = (db + 15) & ~static_cast<size_t>(15), kb_al = (kb + 15) & ~static_cast<size_t>(15);
-    FR_CUDA(g->pin.need(qb + db_al + kb_al));
-    uint8_t *pin_keys = static_cast<uint8_t *>(g->pin.p), *pin_dist = pin_keys + kb_al, *pin_q = pin_dist + db_al;
-    std::vector<const float *> dq(static_cast<size_t>(g->nl));
-    std::vector<float *> od(static_cast<size_t>(g->nl), nullptr);
-    std::vector<int64_t *> ok(static_cast<size_t>(g->nl), nullptr);
-    for (int j = 0; j < g->nl; ++j) {
-        DeviceGuard dg(g->dev[j]);
-        FR_CUDA(g->q[j].need(qb));
-        dq[static_cast<size_t>(j)] = static_cast<const float *>(g->q[j].p);
-    }
     {
         DeviceGuard dg(g->dev[0]);
-        FR_CUDA(g->out_dist[0].need(db));
-        FR_CUDA(g->out_keys[0].need(kb));
-        od[0] = static_cast<float *>(g->out_dist[0].p);
-        ok[0] = static_cast<int64_t *>(g->out_keys[0].p);
+        if (!slot.done) FR_CUDA(cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
+        FR_CUDA(slot.pin.need(qb + db_al + kb_al));
     }
+    uint8_t *pin_keys = static_cast<uint8_t *>(slot.pin.p), *pin_dist = pin_keys + kb_al, *pin_q = pin_dist + db_al;
     if (has_root) std::memcpy(pin_q, queries, qb);
-    if (g->all_local()) {
-        // every device pulls the block over its own PCIe link at once
-        for (int j = 0; j < g->nl; ++j) {
-            DeviceGuard dg(g->dev[j]);
-            FR_CUDA(cudaStreamWaitEvent(g->stream[j], g->ev_use[j], 0));
-            FR_CUDA(cudaMemcpyAsync(g->q[j].p, pin_q, qb, cudaMemcpyHostToDevice, g->stream[j]));
-        }
-    } else {
-        for (int j = 0; j < g->nl; ++j) {
-            DeviceGuard dg(g->dev[j]);
-            FR_CUDA(cudaStreamWaitEvent(g->stream[j], g->ev_use[j], 0));
-            if (has_root && j == 0) FR_CUDA(cudaMemcpyAsync(g->q[0].p, pin_q, qb, cudaMemcpyHostToDevice, g->stream[0]));
-        }
-        FR_NCCL(g_nccl.GroupStart());
-        for (int j = 0; j < g->nl; ++j) {
-            int r = g_nccl.Broadcast(g->q[j].p, g->q[j].p, static_cast<size_t>(B) * g->dim, NCCL_FLOAT32, 0, g->comm[j], g->stream[j]);
-            if (r != 0) {
-                g_nccl.GroupEnd();
-                return fail(FR_ECUDA, "ncclBroadcast failed: %s", g_nccl.GetErrorString(r));
-            }
-        }
-        FR_NCCL(g_nccl.GroupEnd());
-    }
-    rc = group_search_enqueue(g, dq.data(), B, k, od.data(), ok.data(), g->stream.data());
-    if (rc != FR_OK) return rc;
     {
+        std::lock_guard<std::mutex> lk(g->mu);
+        std::vector<const float *> dq(static_cast<size_t>(g->nl));
+        std::vector<float *> od(static_cast<size_t>(g->nl), nullptr);
+        std::vector<int64_t *> ok(static_cast<size_t>(g->nl), nullptr);
+        for (int j = 0; j < g->nl; ++j) {
+            DeviceGuard dg(g->dev[j]);
+            FR_CUDA(g->q[j].need(qb));
+            dq[static_cast<size_t>(j)] = static_cast<const float *>(g->q[j].p);
+        }
+        {
+            DeviceGuard dg(g->dev[0]);
+            FR_CUDA(g->out_dist[0].need(db));
+            FR_CUDA(g->out_keys[0].need(kb));
+            od[0] = static_cast<float *>(g->out_dist[0].p);
+            ok[0] = static_cast<int64_t *>(g->out_keys[0].p);
+        }
+        if (g->all_local()) {
+            // every device pulls the block over its own PCIe link at once
+            for (int j = 0; j < g->nl; ++j) {
+                DeviceGuard dg(g->dev[j]);
+                FR_CUDA(cudaStreamWaitEvent(g->stream[j], g->ev_use[j], 0));
+                FR_CUDA(cudaMemcpyAsync(g->q[j].p, pin_q, qb, cudaMemcpyHostToDevice, g->stream[j]));
+            }
+        } else {
+            for (int j = 0; j < g->nl; ++j) {
+                DeviceGuard dg(g->dev[j]);
+                FR_CUDA(cudaStreamWaitEvent(g->stream[j], g->ev_use[j], 0));
+                if (has_root && j == 0) FR_CUDA(cudaMemcpyAsync(g->q[0].p, pin_q, qb, cudaMemcpyHostToDevice, g->stream[0]));
+            }
+            FR_NCCL(g_nccl.GroupStart());
+            for (int j = 0; j < g->nl; ++j) {
+                int r = g_nccl.Broadcast(g->q[j].p, g->q[j].p, static_cast<size_t>(B) * g->dim, NCCL_FLOAT32, 0, g->comm[j], g->stream[j]);
+                if (r != 0) {
+                    g_nccl.GroupEnd();
+                    return fail(FR_ECUDA, "ncclBroadcast failed: %s", g_nccl.GetErrorString(r));
+                }
+            }
+            FR_NCCL(g_nccl.GroupEnd());
+        }
+        rc = group_search_enqueue(g, dq.data(), B, k, od.data(), ok.data(), g->stream.data());
+        if (rc != FR_OK) return rc;
         DeviceGuard dg(g->dev[0]);
         FR_CUDA(cudaMemcpyAsync(pin_dist, od[0], db, cudaMemcpyDeviceToHost, g->stream[0]));
         FR_CUDA(cudaMemcpyAsync(pin_keys, ok[0], kb, cudaMemcpyDeviceToHost, g->stream[0]));
         FR_CUDA(cudaEventRecord(g->ev_use[0], g->stream[0]));
-        FR_CUDA(cudaStreamSynchronize(g->stream[0]));
+        FR_CUDA(cudaEventRecord(slot.done, g->stream[0]));
+    }
+    {
+        // stream 0's merge waited for every shard's lists, so every device has also finished READING this slot's queries
+        DeviceGuard dg(g->dev[0]);
+        FR_CUDA(cudaEventSynchronize(slot.done));
     }
     std::memcpy(out_dist, pin_dist, db);
     std::memcpy(out_keys, pin_keys, kb);

@@ -293,3 +293,37 @@ def test_multi_process_group_under_torchrun(world):
                        capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert f"SPMD-OK world={world}" in r.stdout
+
+
+def test_concurrent_host_searches_on_a_group(frb):
+    """Several request threads on one row-sharded collection: each call holds the group's lock only while it is
+    enqueued and reads its own pinned slot; every thread gets the lone call's answer."""
+    import threading
+
+    corpus = make_corpus(50000, seed=31)
+    grp = frb.ShardGroup(dim=384, dtype="bf16", devices=[0, 0, 0])
+    _fill(grp, corpus)
+    jobs = []
+    for t in range(6):
+        q = make_queries((1, 5, 40, 70, 200, 300)[t], corpus, seed=40 + t)
+        jobs.append((q, grp.search(q, 10)))
+    errors = []
+
+    def worker(t):
+        q, (want_d, want_k) = jobs[t]
+        try:
+            for _ in range(15):
+                d, kk = grp.search(q, 10)
+                if not ((kk == want_k).all() and (d == want_d).all()):
+                    errors.append(f"thread {t}: answer differs from the lone call")
+                    return
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"thread {t}: {e!r}")
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    grp.close()
