@@ -111,8 +111,10 @@ struct fr_index {
     cudaEvent_t last_use = nullptr;  // orders scratch reuse across caller streams
     DevBuf q_raw, q_prep, q_keys, partials, out_dist, out_keys, stage_vecs, stage_keys, stage_rows;
     DevBuf q_bf16, err_bound, sel, sel_keys, flags, fail, fb_partials, tau, progress, s_lists;  // K2 path
-    DevBuf cmax;             // inner-product collections: largest row norm (device float), the scale of the error bounds
+    DevBuf cmax;             // inner-product / l2 collections: largest row norm (device float), the scale of the error bounds
     int64_t cmax_rows = 0;   // rows it covers; an in-place overwrite resets it
+    DevBuf norm2;            // l2 collections: |c|^2 per row (the tensor-core selection ranks by 2 q.c - |c|^2)
+    int64_t norm2_cap = 0;
     DevBuf kth_exact, r_q, r_misc, r_tau, r_partials, r_sel, r_sel_keys;     // K2 second-chance pass
     int mma_min_batch = 2;  // FR_PATH_AUTO: batches at least this large go to the tensor-core scans; smaller ones
                             // too when the swapped-operand kernel K2s serves them (it out-streams K1: TMA ring)
@@ -285,16 +287,25 @@ bool shadow_serves(const fr_index *ix) {
 
 // inner-product collections: bring the largest row norm up to date (stream-ordered on `s`)
 int ensure_cmax(fr_index *ix, cudaStream_t s) {
-    if (ix->metric != FR_IP) return FR_OK;
+    if (ix->metric != FR_IP && ix->metric != FR_L2) return FR_OK;
     if (!ix->cmax.p) {
         FR_CUDA(ix->cmax.need(64));
+        ix->cmax_rows = 0;
+    }
+    const bool want_norm2 = ix->metric == FR_L2;
+    if (want_norm2 && ix->norm2_cap < ix->cap_rows + PAD_ROWS) {  // the shard grew: recompute into a larger array
+        FR_CUDA(cudaStreamSynchronize(s));
+        ix->norm2.release();
+        FR_CUDA(ix->norm2.need(static_cast<size_t>(ix->cap_rows + PAD_ROWS) * sizeof(float)));
+        ix->norm2_cap = ix->cap_rows + PAD_ROWS;
         ix->cmax_rows = 0;
     }
     if (ix->cmax_rows == 0) FR_CUDA(cudaMemsetAsync(ix->cmax.p, 0, 64, s));
     if (ix->cmax_rows < ix->rows) {
         const size_t rb = ix->row_bytes();
         FR_CUDA(fr::launch_row_norm_max(ix->corpus + static_cast<size_t>(ix->cmax_rows) * rb, ix->dtype == FR_BF16,
-                                        ix->rows - ix->cmax_rows, ix->dim, static_cast<float *>(ix->cmax.p), s));
+                                        ix->rows - ix->cmax_rows, ix->dim, static_cast<float *>(ix->cmax.p),
+                                        want_norm2 ? static_cast<float *>(ix->norm2.p) + ix->cmax_rows : nullptr, s));
         ix->cmax_rows = ix->rows;
     }
     return FR_OK;
@@ -345,7 +356,12 @@ bool small_serves(const fr_index *ix, int B, int ksel) {
 }
 int mma_slice(const fr_index *ix, int k) {  // 0 = not eligible, else the largest batch one pass may take
     const int ksel = fr::scan_mma_ksel(k, ix->mma_wide_lists);
-    if ((ix->metric != FR_COSINE && ix->metric != FR_IP) || ksel == 0 || ix->rows <= 0) return 0;
+    if (ksel == 0 || ix->rows <= 0) return 0;
+    if (ix->metric == FR_L2) {  // l2: the swapped-operand kernel only (its epilogue subtracts the row norms), in slices it holds
+        if (ix->dtype != FR_BF16 || ix->dim != 384) return 0;
+        const int m = fr::scan_mma_small_max_batch(ksel, ix->dim, 0);
+        return m < ix->mma_small_max ? m : ix->mma_small_max;
+    }
     if (ix->dtype != FR_BF16) return shadow_serves(ix) ? 1 << 30 : 0;  // fp32 rows: selection on a bf16 copy
     if (ix->dim == 384) return 1 << 30;
     if (ix->dim != 768) return 0;  // the re-scan safety net exists for 384 and 768 only
@@ -421,7 +437,9 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     const bool small = small_serves(ix, B, ksel);
     const int split = small ? small_split(ix, B, ksel) : 0;
     if (!small && ix->dim != 384) return fail(FR_EUNSUP, "internal: width %d needs the small-batch kernel", ix->dim);
-    const bool second_chance = ix->dim == 384;  // the second-chance pass runs on K2, which is 384-wide
+    const bool l2 = ix->metric == FR_L2;
+    if (l2 && !small) return fail(FR_EUNSUP, "internal: l2 collections take the small-batch kernel only");
+    const bool second_chance = ix->dim == 384 && !l2;  // the second-chance pass runs on K2 (384-wide, dot products)
     const fr::MmaPlan plan = fr::scan_mma_plan(ix->sm_count, ix->rows, B, ix->mma_co_groups);
     const int grid = plan.lists_max;  // partial lists per query (at most)
     // second-chance blocks: R queries each, enough of them for every query of the call
@@ -436,7 +454,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
         }
     }
     FR_CUDA(ix->q_bf16.need(static_cast<size_t>(nq_pad) * ix->dim * 2 * (1 + split)));
-    FR_CUDA(ix->err_bound.need(5 * static_cast<size_t>(B) * sizeof(float)));  // |e| one-term | two-term | |e.q| one-term | two-term | 1/scale
+    FR_CUDA(ix->err_bound.need(6 * static_cast<size_t>(B) * sizeof(float)));  // |e| one-term | two-term | |e.q| one-term | two-term | 1/scale | |q|^2
     FR_CUDA(ix->partials.need(static_cast<size_t>(grid) * B * ksel * sizeof(uint64_t)));
     FR_CUDA(ix->sel.need(static_cast<size_t>(B) * ksel * sizeof(uint64_t)));
     FR_CUDA(ix->sel_keys.need(static_cast<size_t>(B) * ksel * sizeof(int64_t)));
@@ -475,12 +493,13 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     pa.n_counters = 2;
     pa.normalize = ix->metric == FR_COSINE;
     float *inv_scale = eb_one + 4 * static_cast<size_t>(B);
-    if (ix->metric == FR_IP) {
+    if (ix->metric != FR_COSINE) {
         int rcm = ensure_cmax(ix, s);
         if (rcm != FR_OK) return rcm;
         pa.cmax = static_cast<const float *>(ix->cmax.p);
     }
     pa.inv_scale = inv_scale;
+    pa.qnorm2 = inv_scale + B;
     pa.stream = s;
     FR_CUDA(fr::launch_prep_queries(pa));
     const float *q = pa.q_prep;
@@ -509,6 +528,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
         ms.max_lead = ix->mma_max_lead;
     }
     ms.tau_g = static_cast<uint32_t *>(ix->tau.p);
+    ms.norm2 = l2 ? static_cast<const float *>(ix->norm2.p) : nullptr;
     ms.stream = s;
     ProfScope prof{ix, s};
     int rc = prof.begin();
@@ -533,7 +553,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
         ma.k = ksel;
         ma.shards = false;
         ma.row_keys = ix->keys;
-        ma.l2 = false;
+        ma.l2 = false;  // (selection lists carry packed keys only; distances come out of the rescore pass)
         ma.out_packed = static_cast<uint64_t *>(ix->sel.p) + static_cast<size_t>(q0) * ksel;
         ma.out_keys = static_cast<int64_t *>(ix->sel_keys.p) + static_cast<size_t>(q0) * ksel;
         ma.stream = s;
@@ -556,6 +576,9 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     ra.err_bound = split ? eb_two : eb_one;
     ra.err_alpha = split ? ea_two : ea_one;
     ra.inv_scale = inv_scale;
+    ra.l2 = l2 ? 1 : 0;
+    ra.qnorm2 = pa.qnorm2;
+    ra.cmax = pa.cmax;
     ra.split = split;
     ra.B = B;
     ra.k = k;
@@ -666,7 +689,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     sa.n_rows = ix->rows;
     sa.dim = ix->dim;
     sa.bf16 = !f32_rows;  // the re-scan reads the rows the collection stores
-    sa.l2 = false;
+    sa.l2 = l2;
     sa.k = k;
     sa.nq_total = B;
     sa.stream = s;
@@ -684,7 +707,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     mf.k = k;
     mf.shards = false;
     mf.row_keys = ix->keys;
-    mf.l2 = false;
+    mf.l2 = l2;
     mf.out_dist = d_out_dist;
     mf.out_packed = d_out_packed;
     mf.out_keys = d_out_keys;
@@ -721,7 +744,7 @@ int search_on_stream(fr_index *ix, const float *d_queries, int B, int k, float *
     const bool eligible = mma_eligible(ix, k);
     if (ix->path == FR_PATH_MMA && !eligible)
         return fail(FR_EUNSUP,
-                    "FR_PATH_MMA serves cosine and inner-product collections of width 384 (bf16 or fp32 rows, k <= 100) or 768 (bf16) with at least one row "
+                    "FR_PATH_MMA serves cosine and inner-product collections of width 384 (bf16 or fp32 rows, k <= 100) or 768 (bf16) and l2 collections of width 384 (bf16), with at least one row "
                     "(this one: dtype %d, dim %d, metric %d, k %d, rows %lld)",
                     ix->dtype, ix->dim, ix->metric, k, (long long)ix->rows);
     const bool k2s = eligible && small_serves(ix, B, fr::scan_mma_ksel(k, ix->mma_wide_lists));
@@ -770,7 +793,7 @@ uint64_t state_hash(const fr_index *ix) {
     };
     const DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist, &ix->out_keys, &ix->q_bf16,
                             &ix->err_bound, &ix->sel, &ix->sel_keys, &ix->flags, &ix->fail, &ix->fb_partials, &ix->tau,
-                            &ix->progress, &ix->s_lists, &ix->cmax, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau, &ix->r_partials, &ix->r_sel,
+                            &ix->progress, &ix->s_lists, &ix->cmax, &ix->norm2, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau, &ix->r_partials, &ix->r_sel,
                             &ix->r_sel_keys};
     for (const DevBuf *b : bufs) mix(reinterpret_cast<uintptr_t>(b->p));
     mix(reinterpret_cast<uintptr_t>(ix->fail_mirror));
@@ -894,7 +917,7 @@ int fr_index_destroy(fr_index *ix) {
         DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist,
                           &ix->out_keys, &ix->stage_vecs, &ix->stage_keys, &ix->stage_rows,
                           &ix->q_bf16, &ix->err_bound, &ix->sel, &ix->sel_keys, &ix->flags, &ix->fail,
-                          &ix->fb_partials, &ix->tau, &ix->progress, &ix->s_lists, &ix->cmax, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau,
+                          &ix->fb_partials, &ix->tau, &ix->progress, &ix->s_lists, &ix->cmax, &ix->norm2, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau,
                           &ix->r_partials, &ix->r_sel, &ix->r_sel_keys};
         for (DevBuf *b : bufs) b->release();
         for (auto &sl : ix->slots) {

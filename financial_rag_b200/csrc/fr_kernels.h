@@ -65,6 +65,7 @@ struct MmaScanArgs {
                                 // groups of a stream stay within max_lead tiles of each other (zeroed by the launcher)
     int max_lead;
     int dbg;                    // diagnostics only (option "mma_debug"): 1 = no corpus loads, 2 = no accumulator reads
+    const float *norm2;         // K2s, l2 collections: |c|^2 per row (selection on 2 q.c - |c|^2); null otherwise
     uint32_t *tau_g;            // ksel * nq_total shared threshold slots (order_bits of a score), zeroed before the launches;
                                 // K2 lays them out [ksel][nq_total], K2s [nq_total][ksel]
     cudaStream_t stream;
@@ -89,10 +90,12 @@ struct PrepArgs {
     bool normalize;     // cosine collections; inner-product collections read the raw query
     const float *cmax;  // device scalar: largest row norm (inner product), null = rows of norm <= 1.004 (cosine)
     float *inv_scale;   // [nq] out: 1 / (|q| * max row norm) -- 1 for cosine -- the scale of the absolute error slacks
+    float *qnorm2;      // [nq] out or null: |q|^2 of the query as scanned (l2 certification)
     cudaStream_t stream;
 };
 // largest row norm of rows [0, n) folded into *out by atomicMax (a float >= 0 stored as its bits)
-cudaError_t launch_row_norm_max(const void *rows, bool bf16, int64_t n, int dim, float *out, cudaStream_t s);
+// norm2_out (optional, [n]): the squared norm of every row (l2 collections)
+cudaError_t launch_row_norm_max(const void *rows, bool bf16, int64_t n, int dim, float *out, float *norm2_out, cudaStream_t s);
 cudaError_t launch_prep_queries(const PrepArgs &a);
 cudaError_t launch_scan_mma(const MmaScanArgs &a);
 // K2s (scan_mma_small.cu): operands swapped for 1..64 queries, k' <= 64.  Uses plan.lists CTAs per launch;
@@ -110,6 +113,9 @@ struct RescoreArgs {
     int f32_rows;            // the scan read a bf16 copy of fp32 rows: exact scores come from the fp32 rows, and
     float extra_bound;       // the copy's rounding (<= 2^-9 sum|q_i c_i| <= 2^-9) widens the certification bound
     const float *inv_scale;  // [B] or null: see PrepArgs (absolute slacks are divided by it)
+    int l2;                  // l2 collection: exact distance = sum (q - c)^2, selection scores are 2 q.c - |c|^2
+    const float *qnorm2;     // l2: [B] |q|^2
+    const float *cmax;       // l2: device scalar, largest row norm
     const int64_t *row_keys;
     const float *err_bound;  // [B] |e|_2, e = q - (what the scan read)
     const float *err_alpha;  // [B] |e . q|

@@ -508,7 +508,8 @@ __global__ void prep_queries_kernel(const float *__restrict__ raw, int nq, int n
                                     float *__restrict__ err_bound_split, float *__restrict__ err_alpha,
                                     float *__restrict__ err_alpha_split, int split, uint32_t *__restrict__ tau_g, int ksel,
                                     int *__restrict__ counters, int n_counters, float bound_scale, int normalize,
-                                    const float *__restrict__ cmax, float *__restrict__ inv_scale) {
+                                    const float *__restrict__ cmax, float *__restrict__ inv_scale,
+                                    float *__restrict__ qnorm2) {
     const int row = blockIdx.x;
     const int lane = threadIdx.x;  // 32 threads
     if (row == 0 && lane < n_counters) counters[lane] = 0;
@@ -593,6 +594,7 @@ __global__ void prep_queries_kernel(const float *__restrict__ raw, int nq, int n
         const float scale = fmaxf(qn * cm, 1e-30f);
         const float a_scale = cm / fmaxf(qn, 1e-30f);
         if (inv_scale) inv_scale[row] = 1.0f / scale;
+        if (qnorm2) qnorm2[row] = normalize ? 1.0f : ss;
         err_bound[row] = sqrtf(es) * bound_scale * cm;
         err_alpha[row] = fabsf(al) * bound_scale * a_scale;
         if (split) {
@@ -636,7 +638,8 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
                int *__restrict__ fail_count, int *__restrict__ fail_list, unsigned long long *__restrict__ fail_total,
                float *__restrict__ kth_exact_out, const int *__restrict__ idx_list, const int *__restrict__ limit,
                const float *__restrict__ tau0, int dim, unsigned long long *__restrict__ fail_total2, float acc_slack,
-               float extra_bound, const float *__restrict__ inv_scale) {
+               float extra_bound, const float *__restrict__ inv_scale, int l2, const float *__restrict__ qnorm2,
+               const float *__restrict__ cmax) {
     __shared__ float sq[RESCORE_MAX_DIM];
     __shared__ uint64_t exact[32 * KPL];
     const int j_cta = blockIdx.x;
@@ -678,14 +681,30 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
             for (int c = lane; c < dim / 4; c += 32) {
                 const uint2 w0 = rp0[c], w1 = rp1[c];
                 const float *qq = sq + c * 4;
-                acc0 = fmaf(__uint_as_float(w0.x << 16), qq[0], acc0);
-                acc0 = fmaf(__uint_as_float(w0.x & 0xffff0000u), qq[1], acc0);
-                acc0 = fmaf(__uint_as_float(w0.y << 16), qq[2], acc0);
-                acc0 = fmaf(__uint_as_float(w0.y & 0xffff0000u), qq[3], acc0);
-                acc1 = fmaf(__uint_as_float(w1.x << 16), qq[0], acc1);
-                acc1 = fmaf(__uint_as_float(w1.x & 0xffff0000u), qq[1], acc1);
-                acc1 = fmaf(__uint_as_float(w1.y << 16), qq[2], acc1);
-                acc1 = fmaf(__uint_as_float(w1.y & 0xffff0000u), qq[3], acc1);
+                const float a0 = __uint_as_float(w0.x << 16), a1 = __uint_as_float(w0.x & 0xffff0000u);
+                const float a2 = __uint_as_float(w0.y << 16), a3 = __uint_as_float(w0.y & 0xffff0000u);
+                const float b0 = __uint_as_float(w1.x << 16), b1 = __uint_as_float(w1.x & 0xffff0000u);
+                const float b2 = __uint_as_float(w1.y << 16), b3 = __uint_as_float(w1.y & 0xffff0000u);
+                if (l2) {  // warp-uniform: squared distance by direct differences (no cancellation), as K1 computes it
+                    float d;
+                    d = qq[0] - a0; acc0 = fmaf(d, d, acc0);
+                    d = qq[1] - a1; acc0 = fmaf(d, d, acc0);
+                    d = qq[2] - a2; acc0 = fmaf(d, d, acc0);
+                    d = qq[3] - a3; acc0 = fmaf(d, d, acc0);
+                    d = qq[0] - b0; acc1 = fmaf(d, d, acc1);
+                    d = qq[1] - b1; acc1 = fmaf(d, d, acc1);
+                    d = qq[2] - b2; acc1 = fmaf(d, d, acc1);
+                    d = qq[3] - b3; acc1 = fmaf(d, d, acc1);
+                } else {
+                    acc0 = fmaf(a0, qq[0], acc0);
+                    acc0 = fmaf(a1, qq[1], acc0);
+                    acc0 = fmaf(a2, qq[2], acc0);
+                    acc0 = fmaf(a3, qq[3], acc0);
+                    acc1 = fmaf(b0, qq[0], acc1);
+                    acc1 = fmaf(b1, qq[1], acc1);
+                    acc1 = fmaf(b2, qq[2], acc1);
+                    acc1 = fmaf(b3, qq[3], acc1);
+                }
             }
         }
 #pragma unroll
@@ -693,9 +712,9 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
             acc0 += __shfl_xor_sync(FULL_MASK, acc0, sft);
             acc1 += __shfl_xor_sync(FULL_MASK, acc1, sft);
         }
-        if (lane == 0) {
-            if (key0 != 0ull) exact[j] = pack_key(acc0, row0);
-            if (key1 != 0ull) exact[j1] = pack_key(acc1, row1);
+        if (lane == 0) {  // l2: the exact key orders by -distance (larger is better, like every other score)
+            if (key0 != 0ull) exact[j] = pack_key(l2 ? -acc0 : acc0, row0);
+            if (key1 != 0ull) exact[j1] = pack_key(l2 ? -acc1 : acc1, row1);
         }
     }
     __syncthreads();
@@ -727,7 +746,14 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
     //  evaluated at the normalised score -- see prep_queries_kernel; cosine: inv_scale = 1)
     const float isc = inv_scale != nullptr ? inv_scale[b] : 1.0f;
     const float t_copy = kth_exact - extra_bound / isc;
-    const float floor_sel = t_copy - selection_error_bound(t_copy * isc, err_bound[b], err_alpha[b]) - acc_slack / isc;
+    float floor_sel = t_copy - selection_error_bound(t_copy * isc, err_bound[b], err_alpha[b]) - acc_slack / isc;
+    if (l2) {
+        // kth_exact = -(k-th smallest exact distance).  In exact arithmetic 2 q.c - |c|^2 = |q|^2 - d, so every row at least
+        // as close has t >= |q|^2 - d_k, and its selection value 2 qb.c - |c|^2 is below t by at most 2 |e . c| <= 2 |e| C
+        // (err_bound = |e| C) plus rounding: three fp32 sums of 384 non-negative terms, <= 2.3e-5 (|q| + C)^2 in all.
+        const float qn = sqrtf(qnorm2[b]), cm = *cmax;
+        floor_sel = (qnorm2[b] + kth_exact) - 2.0f * 1.004f * err_bound[b] - 4e-5f * (qn + cm) * (qn + cm) - acc_slack / isc;
+    }
     bool certified = true;
     if (last_sel != 0ull) {                       // list full: ceiling = the k'-th selection score
         certified = n_valid >= k && floor_sel > key_score(last_sel);
@@ -745,7 +771,7 @@ rescore_kernel(const uint64_t *__restrict__ sel, int ksel, const float *__restri
             if (out_packed) out_packed[o] = 0ull;
             out_keys[o] = -1;
         } else {
-            if (out_dist) out_dist[o] = 1.0f - key_score(key);
+            if (out_dist) out_dist[o] = l2 ? -key_score(key) : 1.0f - key_score(key);
             if (out_packed) out_packed[o] = key;
             out_keys[o] = row_keys[key_row(key)];
         }
@@ -814,7 +840,8 @@ __global__ void retry_prep_kernel(const float *__restrict__ queries, const float
 
 // Largest row norm of rows [0, n) (inner-product collections: the scale of every selection error bound).  Warp per row.
 template <bool BF16>
-__global__ void row_norm_max_kernel(const uint8_t *__restrict__ rows, int64_t n, int dim, float *__restrict__ out) {
+__global__ void row_norm_max_kernel(const uint8_t *__restrict__ rows, int64_t n, int dim, float *__restrict__ out,
+                                    float *__restrict__ norm2_out) {
     const int lane = threadIdx.x & 31;
     float mx = 0.0f;
     for (int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); r < n;
@@ -834,6 +861,7 @@ __global__ void row_norm_max_kernel(const uint8_t *__restrict__ rows, int64_t n,
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL_MASK, ss, o);
         mx = fmaxf(mx, ss);
+        if (norm2_out != nullptr && lane == 0) norm2_out[r] = ss;
     }
     // (1 + 2^-7): fp32 summation noise, and for fp32 rows the bf16 copy the scan reads may be 2^-9 longer
     if (lane == 0 && mx > 0.0f) atomicMax(reinterpret_cast<unsigned int *>(out), __float_as_uint(sqrtf(mx) * 1.0078125f));
@@ -841,11 +869,11 @@ __global__ void row_norm_max_kernel(const uint8_t *__restrict__ rows, int64_t n,
 
 }  // namespace mma
 
-cudaError_t launch_row_norm_max(const void *rows, bool bf16, int64_t n, int dim, float *out, cudaStream_t s) {
+cudaError_t launch_row_norm_max(const void *rows, bool bf16, int64_t n, int dim, float *out, float *norm2_out, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     const int grid = static_cast<int>(n / 8 + 1 < 148 * 8 ? n / 8 + 1 : 148 * 8);
-    if (bf16) mma::row_norm_max_kernel<true><<<grid, 256, 0, s>>>(static_cast<const uint8_t *>(rows), n, dim, out);
-    else mma::row_norm_max_kernel<false><<<grid, 256, 0, s>>>(static_cast<const uint8_t *>(rows), n, dim, out);
+    if (bf16) mma::row_norm_max_kernel<true><<<grid, 256, 0, s>>>(static_cast<const uint8_t *>(rows), n, dim, out, norm2_out);
+    else mma::row_norm_max_kernel<false><<<grid, 256, 0, s>>>(static_cast<const uint8_t *>(rows), n, dim, out, norm2_out);
     count_launch();
     return cudaGetLastError();
 }
@@ -867,7 +895,7 @@ cudaError_t launch_prep_queries(const PrepArgs &a) {
                                                            static_cast<__nv_bfloat16 *>(a.qb), a.err_bound, a.err_bound_split,
                                                            a.err_alpha, a.err_alpha_split, a.split, a.tau_g, a.ksel,
                                                            a.counters, a.n_counters, a.bound_scale >= 1.0f ? a.bound_scale : 1.0f,
-                                                           a.normalize ? 1 : 0, a.cmax, a.inv_scale);
+                                                           a.normalize ? 1 : 0, a.cmax, a.inv_scale, a.qnorm2);
     count_launch();
     return cudaGetLastError();
 }
@@ -967,7 +995,7 @@ cudaError_t launch_rescore(const RescoreArgs &a) {
                                                             a.fail_total, a.kth_exact, a.idx_list, a.limit, a.tau0, \
                                                             a.dim, a.fail_total2,                                   \
                                                             1e-5f * static_cast<float>(((a.dim + 383) / 384) * (1 + a.split)), \
-                                                            a.extra_bound, a.inv_scale)
+                                                            a.extra_bound, a.inv_scale, a.l2, a.qnorm2, a.cmax)
 #define FR_RESCORE(KPL)                  \
     do {                                 \
         if (a.f32_rows) FR_RESCORE_T(KPL, true); \

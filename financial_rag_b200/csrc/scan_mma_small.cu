@@ -105,7 +105,10 @@ __global__ void __launch_bounds__(64 + 32 * small_epilogue_warps(NQ), 1)
 scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                       const int64_t *__restrict__ keys_or_null, int64_t n_rows, int nq, int ksel,
                       uint64_t *__restrict__ partials, int nq_total, uint32_t *__restrict__ tau_g, int k_chunks,
-                      int q0, const int *__restrict__ nq_dev) {
+                      int q0, const int *__restrict__ nq_dev, const float *__restrict__ norm2) {
+    // norm2 (l2 collections): |c|^2 of every row.  The squared distance |q - c|^2 = |q|^2 - 2 q.c + |c|^2 is smallest where
+    // 2 q.c - |c|^2 is largest, so the epilogue turns each dot product into that with ONE FFMA per score and everything
+    // downstream (gate, thresholds, lists) works on it unchanged.
     // q0: first query (row of the query block, index into partials / tau_g) this launch serves; with nq_dev the
     // live count comes from the device (retry slices: *nq_dev queries in all, this slice takes [q0, q0 + nq))
     if (nq_dev != nullptr) {
@@ -304,6 +307,11 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     }
                 }
             }
+            float cn = 0.0f;  // l2: this thread's row norm, requested before the accumulator wait hides its latency
+            if (norm2 != nullptr) {
+                const int64_t nrow = t * TILE_ROWS_CTA + quarter * 32 + lane;
+                if (nrow < n_rows) cn = __ldg(norm2 + nrow);
+            }
             mbar_wait(bar_tfull + 8 * buf, bphase);
             tc_fence_after();
             uint32_t r[NQH * (1 + SPLIT)];  // this warp's queries: hi columns [qbase, +NQH), lo columns NQ further on
@@ -322,6 +330,10 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             float v[NQH];
 #pragma unroll
             for (int q = 0; q < NQH; ++q) v[q] = SPLIT ? __uint_as_float(r[q]) + __uint_as_float(r[NQH + q]) : __uint_as_float(r[q]);
+            if (norm2 != nullptr) {  // warp-uniform
+#pragma unroll
+                for (int q = 0; q < NQH; ++q) v[q] = fmaf(2.0f, v[q], -cn);
+            }
             if (it == 0u && LMODE != LM_SHARED) {
                 // first tile of this warp: every list is empty and every row would pass one by one (32 x NQ sorted
                 // inserts).  Load the lists in bulk instead: per query one 32-key bitonic sort of the tile's scores.
@@ -497,7 +509,7 @@ cudaError_t launch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CUte
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.alloc));
     if (e != cudaSuccess) return e;
     kern<<<a.plan.lists, mma::SmallPlan<NQ, KPL, SPLIT>::THREADS, plan.alloc, a.stream>>>(tq, tc, a.keys_or_null, a.n_rows, nq, a.ksel, a.partials,
-                                                                a.nq_total, a.tau_g, k_chunks, q0, a.nq_dev);
+                                                                a.nq_total, a.tau_g, k_chunks, q0, a.nq_dev, a.norm2);
     count_launch();
     return cudaGetLastError();
     }

@@ -454,10 +454,10 @@ cudaError_t launch_scan_stream(const ScanArgs &a) { return dispatch(a, nullptr);
 // fallback: bf16 rows of 768 B (width 384, two per unit) or 1536 B (width 768), or fp32 rows of 1536 B (width 384, the
 // collections whose tensor-core scans read a bf16 copy); dot metrics only
 namespace {
-template <int KPL, int RU, bool BF16>
+template <int KPL, int RU, bool BF16, bool L2 = false>
 cudaError_t fallback_impl(const ScanArgs &a, const int *fail_count, const int *fail_list, int *occ_out) {
     const size_t smem = static_cast<size_t>(THREADS / 32) * 32 * KPL * sizeof(uint64_t);
-    auto kern = scan_stream_fallback_kernel<BF16, RU, KPL, false>;
+    auto kern = scan_stream_fallback_kernel<BF16, RU, KPL, L2>;
     cudaError_t e = prepare_kernel(kern, smem, occ_out);
     if (e != cudaSuccess || occ_out) return e;
     kern<<<a.grid, THREADS, smem, a.stream>>>(a.corpus, a.keys_or_null, a.queries, a.n_rows, a.k, a.partials,
@@ -469,6 +469,9 @@ cudaError_t fallback_dispatch(const ScanArgs &a, const int *fail_count, const in
     if (!a.bf16)  // fp32 x 384: one row per 1536-byte unit
         return a.k <= 32 ? fallback_impl<1, 1, false>(a, fail_count, fail_list, occ_out)
                          : fallback_impl<4, 1, false>(a, fail_count, fail_list, occ_out);
+    if (a.dim == 384 && a.l2)  // l2 collections of width 384 (the K2s selection's safety net)
+        return a.k <= 32 ? fallback_impl<1, 2, true, true>(a, fail_count, fail_list, occ_out)
+                         : fallback_impl<4, 2, true, true>(a, fail_count, fail_list, occ_out);
     if (a.dim == 384)
         return a.k <= 32 ? fallback_impl<1, 2, true>(a, fail_count, fail_list, occ_out)
                          : fallback_impl<4, 2, true>(a, fail_count, fail_list, occ_out);
@@ -478,7 +481,7 @@ cudaError_t fallback_dispatch(const ScanArgs &a, const int *fail_count, const in
 }  // namespace
 
 bool scan_stream_fallback_serves(const ScanArgs &a) {
-    if (a.l2) return false;
+    if (a.l2) return a.bf16 && a.dim == 384;
     return a.bf16 ? (a.dim == 384 || a.dim == 768) : a.dim == 384;
 }
 

@@ -509,6 +509,45 @@ def test_inner_product_collections_on_the_tensor_cores(frb, n, B, k, dtype):
     ix.close()
 
 
+@pytest.mark.parametrize("n,B,k", [(300, 3, 10), (70001, 1, 10), (70001, 33, 32), (50000, 64, 10), (40000, 200, 50),
+                                   (30000, 40, 100), (30000, 20, 100)])
+def test_l2_collections_on_the_tensor_cores(frb, n, B, k):
+    """l2 (squared Euclidean, chromadb's definition) through the swapped-operand tensor-core kernel: it ranks rows by
+    2 q.c - |c|^2 (one FFMA per score on stored row norms), the exact distances come from direct differences in the rescore
+    pass, batches above 64 go through in slices.  Same answer as the CUDA-core stream kernel; clustered rows of mixed
+    lengths so that norms matter."""
+    rng = np.random.default_rng(n + B)
+    corpus, centres = make_clustered(n, 30, 0.5, seed=8000 + n)
+    corpus = corpus * rng.uniform(0.5, 2.0, size=(n, 1)).astype(np.float32)
+    queries = (centres[rng.integers(0, 30, B)] * rng.uniform(0.5, 2.0, size=(B, 1)) +
+               0.3 / np.sqrt(384.0) * rng.standard_normal((B, 384))).astype(np.float32)
+    queries[0] = corpus[5]
+    ix = build_index(frb, corpus, "l2", "bf16")
+    ix.set_path("stream")
+    d_s, k_s = ix.search(queries, k)
+    ix.set_path("mma")
+    d_m, k_m = ix.search(queries, k)
+    assert ix.stat("mma_queries") == B
+    rows = keys_to_rows(k_m, KEY_BASE)
+    assert_matches_oracle(d_m, rows, queries, corpus, k, "l2", "bf16", stored=stored_rows(ix), label=f"l2 n={n} B={B} k={k}")
+    fin = np.isfinite(d_s)
+    tol = 3e-6 * np.maximum(np.abs(d_s), 1.0)
+    assert (np.abs(d_m - d_s) <= tol)[fin].all()
+    mism = (k_m != k_s) & fin
+    if mism.any():
+        assert (np.abs(d_m - d_s) <= tol)[mism].all()
+    assert rows[0, 0] == 5 and d_m[0, 0] <= 1e-4
+    # overwrite + append keep the stored norms in step with the rows
+    ix.upsert(corpus[:2] * 3.0, np.array([KEY_BASE + 9, KEY_BASE + n + 1]))
+    corpus2 = np.concatenate([corpus, corpus[1:2] * 3.0, corpus[1:2] * 3.0])[: n + 2]
+    corpus2[9] = corpus[0] * 3.0
+    d_2, k_2 = ix.search(queries, k)
+    rows2 = np.where(k_2 == KEY_BASE + n + 1, n, keys_to_rows(k_2, KEY_BASE))
+    assert_matches_oracle(d_2, rows2, queries, corpus2[: n + 1], k, "l2", "bf16", stored=stored_rows(ix),
+                          label=f"l2 after mutations n={n} B={B} k={k}")
+    ix.close()
+
+
 @pytest.mark.gpu
 def test_mma_co_resident_groups_do_not_change_results(frb):
     """Query groups that share corpus tiles through L2 (option mma_co_groups) are a scheduling
@@ -965,7 +1004,7 @@ def test_mma_path_with_deletes_and_eligibility(frb):
     with pytest.raises(FrError):
         ix.search(queries, 101)
     ix.close()
-    for kw in ({"dtype": "f32", "dim": 768}, {"space": "l2"}, {"dim": 128}):
+    for kw in ({"dtype": "f32", "dim": 768}, {"space": "l2", "dtype": "f32"}, {"space": "l2", "dim": 768}, {"dim": 128}):
         args = {"dim": 384, "space": "cosine", "dtype": "bf16"}
         args.update(kw)
         jx = frb.ShardIndex(**args)
