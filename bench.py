@@ -82,7 +82,7 @@ def parse_args():
     ap.add_argument("--sweep", default=None, help="extra batch sizes measured briefly (comma list, '' = none)")
     ap.add_argument("--single-process", action="store_true",
                     help="one process owns all --gpus devices (the store API's mode) instead of one process per GPU")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "copy"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "copy", "peer"])
     ap.add_argument("--cpu-sample-rows", type=int, default=0, help="0 = sized for a few seconds of CPU work per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the fp32 reference scan of the parity block")

@@ -19,7 +19,7 @@ FR_PATH_AUTO, FR_PATH_STREAM, FR_PATH_MMA = 0, 1, 2
 FR_MAX_K = 128
 FR_KEY_NONE = -1
 FR_ABI_VERSION = 2
-FR_XCHG_AUTO, FR_XCHG_NCCL, FR_XCHG_COPY = 0, 1, 2
+FR_XCHG_AUTO, FR_XCHG_NCCL, FR_XCHG_COPY, FR_XCHG_PEER = 0, 1, 2, 3
 
 # every symbol include/fr_index.h declares: name -> (restype, argtypes)
 SYMBOLS = {

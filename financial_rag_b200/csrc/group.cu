@@ -13,6 +13,13 @@
 // row at every moment and makes the global insertion order of two tied candidates computable from (local row, shard)
 // alone (merge_topk.cu).  Upserts of an existing key go to the shard that holds it (overwrite in place).
 //
+// Exchange modes.  FR_XCHG_NCCL: the grouped all-gather above (every device ends up with every list; the only mode when the
+// shards live in several processes).  FR_XCHG_PEER (one process, the default there): no collective at all -- every
+// shard's last kernel writes its [packed | keys] lists STRAIGHT INTO the merging GPU's buffer through NVLink peer
+// addressing (the output pointers handed to fr_index_search_partial_device are peer pointers), an event per shard tells
+// the merging stream when they have landed.  The gather is fused into the producers; what is left of the exchange is W
+// event waits.  FR_XCHG_COPY: local lists + cudaMemcpyPeerAsync (kept as the plain reference of the three).
+//
 // NCCL is bound at run time (dlopen): the process usually has torch's bundled libnccl.so.2 loaded already and two copies
 // of NCCL in one process is asking for trouble; fr_nccl_load() names another one.  Groups whose devices are not distinct
 // (tests on a one-GPU box) or that ask for it exchange the lists with peer copies instead (FR_XCHG_COPY).
@@ -192,12 +199,20 @@ int group_search_enqueue(fr_group *g, const float *const *d_queries, int B, int 
         const bool gathers = g->exchange == FR_XCHG_NCCL || d_out_keys[j] != nullptr;
         if (gathers) FR_CUDA(g->recv[j].need(static_cast<size_t>(g->W) * 2 * m * sizeof(int64_t)));
         FR_CUDA(cudaStreamWaitEvent(streams[j], g->ev_use[j], 0));
-        if (g->exchange == FR_XCHG_COPY)  // nobody may still be reading the lists this call is about to overwrite
+        if (g->exchange != FR_XCHG_NCCL)  // nobody may still be reading the lists this call is about to overwrite
             for (int o = 0; o < g->nl; ++o) FR_CUDA(cudaStreamWaitEvent(streams[j], g->ev_done[o], 0));
     }
+    int root = -1;  // FR_XCHG_PEER: the device whose buffer every shard writes into (the first one that wants the result)
+    if (g->exchange == FR_XCHG_PEER)
+        for (int o = 0; o < g->nl && root < 0; ++o)
+            if (d_out_keys[o] != nullptr) root = o;
     for (int j = 0; j < g->nl; ++j) {
         uint64_t *packed = static_cast<uint64_t *>(g->send[j].p);
         int64_t *keys = static_cast<int64_t *>(g->send[j].p) + m;
+        if (root >= 0) {  // peer pointers: the shard's last kernel stores into the merging GPU's memory
+            packed = static_cast<uint64_t *>(g->recv[root].p) + static_cast<size_t>(j) * 2 * m;
+            keys = reinterpret_cast<int64_t *>(packed) + m;
+        }
         int rc = fr_index_search_partial_device(g->shard[j], d_queries[j], B, k, packed, keys, streams[j]);
         if (rc != FR_OK) return rc;
     }
@@ -219,8 +234,15 @@ int group_search_enqueue(fr_group *g, const float *const *d_queries, int B, int 
         for (int o = 0; o < g->nl; ++o) {
             if (d_out_keys[o] == nullptr) continue;
             DeviceGuard dg(g->dev[o]);
-            for (int j = 0; j < g->nl; ++j) {
+            for (int j = 0; j < g->nl; ++j)
                 if (j != o) FR_CUDA(cudaStreamWaitEvent(streams[o], g->ev_local[j], 0));
+            if (root == o) continue;  // the lists are already here
+            if (root >= 0) {          // a second consumer: one copy of the gathered block from the first
+                FR_CUDA(cudaMemcpyPeerAsync(g->recv[o].p, g->dev[o], g->recv[root].p, g->dev[root],
+                                            static_cast<size_t>(g->W) * 2 * m * sizeof(int64_t), streams[o]));
+                continue;
+            }
+            for (int j = 0; j < g->nl; ++j) {
                 uint8_t *dst = static_cast<uint8_t *>(g->recv[o].p) + static_cast<size_t>(j) * 2 * m * sizeof(int64_t);
                 FR_CUDA(cudaMemcpyPeerAsync(dst, g->dev[o], g->send[j].p, g->dev[j], 2 * m * sizeof(int64_t), streams[o]));
             }
@@ -243,7 +265,7 @@ int group_search_enqueue(fr_group *g, const float *const *d_queries, int B, int 
             ma.out_keys = d_out_keys[o];
             ma.stream = streams[o];
             FR_CUDA(fr::launch_merge_topk(ma));
-            if (g->exchange == FR_XCHG_COPY) FR_CUDA(cudaEventRecord(g->ev_done[o], streams[o]));
+            if (g->exchange != FR_XCHG_NCCL) FR_CUDA(cudaEventRecord(g->ev_done[o], streams[o]));
         }
         FR_CUDA(cudaEventRecord(g->ev_use[o], streams[o]));
     }
@@ -320,7 +342,7 @@ int fr_group_create(int dim, int metric, int dtype, const int *devices, int n_lo
     if (first_shard < 0 || first_shard + n_local > world_shards)
         return fail(FR_EINVAL, "local shards [%d, %d) do not fit a world of %d", first_shard, first_shard + n_local,
                     world_shards);
-    if (exchange < FR_XCHG_AUTO || exchange > FR_XCHG_COPY) return fail(FR_EINVAL, "unknown exchange mode %d", exchange);
+    if (exchange < FR_XCHG_AUTO || exchange > FR_XCHG_PEER) return fail(FR_EINVAL, "unknown exchange mode %d", exchange);
     const bool all_local = n_local == world_shards;
     if (!all_local && !nccl_id)
         return fail(FR_EINVAL, "a group spanning several processes needs the NCCL unique id of its rank 0 (fr_nccl_unique_id)");
@@ -328,11 +350,26 @@ int fr_group_create(int dim, int metric, int dtype, const int *devices, int n_lo
     for (int a = 0; a < n_local; ++a)
         for (int b = a + 1; b < n_local; ++b)
             if (devices[a] == devices[b]) distinct = false;
+    // can every local device address every other one's memory?  (the same device twice: trivially)
+    bool peers_ok = true;
+    for (int a = 0; a < n_local && peers_ok; ++a)
+        for (int b = 0; b < n_local; ++b) {
+            if (devices[a] == devices[b]) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[a], devices[b]) != cudaSuccess || !can) {
+                cudaGetLastError();
+                peers_ok = false;
+                break;
+            }
+        }
     if (exchange == FR_XCHG_AUTO) {
-        exchange = FR_XCHG_NCCL;
-        if (all_local && (!distinct || world_shards == 1)) exchange = FR_XCHG_COPY;
+        if (!all_local) exchange = FR_XCHG_NCCL;
+        else if (peers_ok) exchange = FR_XCHG_PEER;
+        else exchange = distinct ? FR_XCHG_NCCL : FR_XCHG_COPY;
     }
-    if (exchange == FR_XCHG_COPY && !all_local) return fail(FR_EINVAL, "FR_XCHG_COPY needs every shard in this process");
+    if ((exchange == FR_XCHG_COPY || exchange == FR_XCHG_PEER) && !all_local)
+        return fail(FR_EINVAL, "FR_XCHG_COPY / FR_XCHG_PEER need every shard in this process");
+    if (exchange == FR_XCHG_PEER && !peers_ok) return fail(FR_EUNSUP, "FR_XCHG_PEER needs peer access between all devices of the group");
     if (exchange == FR_XCHG_NCCL && !distinct)
         return fail(FR_EINVAL, "NCCL needs distinct devices (one communicator rank per GPU); use FR_XCHG_COPY");
     if (exchange == FR_XCHG_NCCL) {

@@ -19,10 +19,10 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import FR_XCHG_AUTO, FR_XCHG_COPY, FR_XCHG_NCCL, check
+from ._lib import FR_XCHG_AUTO, FR_XCHG_COPY, FR_XCHG_NCCL, FR_XCHG_PEER, check
 from .index import _DTYPES, _METRICS, _PATHS, ShardIndex, _stream_ptr, canonical_space
 
-_EXCHANGE = {"auto": FR_XCHG_AUTO, "nccl": FR_XCHG_NCCL, "copy": FR_XCHG_COPY}
+_EXCHANGE = {"auto": FR_XCHG_AUTO, "nccl": FR_XCHG_NCCL, "copy": FR_XCHG_COPY, "peer": FR_XCHG_PEER}
 _EXCHANGE_NAME = {v: k for k, v in _EXCHANGE.items()}
 
 
@@ -86,7 +86,7 @@ class ShardGroup:
             raise ValueError("a group needs at least one device")
         self.world = int(world_shards) if world_shards else len(self.devices)
         self.first_shard = int(first_shard)
-        if _EXCHANGE[exchange] != FR_XCHG_COPY:
+        if _EXCHANGE[exchange] == FR_XCHG_NCCL or (world_shards and world_shards != len(self.devices)):
             _lib.ensure_nccl()
         dev = (ctypes.c_int * len(self.devices))(*self.devices)
         per_shard = rows_of_shard(0, self.world, int(reserve_rows))

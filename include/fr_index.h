@@ -43,7 +43,7 @@ enum { FR_BF16 = 0, FR_F32 = 1 };
 enum { FR_PATH_AUTO = 0, FR_PATH_STREAM = 1, FR_PATH_MMA = 2 };
 
 /* how the shards of an fr_group bring their local top-k lists together */
-enum { FR_XCHG_AUTO = 0, FR_XCHG_NCCL = 1, FR_XCHG_COPY = 2 };
+enum { FR_XCHG_AUTO = 0, FR_XCHG_NCCL = 1, FR_XCHG_COPY = 2, FR_XCHG_PEER = 3 };
 
 enum {
     FR_OK = 0,
@@ -165,9 +165,11 @@ int fr_merge_shards_device(int device, int metric, const uint64_t *d_packed,
  *   (ncclCommInitAll).  One process per GPU (torchrun): n_local 1, first_shard = rank, nccl_id = the 128 bytes
  *   rank 0 got from fr_nccl_unique_id and sent to everybody (ncclCommInitRank); every process then makes the same
  *   calls in the same order (SPMD), upserts included -- each keeps the rows that are its own.
- * exchange: FR_XCHG_NCCL = one grouped ncclAllGather of [packed | keys] (16 B per query and result per shard);
- *   FR_XCHG_COPY = peer copies to the devices that want the result (single process only; the only choice when two
- *   shards share a device, e.g. tests on a one-GPU box); FR_XCHG_AUTO = NCCL when the devices are distinct.
+ * exchange: FR_XCHG_NCCL = one grouped ncclAllGather of [packed | keys] (16 B per query and result per shard), the only
+ *   mode across processes; FR_XCHG_PEER (single process) = no collective: every shard's last kernel stores its lists
+ *   straight into the merging GPU's buffer through NVLink peer addressing, one event per shard orders the merge;
+ *   FR_XCHG_COPY (single process) = local lists + peer copies; FR_XCHG_AUTO = PEER in one process when the devices can
+ *   address each other, NCCL otherwise.
  * NCCL is bound at run time: the copy the process has already loaded (torch's bundled libnccl.so.2), else the
  * system's; fr_nccl_load(path) binds a specific one first. */
 int fr_nccl_load(const char *path_or_null);

@@ -3,9 +3,10 @@
 The bar: a collection spread over W shards answers exactly like the same collection on one GPU -- ids, order (ties in
 global insertion order) and distances -- through the C ABI and through the reference-facing store API.
 
-On a one-GPU box the W shards all sit on device 0 and exchange their lists with peer copies (FR_XCHG_COPY); the tests
-marked ``multi`` need W distinct GPUs and take the NCCL path (they skip on smaller boxes; bench.py's pre-flight and
-``gpurun --gpus N`` runs cover them).
+On a one-GPU box the W shards all sit on device 0 and bring their lists together without NCCL (FR_XCHG_PEER: the shards'
+last kernels store straight into the merging buffer; FR_XCHG_COPY: peer copies); the tests marked ``multi`` need W
+distinct GPUs and cover NCCL, peer stores over NVLink and peer copies (they skip on smaller boxes; bench.py's pre-flight
+and ``gpurun --gpus N`` runs cover them).
 """
 import os
 import subprocess
@@ -74,14 +75,15 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("exchange", ["peer", "copy"])
 @pytest.mark.parametrize("n,world,B,k,space,dtype", CASES)
-def test_group_equals_single_index_and_oracle(frb, n, world, B, k, space, dtype):
+def test_group_equals_single_index_and_oracle(frb, n, world, B, k, space, dtype, exchange):
     corpus = make_corpus(n, seed=n + world, dup_pairs=[(0, n - 1), (1, n // 2)] if n > 4 else [(0, 2)])
     q = make_queries(B, corpus, seed=7)
     q[0] = corpus[0]  # exact ties across shards: rows 0 and n-1 are byte-identical
     one = frb.ShardIndex(dim=384, space=space, dtype=dtype)
-    grp = frb.ShardGroup(dim=384, space=space, dtype=dtype, devices=_devices(world, False))
-    assert grp.exchange == "copy" and grp.world == world
+    grp = frb.ShardGroup(dim=384, space=space, dtype=dtype, devices=_devices(world, False), exchange=exchange)
+    assert grp.exchange == exchange and grp.world == world
     _fill(one, corpus, chunk=1777)
     _fill(grp, corpus, chunk=1777)
     assert grp.count() == one.count() == n and grp.rows() == n
@@ -249,7 +251,7 @@ def test_multi_gpu_store_api_equals_one_gpu(frb, golden, monkeypatch, tmp_path, 
         np.testing.assert_allclose([h["score"] for h in a], [h["score"] for h in b], rtol=0, atol=2e-6)
 
 
-@pytest.mark.parametrize("G,exchange", [(2, "nccl"), (2, "copy"), (4, "nccl"), (8, "nccl")])
+@pytest.mark.parametrize("G,exchange", [(2, "nccl"), (2, "copy"), (2, "peer"), (4, "nccl"), (4, "peer"), (8, "nccl"), (8, "peer")])
 def test_multi_gpu_group_equals_single_index(frb, G, exchange):
     devices = _devices(G, True)
     corpus = make_corpus(60000, seed=G, dup_pairs=[(0, 59999), (1, 30000)])
