@@ -9,7 +9,8 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 cos = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "8").split(",")]
 leads = [int(x) for x in (sys.argv[3] if len(sys.argv) > 3 else "6").split(",")]
 dev = torch.device("cuda", 0)
-sizes = [1_562_500, 3_125_000, 6_250_000, 12_500_000, 25_000_000, 50_000_000]
+sizes = [int(x) for x in os.environ.get("FR_SWEEP_SIZES", "1562500,3125000,6250000,12500000,25000000,50000000").split(",")]
+dbgs = [int(x) for x in os.environ.get("FR_SWEEP_DBG", "0").split(",")]
 ix = frb.ShardIndex(dim=384, dtype="bf16", reserve_rows=sizes[-1])
 g = torch.Generator(device=dev).manual_seed(4321)
 q = torch.randn((batch, 384), generator=g, device=dev)
@@ -22,7 +23,9 @@ for n in sizes:
         have += rows
     torch.cuda.synchronize()
     for co in cos:
+      for dbg in dbgs:
         for lead in leads:
+            ix.set_option("mma_debug", dbg)
             ix.set_option("mma_co_groups", co)
             ix.set_option("mma_max_lead", lead)
             for _ in range(3):
@@ -37,7 +40,7 @@ for n in sizes:
             e1.record(); torch.cuda.synchronize()
             ix.set_profile(False)
             ms, launches, searches = ix.profile_read()
-            print(json.dumps({"rows": n, "batch": batch, "co": co, "lead": lead, "steps": steps,
+            print(json.dumps({"rows": n, "batch": batch, "co": co, "lead": lead, "dbg": dbg, "steps": steps,
                               "step_ms": round(e0.elapsed_time(e1) / steps, 4), "scan_launch_ms": round(ms / launches, 4),
                               "launches_per_step": launches / steps,
                               "tflops": round(2.0 * n * 384 * batch / (e0.elapsed_time(e1) / steps) / 1e9, 1),
