@@ -82,6 +82,22 @@ static_assert(SmemPlan<1>::ALLOC <= 232448 && SmemPlan<2>::ALLOC <= 232448 && Sm
                   SmemPlan<8>::ALLOC <= 232448,
               "exceeds 227 KB of shared memory");
 
+// v[i] for a run-time i: registers cannot be indexed, so a 6-level tree of selects (63 of them)
+__device__ __forceinline__ float mux64(const float (&v)[64], int i) {
+    float a[32], b[16], c[8], d[4], e[2];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] = (i & 1) ? v[2 * j + 1] : v[2 * j];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) b[j] = (i & 2) ? a[2 * j + 1] : a[2 * j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c[j] = (i & 4) ? b[2 * j + 1] : b[2 * j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[j] = (i & 8) ? c[2 * j + 1] : c[2 * j];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) e[j] = (i & 16) ? d[2 * j + 1] : d[2 * j];
+    return (i & 32) ? e[1] : e[0];
+}
+
 // Fold the pending candidates of one query into its sorted list (all 32 lanes cooperate).
 //   list: [32*KPL] sorted descending (0 = empty), pend_w: this warp's pending block, n = pending count.
 // Returns the new k'-th key (0 while the list is not full).
@@ -391,9 +407,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 // ---- candidate path.  Every lane appends its own query's passing scores to its pending
                 //      block; a lane whose block fills up gets it folded into its sorted list (warp-wide
                 //      bitonic network) and resumes where it stopped, with the raised threshold.
-                //      The walk is warp-uniform: OR of the lanes' pass masks, one iteration per column
-                //      that holds a candidate, the column re-read from TMEM (registers cannot be
-                //      indexed by a run-time column number). ----
+                //      Each lane walks its own pass mask (see below). ----
                 const uint32_t rbase = row0 + c * 64;
                 int resume = 0;
                 while (true) {
@@ -405,33 +419,30 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     }
                     uint64_t m = (static_cast<uint64_t>(mhi) << 32) | mlo;
                     m = resume < 64 ? (m & (~0ull << resume)) : 0ull;
-                    uint32_t alo = __reduce_or_sync(FULL_MASK, static_cast<uint32_t>(m));
-                    uint32_t ahi = __reduce_or_sync(FULL_MASK, static_cast<uint32_t>(m >> 32));
                     bool full = false;
                     int stop = 64;
-                    while ((alo | ahi) != 0u) {
-                        int i;
-                        if (alo != 0u) {
-                            i = __ffs(alo) - 1;
-                            alo &= alo - 1;
-                        } else {
-                            i = 32 + __ffs(ahi) - 1;
-                            ahi &= ahi - 1;
-                        }
-                        const float x = tmem_ld1(tcol + c * 64 + i);
-                        if (((m >> i) & 1ull) != 0ull && !full) {
+                    // every lane walks ITS OWN passing columns; the score comes out of the lane's registers through a
+                    // 6-level select tree (mux64).  The first version walked the UNION of the lanes' columns warp-uniformly
+                    // and re-read each one from TMEM: ~4.6 iterations and TMEM round trips per chunk where one lane in
+                    // 32 has a candidate -- the dominant fixed cost of a launch (k' ln(rows) candidates per query whatever
+                    // the shard size: 0.76 ms per 2048-query launch, profiles/r02_ncu_stall_buckets_scan_mma_short_390k.txt).
+                    while (__any_sync(FULL_MASK, m != 0ull && !full)) {
+                        if (m != 0ull && !full) {
+                            const int i = __ffsll(static_cast<long long>(m)) - 1;
+                            const float x = mux64(v, i);
                             const uint32_t row = rbase + i;
                             bool ok = row < n_rows;
                             if (ok && keys_or_null != nullptr) ok = keys_or_null[row] != KEY_TOMBSTONE;
-                            if (ok) {
-                                if (cnt == PEND) {
-                                    full = true;
-                                    stop = i;
-                                } else {
+                            if (ok && cnt == PEND) {
+                                full = true;  // resume from this column after the compaction
+                                stop = i;
+                            } else {
+                                if (ok) {
                                     pend_w[cnt * 32 + ((lane + cnt) & 31)] = pack_key(x, row);
                                     ++cnt;
                                     best = max(best, order_bits(x));
                                 }
+                                m &= m - 1;
                             }
                         }
                     }
