@@ -819,7 +819,7 @@ def run_ours(args, out=sys.stdout):
     if rank == 0:
         par = "row-shard x%d (%s)" % (n_gpus, "one GPU" if n_gpus == 1 else
                                       ("one process per GPU, fr_group over NCCL" if world > 1 else
-                                       f"one process, fr_group exchange={pre.get('exchange')}"))
+                                       f"one process, fr_group exchange={cols[0].grp.exchange}"))
         line = {
             "metric": metric_name(args), "value": value, "unit": "queries/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,

@@ -90,6 +90,7 @@ constexpr int64_t PAD_ROWS = 32;
 
 namespace fr {
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_launches(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace fr
 
 struct fr_index {

@@ -7,6 +7,7 @@
 namespace fr {
 
 void count_launch();  // bumps the process-wide kernel launch counter (api.cu)
+void count_launches(int64_t n);  // ... by n (negative: a stream capture enqueued nothing; positive: a graph replay)
 
 // ---- K1 scan_topk_stream ------------------------------------------------------------------
 struct ScanArgs {

@@ -18,8 +18,22 @@
  *     are int64-representable decimal strings); FR_KEY_NONE (-1) pads short result lists.
  *   - distances follow chromadb/hnswlib: cosine d = 1 - <a/|a|, b/|b|>, ip d = 1 - <a,b>,
  *     l2 d = sum (a-b)^2.  Results are sorted by ascending distance, ties by insertion order.
- *   - all entry points are thread-safe; calls on one index are serialised internally.
+ *   - all entry points are thread-safe.  Mutations of one index are serialised; concurrent host searches hold the
+ *     index's lock only while they are enqueued on its stream, then wait for their own event and read their own
+ *     pinned staging slot (four slots per index / group).
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *   - exactness.  Results are those of an fp32-query scan of the stored rows.  The tensor-core paths SELECT candidates
+ *     with bf16 query terms and certify the selection against the exact fp32 rescoring; an uncertified query is
+ *     re-scanned exactly inside the same call.  The certification margin is (rigorous bound on the query rounding,
+ *     |q - q_bf16| * |c|, score-aware) + (accumulation slack: 1e-5 per 384 products, x2 for two-term queries).  The
+ *     slack is a statistical bound, not a worst-case one: fp32 accumulation errors of 384 products behave like
+ *     sqrt(384) * 2^-24 * sum|q_i c_i| ~ 1.2e-6 (the slack is ~8 sigma); the worst case, every rounding in the same
+ *     direction with truncating tensor-core accumulation, would be 384 * 2^-23 ~ 4.6e-5.
+ *   - the final distances are fp32 sums of 384 products whose ORDER depends on the kernel that produced them (the
+ *     streaming scan, the rescore pass after a tensor-core selection, the re-scan): the same query may return
+ *     distances that differ in the last ulp (<= 2e-6 on unit vectors), and therefore a different order of rows whose
+ *     exact scores tie to that precision, depending on batch size and routing.  Exact duplicates always tie exactly
+ *     and come back in insertion order.
  */
 #ifndef FR_INDEX_H
 #define FR_INDEX_H
