@@ -106,10 +106,16 @@ class B200MultiVectorChildStore:
         ix = self.col.index
         if ix is None or ix.count() == 0:
             return []
-        dev = torch.device("cuda", ix.device)
-        q = torch.as_tensor(np.ascontiguousarray(qvecs, dtype=np.float32)).to(dev)
-        t, kp = q.shape[0], self.topk_per_token
-        dist, keys = ix.search_device(q, kp)                      # ONE scan for all T tokens
+        from .group import ShardGroup
+
+        q_host = torch.as_tensor(np.ascontiguousarray(qvecs, dtype=np.float32))
+        t, kp = q_host.shape[0], self.topk_per_token
+        if isinstance(ix, ShardGroup):                            # row-sharded collection: the merged lists land on its first GPU
+            qs = [q_host.to(torch.device("cuda", d)) for d in ix.devices]
+            dl, kl = ix.search_device(qs, kp, merge_on=[0])
+            dist, keys = dl[0], kl[0]
+        else:
+            dist, keys = ix.search_device(q_host.to(torch.device("cuda", ix.device)), kp)   # ONE scan for all T tokens
         sc, grp = maxsim_aggregate_device(dist.view(1, t, kp), keys.view(1, t, kp), TOKEN_BITS, top_k_children)
         sc, grp = sc[0].cpu().tolist(), grp[0].cpu().tolist()
         out: List[Dict[str, Any]] = []

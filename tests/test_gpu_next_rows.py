@@ -446,6 +446,34 @@ def test_migrate_chroma_wal_replay(frb, golden, tmp_path, monkeypatch):
 
 # ---------------------------------------------------------------------------------------------
 # round-2 additions: shared ordinals, crash-safe flushes, the directory lock, score fusion, the ensemble searcher
+def test_multivector_store_on_a_row_sharded_collection(frb, tmp_path, monkeypatch):
+    """B200_CHILD_DEVICES also shards the token collection of the multi-vector store: same MaxSim ranking."""
+    rng = np.random.default_rng(9)
+    table = {}
+
+    def embedder(text, max_tokens):
+        return [table.setdefault(w, rng.standard_normal(384).astype(np.float32)) for w in text.split()[:max_tokens]]
+
+    words = [f"w{i}" for i in range(300)]
+    kids = [_Child(7000 + c, c // 4, " ".join(rng.choice(words, size=int(rng.integers(5, 25)))), None) for c in range(80)]
+    query = " ".join(kids[11].content.split()[:5] + kids[30].content.split()[:3])
+    answers = []
+    for devices in (None, "0,0,0"):
+        if devices is None:
+            monkeypatch.delenv("B200_CHILD_DEVICES", raising=False)
+        else:
+            monkeypatch.setenv("B200_CHILD_DEVICES", devices)
+        monkeypatch.setenv("CHROMA_CHILD_PERSIST_DIR", str(tmp_path / (devices or "one").replace(",", "_")))
+        frb.reset_registry()
+        store = frb.B200MultiVectorChildStore(token_embedder=embedder)
+        store.upsert_child_tokens(kids)
+        answers.append(store.search_aggregate(query, top_k_children=10))
+        frb.reset_registry()
+    assert [h["child_id"] for h in answers[1]] == [h["child_id"] for h in answers[0]]
+    np.testing.assert_allclose([h["score"] for h in answers[1]], [h["score"] for h in answers[0]], rtol=0, atol=1e-5)
+    assert answers[0][0]["child_id"] in ("7011", "7030")
+
+
 def test_multivector_store_objects_share_the_collections_ordinals(frb, tmp_path, monkeypatch):
     """The reference builds a MultiVectorChildStore per request (rag_backend.py:656) and another for ingest
     (pipeline.py:25).  Two live objects that ingest different children must not hand out the same ordinal: the map
