@@ -25,6 +25,9 @@
 // (tests on a one-GPU box) or that ask for it exchange the lists with peer copies instead (FR_XCHG_COPY).
 #include <dlfcn.h>
 
+#include <functional>
+#include <thread>
+
 #include <algorithm>
 #include <condition_variable>
 #include <cstring>
@@ -122,6 +125,50 @@ constexpr int64_t SHARD_ROW_LIMIT = 0xfffffff0ll;
 
 }  // namespace
 
+// One enqueueing thread per local shard beyond the first: a local search is ~11 kernel launches, and eight of them issued
+// back to back from one thread cost a batch-1 search over 8 GPUs 0.4 ms of host time (1.83 ms against 1.44 ms with one
+// process per GPU, profiles/r02_bench_cfg4_n8_single_process.json).
+struct ShardWorker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, done = true, quit = false;
+    void loop() {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv.wait(lk, [&] { return has_job || quit; });
+            if (quit) return;
+            std::function<void()> j = std::move(job);
+            has_job = false;
+            lk.unlock();
+            j();
+            lk.lock();
+            done = true;
+            cv.notify_all();
+        }
+    }
+    void submit(std::function<void()> j) {
+        std::lock_guard<std::mutex> lk(m);
+        job = std::move(j);
+        has_job = true;
+        done = false;
+        cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return done; });
+    }
+    void stop() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            quit = true;
+        }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+    }
+};
+
 struct fr_group {
     int dim = 0, metric = FR_COSINE, dtype = FR_BF16;
     int W = 1, first = 0, nl = 1;  // shards in the world, first local shard, local shards
@@ -150,6 +197,8 @@ struct fr_group {
     std::unordered_map<int64_t, int64_t> keymap;  // key -> global row (live rows only)
     bool keymap_valid = true;
     int64_t n_searches = 0;
+    bool enqueue_threads = true;
+    std::vector<ShardWorker *> workers;  // [nl], entry 0 unused (the calling thread serves shard 0); created on first use
 
     bool all_local() const { return nl == W; }
     size_t row_bytes() const { return static_cast<size_t>(dim) * (dtype == FR_BF16 ? 2 : 4); }
@@ -206,16 +255,38 @@ int group_search_enqueue(fr_group *g, const float *const *d_queries, int B, int 
     if (g->exchange == FR_XCHG_PEER)
         for (int o = 0; o < g->nl && root < 0; ++o)
             if (d_out_keys[o] != nullptr) root = o;
-    for (int j = 0; j < g->nl; ++j) {
+    // the local searches: shard 0 from this thread, the others from their own enqueueing threads, all at once
+    const bool threaded = g->nl > 1 && g->enqueue_threads;
+    if (threaded && g->workers.empty()) {
+        g->workers.assign(static_cast<size_t>(g->nl), nullptr);
+        for (int j = 1; j < g->nl; ++j) {
+            g->workers[static_cast<size_t>(j)] = new ShardWorker();
+            ShardWorker *w = g->workers[static_cast<size_t>(j)];
+            w->th = std::thread([w] { w->loop(); });
+        }
+    }
+    std::vector<int> rcs(static_cast<size_t>(g->nl), FR_OK);
+    std::vector<std::string> errs(static_cast<size_t>(g->nl));
+    auto local = [&, root, m](int j) {
         uint64_t *packed = static_cast<uint64_t *>(g->send[j].p);
         int64_t *keys = static_cast<int64_t *>(g->send[j].p) + m;
         if (root >= 0) {  // peer pointers: the shard's last kernel stores into the merging GPU's memory
             packed = static_cast<uint64_t *>(g->recv[root].p) + static_cast<size_t>(j) * 2 * m;
             keys = reinterpret_cast<int64_t *>(packed) + m;
         }
-        int rc = fr_index_search_partial_device(g->shard[j], d_queries[j], B, k, packed, keys, streams[j]);
-        if (rc != FR_OK) return rc;
+        rcs[static_cast<size_t>(j)] = fr_index_search_partial_device(g->shard[j], d_queries[j], B, k, packed, keys, streams[j]);
+        if (rcs[static_cast<size_t>(j)] != FR_OK) errs[static_cast<size_t>(j)] = fr_last_error();  // (thread-local: carry it over)
+    };
+    if (threaded) {
+        for (int j = 1; j < g->nl; ++j) g->workers[static_cast<size_t>(j)]->submit([&local, j] { local(j); });
+        local(0);
+        for (int j = 1; j < g->nl; ++j) g->workers[static_cast<size_t>(j)]->wait();
+    } else {
+        for (int j = 0; j < g->nl; ++j) local(j);
     }
+    for (int j = 0; j < g->nl; ++j)
+        if (rcs[static_cast<size_t>(j)] != FR_OK)
+            return fail(rcs[static_cast<size_t>(j)], "shard %d: %s", g->first + j, errs[static_cast<size_t>(j)].c_str());
     if (g->exchange == FR_XCHG_NCCL) {
         FR_NCCL(g_nccl.GroupStart());
         for (int j = 0; j < g->nl; ++j) {
@@ -300,6 +371,12 @@ int fr_nccl_unique_id(void *out, int nbytes) {
 
 int fr_group_destroy(fr_group *g) {
     if (!g) return FR_OK;
+    for (ShardWorker *w : g->workers)
+        if (w) {
+            w->stop();
+            delete w;
+        }
+    g->workers.clear();
     for (int j = 0; j < static_cast<int>(g->shard.size()); ++j) {
         DeviceGuard dg(g->dev[j]);
         cudaDeviceSynchronize();
@@ -475,6 +552,11 @@ int fr_group_shard(fr_group *g, int local_shard, fr_index **out) {
 
 int fr_group_set_option(fr_group *g, const char *name, int64_t value) {
     if (!g || !name) return fail(FR_EINVAL, "NULL argument");
+    if (std::strcmp(name, "enqueue_threads") == 0) {  // 0: this thread enqueues every local search itself (for A/B timing)
+        std::lock_guard<std::mutex> lk(g->mu);
+        g->enqueue_threads = value != 0;
+        return FR_OK;
+    }
     for (fr_index *ix : g->shard) {
         int rc = fr_index_set_option(ix, name, value);
         if (rc != FR_OK) return rc;
