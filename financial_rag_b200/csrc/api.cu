@@ -489,7 +489,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     pa.split = split;
     pa.bound_scale = static_cast<float>(ix->mma_bound_scale_pct) / 100.0f;
     pa.tau_g = static_cast<uint32_t *>(ix->tau.p);
-    pa.ksel = ksel;
+    pa.ksel = (ix->mma_debug & 128) ? 0 : ksel;  // diagnostics: 128 = the threshold slots keep the previous search's values
     pa.counters = counters;
     pa.n_counters = 2;
     pa.normalize = ix->metric == FR_COSINE;

@@ -42,17 +42,19 @@ constexpr int S_TMEM_BUFS = 4;
 // offsets are computed, identically, on the host (launch size) and in the kernel.
 constexpr int S_MAX_STAGES = 8;
 // Where the candidate lists live (k' = 32 KPL entries per query):
-//   LM_WARP   k' <= 64: one list per (epilogue warp, query) in shared memory, merged at the end -- no sharing, no locks;
-//   LM_SHARED k' = 128 / 256 (k up to 100: cfg3's per-collection top-50, cfg5's top-100): per-warp lists would be 256 KB+,
-//             so the four lane-quarter warps that serve a query share ONE list per query in shared memory (<= 64 KB)
-//             under a per-query spin lock; a warp folds all its passing rows of a tile into it in one bitonic network;
+//   LM_WARP   while they fit in 64 KB (k' = 32; k' = 64 up to 32 queries): one list per (epilogue warp, query) in shared
+//             memory, merged at the end -- no sharing, no locks;
+//   LM_SHARED beyond (k' = 128 / 256 -- k up to 100: cfg3's per-collection top-50, cfg5's top-100 -- and 64 queries at
+//             k' = 64): per-warp lists would be 128 KB+ and leave no room for the ring, so the four lane-quarter warps
+//             that serve a query share ONE list per query in shared memory (<= 64 KB) under a per-query spin lock; a
+//             warp folds all its passing rows of a tile into it in one bitonic network;
 //   (not served) 64 queries x k' = 256 is 128 KB even when shared.  Lists in global memory were tried: the corpus stream
 //             evicts them from L2, every insert is a DRAM round trip -- 0.75 of the copy peak at k' = 128
 //             (profiles/r02_ncu_full_scan_mma_small_64q_k128_10m_global_lists.txt) and 8 x the roofline time at k' = 256
 //             (profiles/r02_launches_k100_b1024_25m.txt).  Batches of 33-64 with k > 64 take K2 instead.
 enum { LM_WARP = 0, LM_SHARED = 1, LM_NONE = 2 };
 __host__ __device__ constexpr int small_list_mode(int nq, int kpl) {
-    return kpl <= 2 ? LM_WARP : (nq * 32 * kpl * 8 <= 65536 ? LM_SHARED : LM_NONE);
+    return (kpl <= 2 && 4 * nq * 32 * kpl * 8 <= 65536) ? LM_WARP : (nq * 32 * kpl * 8 <= 65536 ? LM_SHARED : LM_NONE);
 }
 template <int NQ, int KPL, int SPLIT>
 struct SmallPlan {
@@ -105,7 +107,9 @@ __global__ void __launch_bounds__(64 + 32 * small_epilogue_warps(NQ), 1)
 scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                       const int64_t *__restrict__ keys_or_null, int64_t n_rows, int nq, int ksel,
                       uint64_t *__restrict__ partials, int nq_total, uint32_t *__restrict__ tau_g, int k_chunks,
-                      int q0, const int *__restrict__ nq_dev, const float *__restrict__ norm2) {
+                      int q0, const int *__restrict__ nq_dev, const float *__restrict__ norm2, int dbg) {
+    // dbg (option "mma_debug", diagnostics: results are wrong): 2 = the gate runs but no row ever enters a list, 64 = no
+    // threshold refresh from the other CTAs
     // norm2 (l2 collections): |c|^2 of every row.  The squared distance |q - c|^2 = |q|^2 - 2 q.c + |c|^2 is smallest where
     // 2 q.c - |c|^2 is largest, so the epilogue turns each dot product into that with ONE FFMA per score and everything
     // downstream (gate, thresholds, lists) works on it unchanged.
@@ -269,7 +273,13 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
         for (int q = 0; q < NQH; ++q) tau[q] = q < nqw ? -INFINITY : INFINITY;  // padded queries never pass
         // shared thresholds (see scan_mma.cu): this CTA raises slot cta % k' of a query to the best score it holds
+        // With fewer CTAs than slots (k' = 256 on 148 SMs) CTA c owns the slots c, c + P, c + 2P, ... and raises slot
+        // c + r P to the r-th best score it holds: every slot is still backed by a row of its own, so the minimum over
+        // the k' slots stays a score that k' distinct rows reach.  (Without this the slots beyond P stayed empty, the
+        // shared threshold never switched on and a top-100 search of 16 queries took 7 x the corpus read,
+        // profiles/r02_k2s_wide_lists_10m.jsonl.)
         uint32_t *my_slots = tau_g + static_cast<size_t>(q0 + qbase) * ksel + (cta % ksel);  // + q * ksel
+        const int n_own = ncta >= ksel ? 1 : min(32, (ksel - cta + ncta - 1) / ncta);
         uint32_t it = 0;
         uint32_t next_refresh = 0;
         for (int64_t t = cta; t < num_tiles; t += ncta, ++it) {
@@ -281,7 +291,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             // (Tried: a seventh warp polling the slots every 1.5 us and handing the thresholds over through shared
             // memory -- 5-8 % slower at every batch size: the polling traffic costs more than the refresh.)
             // (schedule as in K2: every tile at first, then geometrically thinning out to every 64th tile)
-            const bool refresh_now = it >= next_refresh;
+            const bool refresh_now = it >= next_refresh && !(dbg & 64);
             if (refresh_now) next_refresh = it + 1u + min(it >> 1, 63u);
             if (refresh_now) {
                 uint32_t x[NQH];
@@ -347,7 +357,6 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     uint64_t key = valid ? pack_key(my_stash[q * 32 + lane], row) : 0ull;
                     key = bitonic_sort32_desc(key, lane);
                     my_lists[q * CAP + lane] = key;  // entries 32 .. CAP-1 stay empty
-                    const uint32_t best = __shfl_sync(FULL_MASK, static_cast<uint32_t>(key >> 32), 0);
                     if (KPL == 1) {  // a full list already gates
                         const uint32_t last = __shfl_sync(FULL_MASK, static_cast<uint32_t>(key >> 32), 31);
                         const float nt = last != 0u ? unorder_bits(last) : -INFINITY;
@@ -362,7 +371,8 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                             default: break;
                         }
                     }
-                    if (lane == 0 && best != 0u) atomicMax(my_slots + static_cast<size_t>(q) * ksel, best);
+                    const uint32_t mine_hi = static_cast<uint32_t>(key >> 32);  // lane r: the r-th best row of this warp
+                    if (lane < n_own && mine_hi != 0u) atomicMax(my_slots + static_cast<size_t>(q) * ksel + lane * ncta, mine_hi);
                 }
                 __syncwarp();
                 continue;
@@ -383,7 +393,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             float mall = gm[0];
 #pragma unroll
             for (int g = 1; g < NG; ++g) mall = fmaxf(mall, gm[g]);
-            if (!__any_sync(FULL_MASK, mall > 0.0f)) continue;  // the common case
+            if (!__any_sync(FULL_MASK, mall > 0.0f) || (dbg & 2)) continue;  // the common case
             // ---- candidate path (one copy of the insert code whatever NQ: the queries with a passing row are
             //      walked with a run-time index, so the scores of the groups that hold one go through shared memory) ----
             const uint32_t row = static_cast<uint32_t>(t * TILE_ROWS_CTA) + quarter * 32 + lane;
@@ -405,8 +415,13 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
             for (int h = 0; h < 1; ++h) {
                 uint32_t qm = __reduce_or_sync(FULL_MASK, pm[h]);  // queries with at least one passing row
+                // LM_SHARED: the four warps that share the lists start their walk a quarter of the queries apart; walking in
+                // the same order they met at every lock of the early, busy tiles (14 spins per acquisition measured)
+                constexpr uint32_t QMASK = NQH >= 32 ? 0xffffffffu : ((1u << (NQH & 31)) - 1u);
+                const int rot = LMODE == LM_SHARED ? quarter * (NQH / 4) : 0;
+                qm = ((qm >> rot) | (qm << ((NQH - rot) & 31))) & QMASK;
                 while (qm != 0u) {
-                    const int qb = __ffs(qm) - 1;
+                    const int qb = (__ffs(qm) - 1 + rot) & (NQH - 1);
                     qm &= qm - 1;
                     const int q = h * 32 + qb;
                     const bool has = ((pm[h] >> qb) & 1u) != 0u;
@@ -414,7 +429,8 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     uint64_t *lp = my_lists + q * CAP;
                     if (LMODE == LM_SHARED) {  // the other lane quarters' warps fold into the same list
                         if (lane == 0)
-                            while (atomicCAS(my_locks + q, 0, 1) != 0) __nanosleep(32);
+                            while (atomicCAS(my_locks + q, 0, 1) != 0)
+                                while (*(volatile int *)(my_locks + q) != 0) {}  // held for a few hundred cycles: poll, no sleep
                         __syncwarp();
                         __threadfence_block();
                     }
@@ -422,11 +438,9 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
                     for (int j = 0; j < KPL; ++j) lst.e[j] = LMODE == LM_SHARED ? *(volatile uint64_t *)(lp + j * 32 + lane) : lp[j * 32 + lane];
                     const uint64_t mine = pack_key(my_stash[q * 32 + lane], row);
-                    uint32_t best = 0;
-                    if (KPL >= 4 && __popc(mask) > 3) {
+                    if (LMODE == LM_SHARED && __popc(mask) > 3) {
                         // many rows at once (the first tiles, before the thresholds bite): one sort + one fold network
                         const uint64_t p = bitonic_sort32_desc(has ? mine : 0ull, lane);
-                        best = __shfl_sync(FULL_MASK, static_cast<uint32_t>(p >> 32), 0);
                         fold_sorted32<KPL>(lst.e, p, lane);
                     } else {
                         while (mask) {
@@ -435,7 +449,6 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                             const uint32_t lo = __shfl_sync(FULL_MASK, static_cast<uint32_t>(mine), src);
                             const uint32_t hi = __shfl_sync(FULL_MASK, static_cast<uint32_t>(mine >> 32), src);
                             lst.insert((static_cast<uint64_t>(hi) << 32) | lo, CAP, lane);
-                            best = max(best, hi);
                         }
                     }
 #pragma unroll
@@ -457,7 +470,8 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #undef FR_TAU_CASE
                         default: break;
                     }
-                    if (lane == 0) atomicMax(my_slots + static_cast<size_t>(q) * ksel, best);
+                    const uint32_t own_hi = static_cast<uint32_t>(lst.e[0] >> 32);  // lane r: the r-th best row of the list
+                    if (lane < n_own && own_hi != 0u) atomicMax(my_slots + static_cast<size_t>(q) * ksel + lane * ncta, own_hi);
                 }
             }
             __syncwarp();
@@ -509,7 +523,7 @@ cudaError_t launch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CUte
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.alloc));
     if (e != cudaSuccess) return e;
     kern<<<a.plan.lists, mma::SmallPlan<NQ, KPL, SPLIT>::THREADS, plan.alloc, a.stream>>>(tq, tc, a.keys_or_null, a.n_rows, nq, a.ksel, a.partials,
-                                                                a.nq_total, a.tau_g, k_chunks, q0, a.nq_dev, a.norm2);
+                                                                a.nq_total, a.tau_g, k_chunks, q0, a.nq_dev, a.norm2, a.dbg);
     count_launch();
     return cudaGetLastError();
     }

@@ -575,7 +575,8 @@ def test_mma_co_resident_groups_do_not_change_results(frb):
 
 
 @pytest.mark.parametrize("B,k", [(2, 10), (16, 10), (17, 16), (32, 32), (33, 10), (64, 16), (64, 32),
-                                 # k' = 128 / 256: candidate lists in global memory (cfg3's top-50, cfg5's top-100)
+                                 # k' = 128 / 256 (cfg3's top-50, cfg5's top-100) and 64 queries at k' = 64: one list per
+                                 # query shared by four warps; k' = 256 > 148 CTAs: a CTA publishes its two best rows
                                  (1, 50), (16, 50), (24, 64), (64, 50), (8, 100), (32, 100), (64, 100)])
 def test_small_batch_swapped_operand_kernel_equals_k2(frb, B, k):
     """K2s (corpus rows as the MMA's M operand, queries as N; batches <= 64) and K2 select the same candidates:
@@ -603,6 +604,22 @@ def test_small_batch_swapped_operand_kernel_equals_k2(frb, B, k):
             assert keys_to_rows(k_s[int(B > 1)], KEY_BASE)[0] == 11 and (k < 2 or keys_to_rows(k_s[int(B > 1)], KEY_BASE)[1] == 30000)
             victims = np.unique(k_s[:, 0])
             ix.delete(victims)
+    ix.close()
+
+
+@pytest.mark.parametrize("n,B,k", [(700, 3, 100), (3000, 40, 50), (3000, 20, 100), (9000, 64, 32)])
+def test_small_batch_kernel_with_fewer_ctas_than_threshold_slots(frb, n, B, k):
+    """A corpus of a few tiles runs on a handful of CTAs: each owns several of a query's k' threshold slots and backs
+    slot c + r P with its r-th best row (up to 32; beyond that slots stay empty and nothing is shared).  Results are
+    the oracle's either way."""
+    corpus = make_corpus(n, 384, seed=77 + n)
+    queries = make_queries(B, corpus, seed=78 + k)
+    ix = build_index(frb, corpus, "cosine", "bf16")
+    ix.set_path("mma")
+    d, kk = ix.search(queries, k)
+    assert_matches_oracle(d, keys_to_rows(kk, KEY_BASE), queries, corpus, k, "cosine", "bf16", stored=stored_rows(ix),
+                          label=f"few CTAs n={n} B={B} k={k}")
+    assert ix.stat("mma_queries") == B
     ix.close()
 
 
