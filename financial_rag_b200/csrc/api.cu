@@ -111,7 +111,7 @@ struct fr_index {
     cudaStream_t stream = nullptr;   // host-path stream
     cudaEvent_t last_use = nullptr;  // orders scratch reuse across caller streams
     DevBuf q_raw, q_prep, q_keys, partials, out_dist, out_keys, stage_vecs, stage_keys, stage_rows;
-    DevBuf q_bf16, err_bound, sel, sel_keys, flags, fail, fb_partials, tau, progress, s_lists;  // K2 path
+    DevBuf q_bf16, err_bound, sel, sel_keys, flags, fail, fb_partials, tau, hist, progress, s_lists;  // K2 path
     DevBuf cmax;             // inner-product / l2 collections: largest row norm (device float), the scale of the error bounds
     int64_t cmax_rows = 0;   // rows it covers; an in-place overwrite resets it
     DevBuf norm2;            // l2 collections: |c|^2 per row (the tensor-core selection ranks by 2 q.c - |c|^2)
@@ -124,6 +124,7 @@ struct fr_index {
     int mma_split_max = 32;  // (measured: free up to 32 queries -- one MMA of N = 2 x 32 per K step; 64 do not fit an accumulator)
     int64_t small_rows_b1 = 2000000, small_rows_b4 = 200000;  // FR_PATH_AUTO: below these sizes batch 1 / batch <= 4 take K1
     int mma_bound_scale_pct = 100;  // diagnostics / tests: certification error bounds x this / 100 (>= 100: stricter, still exact)
+    int mma_score_hist = 1; // K2s: share a score histogram between the CTAs (0 = threshold slots only; for A/B timing)
     int mma_debug = 0;      // diagnostics (scripts/ablate_mma.py): results are wrong when non-zero
     int mma_wide_lists = 1; // k in (64, 100]: keep 256 candidates per query instead of 128
     int mma_max_lead = 6;   // K2 co-resident groups: tiles a group may run ahead of the slowest group of its stream (0 = unthrottled)
@@ -463,6 +464,9 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     // 2 counters (+2 pad) | fail_list [B] | fail_list2 [B] | retry_n [slices]
     FR_CUDA(ix->fail.need((4 + 2 * static_cast<size_t>(B) + static_cast<size_t>(slices)) * sizeof(int)));
     FR_CUDA(ix->tau.need(static_cast<size_t>(B) * ksel * sizeof(uint32_t)));
+    // K2s on a cosine collection: the CTAs also share a score histogram per query (scan_mma_small.cu)
+    const bool use_hist = small && ix->metric == FR_COSINE && ix->mma_score_hist != 0;
+    if (use_hist) FR_CUDA(ix->hist.need(static_cast<size_t>(B) * fr::SCORE_HIST_WORDS * sizeof(uint32_t)));
     FR_CUDA(ix->q_prep.need(static_cast<size_t>(B) * ix->dim * sizeof(float)));
     if (!ix->stats.p) {
         FR_CUDA(ix->stats.need(64));
@@ -490,6 +494,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     pa.bound_scale = static_cast<float>(ix->mma_bound_scale_pct) / 100.0f;
     pa.tau_g = static_cast<uint32_t *>(ix->tau.p);
     pa.ksel = (ix->mma_debug & 128) ? 0 : ksel;  // diagnostics: 128 = the threshold slots keep the previous search's values
+    pa.hist = use_hist ? static_cast<uint32_t *>(ix->hist.p) : nullptr;
     pa.counters = counters;
     pa.n_counters = 2;
     pa.normalize = ix->metric == FR_COSINE;
@@ -529,6 +534,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
         ms.max_lead = ix->mma_max_lead;
     }
     ms.tau_g = static_cast<uint32_t *>(ix->tau.p);
+    ms.hist = pa.hist;
     ms.norm2 = l2 ? static_cast<const float *>(ix->norm2.p) : nullptr;
     ms.stream = s;
     ProfScope prof{ix, s};
@@ -644,6 +650,7 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
             rs.partials = static_cast<uint64_t *>(ix->r_partials.p);
             rs.plan = rplan;
             rs.tau_g = rp.tau_g_retry + static_cast<size_t>(sl) * ksel_r * R;
+            rs.hist = nullptr;
             rs.nq_dev = retry_n + sl;
             rs.tau0 = tau0 + static_cast<size_t>(sl) * R;
             FR_CUDA(fr::launch_scan_mma(rs));
@@ -1014,6 +1021,10 @@ int fr_index_set_option(fr_index *ix, const char *name, int64_t value) {
     }
     if (std::strcmp(name, "mma_debug") == 0) {
         ix->mma_debug = static_cast<int>(value);
+        return FR_OK;
+    }
+    if (std::strcmp(name, "mma_score_hist") == 0) {
+        ix->mma_score_hist = value != 0;
         return FR_OK;
     }
     if (std::strcmp(name, "profile") == 0) {

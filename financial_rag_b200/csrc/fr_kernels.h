@@ -47,6 +47,8 @@ struct MmaPlan {
 };
 MmaPlan scan_mma_plan(int sm_count, int64_t n_rows, int nq_total, int co_max);
 
+// K2s score histogram of one query: 16 coarse counters (scores in [c/16, (c+1)/16)) followed by 256 fine ones
+constexpr int SCORE_HIST_WORDS = 16 + 256;
 struct MmaScanArgs {
     const void *corpus;         // [rows][dim] bf16
     int dim;                    // 384 for K2; K2s takes any multiple of 64 up to 1024
@@ -69,6 +71,8 @@ struct MmaScanArgs {
     const float *norm2;         // K2s, l2 collections: |c|^2 per row (selection on 2 q.c - |c|^2); null otherwise
     uint32_t *tau_g;            // ksel * nq_total shared threshold slots (order_bits of a score), zeroed before the launches;
                                 // K2 lays them out [ksel][nq_total], K2s [nq_total][ksel]
+    uint32_t *hist;             // K2s, cosine collections, optional: [nq_total][SCORE_HIST_WORDS] score histogram shared by
+                                // the CTAs (scan_mma_small.cu), zeroed before the launch
     cudaStream_t stream;
 };
 int scan_mma_ksel(int k, int wide = 1);  // candidates kept per query (0 = k not served by the tensor-core path); wide: 256 for k > 64
@@ -85,6 +89,7 @@ struct PrepArgs {
     int split;
     uint32_t *tau_g;    // nq * ksel threshold slots, zeroed here
     int ksel;
+    uint32_t *hist;     // optional: nq * SCORE_HIST_WORDS histogram counters, zeroed here
     float bound_scale;  // >= 1: inflates the error bounds (diagnostics: forces second-chance passes; never unsafe)
     int *counters;      // n_counters ints zeroed here (failure counters of the call)
     int n_counters;

@@ -518,7 +518,7 @@ __global__ void prep_queries_kernel(const float *__restrict__ raw, int nq, int n
                                     __nv_bfloat16 *__restrict__ qb, float *__restrict__ err_bound,
                                     float *__restrict__ err_bound_split, float *__restrict__ err_alpha,
                                     float *__restrict__ err_alpha_split, int split, uint32_t *__restrict__ tau_g, int ksel,
-                                    int *__restrict__ counters, int n_counters, float bound_scale, int normalize,
+                                    uint32_t *__restrict__ hist, int *__restrict__ counters, int n_counters, float bound_scale, int normalize,
                                     const float *__restrict__ cmax, float *__restrict__ inv_scale,
                                     float *__restrict__ qnorm2) {
     const int row = blockIdx.x;
@@ -526,6 +526,8 @@ __global__ void prep_queries_kernel(const float *__restrict__ raw, int nq, int n
     if (row == 0 && lane < n_counters) counters[lane] = 0;
     if (row < nq)
         for (int j = lane; j < ksel; j += 32) tau_g[static_cast<size_t>(row) * ksel + j] = 0u;
+    if (row < nq && hist != nullptr)
+        for (int j = lane; j < SCORE_HIST_WORDS; j += 32) hist[static_cast<size_t>(row) * SCORE_HIST_WORDS + j] = 0u;
     const int c4 = dim >> 2;
     // split: the row holds bf16(q) in columns [0, dim) and bf16(q - bf16(q)) in [dim, 2 dim)
     uint2 *dst = reinterpret_cast<uint2 *>(qb + static_cast<size_t>(row) * dim * (1 + split));
@@ -904,7 +906,7 @@ cudaError_t launch_prep_queries(const PrepArgs &a) {
     if (a.dim % 4 != 0 || a.n_counters > 32) return cudaErrorInvalidValue;
     mma::prep_queries_kernel<<<a.nq_pad, 32, 0, a.stream>>>(a.raw, a.nq, a.nq_pad, a.dim, a.q_prep,
                                                            static_cast<__nv_bfloat16 *>(a.qb), a.err_bound, a.err_bound_split,
-                                                           a.err_alpha, a.err_alpha_split, a.split, a.tau_g, a.ksel,
+                                                           a.err_alpha, a.err_alpha_split, a.split, a.tau_g, a.ksel, a.hist,
                                                            a.counters, a.n_counters, a.bound_scale >= 1.0f ? a.bound_scale : 1.0f,
                                                            a.normalize ? 1 : 0, a.cmax, a.inv_scale, a.qnorm2);
     count_launch();

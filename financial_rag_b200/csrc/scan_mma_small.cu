@@ -19,6 +19,13 @@
 //     (one bitonic sort per query) instead of 32 x NQ single inserts.  No score ever goes to HBM;
 //   * thresholds are shared between CTAs through tau_g slots as in K2 (slot = stream % k'), laid out
 //     [query][slot] so a warp refreshes a query with one coalesced read and a warp-min;
+//   * cosine collections: the CTAs also share a score HISTOGRAM per query (hist_g: 16 coarse + 256 fine counters over
+//     [0, 1)): every row that passes a gate is counted, and the edge of the highest bin with k' rows at or above it is
+//     a score that k' distinct rows reach -- as valid a threshold as the slots' minimum and several times tighter (the
+//     slots give the minimum over ~k' CTA maxima, ~5.4/n of a CTA's n rows pass; the true k'-th best of all P n rows
+//     lets 0.87/n pass).  With the slots alone 64 queries x top-50 ran 0.28 ms over the 1.10 ms corpus read at 10M
+//     rows; started from the final thresholds of an identical search the same launch runs at the read
+//     (profiles/r02_k2s_wide_lists_10m.jsonl);
 //   * at the end the four warps' lists of each query are merged and written to `partials` in K2's format, so
 //     everything downstream (K3 merge, exact rescoring + certification, second chance, stream re-scan) is shared.
 // Roofline: HBM.  Algorithmic bytes per launch = rows * 768.
@@ -97,6 +104,15 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *r) {
         : "r"(taddr));
 }
 
+// one row of score `v` into a query's histogram (see the kernel): scores below 1/16 are not counted -- their bins' edges are
+// too low to ever matter and the first tile of every CTA would hammer the same few counters
+__device__ __forceinline__ void hist_count(uint32_t *hq, float v) {
+    const int bin = min(255, static_cast<int>(v * 256.0f));  // v >= bin / 256 exactly (a power-of-two scale, truncation)
+    if (bin < 16) return;
+    atomicAdd(hq + 16 + bin, 1u);
+    atomicAdd(hq + (bin >> 4), 1u);
+}
+
 // grid = P CTAs (P = partial lists per query); CTA p takes corpus tiles p, p + P, ... of 128 rows.
 // partials: [P][nq_total][ksel].
 // SPLIT: the queries are read as TWO bf16 terms, q ~ hi + lo with lo = bf16(q - bf16(q)): the operand holds the NQ
@@ -107,7 +123,8 @@ __global__ void __launch_bounds__(64 + 32 * small_epilogue_warps(NQ), 1)
 scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                       const int64_t *__restrict__ keys_or_null, int64_t n_rows, int nq, int ksel,
                       uint64_t *__restrict__ partials, int nq_total, uint32_t *__restrict__ tau_g, int k_chunks,
-                      int q0, const int *__restrict__ nq_dev, const float *__restrict__ norm2, int dbg) {
+                      int q0, const int *__restrict__ nq_dev, const float *__restrict__ norm2, int dbg,
+                      uint32_t *__restrict__ hist_g) {
     // dbg (option "mma_debug", diagnostics: results are wrong): 2 = the gate runs but no row ever enters a list, 64 = no
     // threshold refresh from the other CTAs
     // norm2 (l2 collections): |c|^2 of every row.  The squared distance |q - c|^2 = |q|^2 - 2 q.c + |c|^2 is smallest where
@@ -280,9 +297,24 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         // profiles/r02_k2s_wide_lists_10m.jsonl.)
         uint32_t *my_slots = tau_g + static_cast<size_t>(q0 + qbase) * ksel + (cta % ksel);  // + q * ksel
         const int n_own = ncta >= ksel ? 1 : min(32, (ksel - cta + ncta - 1) / ncta);
+        // histogram refresh: a half-warp per query, two queries per pass; cb_prev keeps, 4 bits per pass, the coarse bin
+        // this half-warp's query had its threshold in at the last refresh (its fine counters are fetched speculatively)
+        const int half = lane >> 4, hl = lane & 15;
+        uint64_t cb_prev = 0ull;
+        // The FIRST tile is not inserted at once (hist_g only): with empty lists and no threshold every one of its
+        // 32 x NQH scores would go through a sort + fold per query and warp -- 50 us per CTA at 64 queries, and again for
+        // the second tile, whose thresholds come from one tile's worth of rows.  Instead the tile is parked in the stash,
+        // a quarter of its rows are counted into the histogram, and it is replayed in front of the second tile, after a
+        // refresh that by then sees the first tiles of all the CTAs: a handful of rows pass instead of all.
+        constexpr uint32_t FIRST_SAMPLE = 0x11111111u;  // lanes whose rows are counted when the first tile is parked
+        const bool defer_first = hist_g != nullptr;
+        bool deferred = false;
+        uint32_t deferred_row0 = 0u;
         uint32_t it = 0;
-        uint32_t next_refresh = 0;
-        for (int64_t t = cta; t < num_tiles; t += ncta, ++it) {
+        uint32_t next_refresh = defer_first ? 1u : 0u;  // (nothing to read before anybody has counted anything)
+        for (int64_t t = cta;; t += ncta, ++it) {
+            const bool have_tile = t < num_tiles;
+            if (!have_tile && !deferred) break;  // (one extra turn replays a parked tile that had no successor)
             const uint32_t buf = it % S_TMEM_BUFS;
             const uint32_t bphase = (it / S_TMEM_BUFS) & 1;
             // refresh from the other CTAs.  tau_g is laid out [query][k' slots] here, so the k' slots of a query
@@ -291,8 +323,10 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             // (Tried: a seventh warp polling the slots every 1.5 us and handing the thresholds over through shared
             // memory -- 5-8 % slower at every batch size: the polling traffic costs more than the refresh.)
             // (schedule as in K2: every tile at first, then geometrically thinning out to every 64th tile)
-            const bool refresh_now = it >= next_refresh && !(dbg & 64);
+            const bool refresh_now = have_tile && it >= next_refresh && !(dbg & 64);
             if (refresh_now) next_refresh = it + 1u + min(it >> 1, 63u);
+            // the refresh in front of the replay first waits for this tile's scores: time for the other CTAs' counts to land
+            if (refresh_now && deferred) mbar_wait(bar_tfull + 8 * buf, bphase);
             if (refresh_now) {
                 uint32_t x[NQH];
 #pragma unroll
@@ -316,38 +350,126 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                         if (m != 0u) tau[q] = fmaxf(tau[q], unorder_bits(m));
                     }
                 }
+                if (hist_g != nullptr) {
+                    // Per query: the 16 coarse counters give the coarse bin the k'-th best counted row lies in, that bin's 16
+                    // fine counters the fine bin; its lower edge is the threshold.  The fine counters are fetched along
+                    // with the coarse ones for the bin of the last refresh (one round trip); only when a query has
+                    // moved to another coarse bin is there a second round.  Counters only grow and each counts distinct
+                    // rows already scanned, so a stale or half-updated view only loosens the threshold.
+#pragma unroll 1
+                    for (int round = 0; round < 2; ++round) {
+                        uint32_t cs[NQH / 2], cf[NQH / 2];
+#pragma unroll
+                        for (int p = 0; p < NQH / 2; ++p) {
+                            cs[p] = 0u;
+                            cf[p] = 0u;
+                            if (2 * p + half < nqw) {
+                                const uint32_t *hp = hist_g + static_cast<size_t>(q0 + qbase + 2 * p + half) * SCORE_HIST_WORDS;
+                                const int cbp = static_cast<int>(cb_prev >> (4 * p)) & 15;
+                                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(cs[p]) : "l"(hp + hl));
+                                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(cf[p]) : "l"(hp + 16 + 16 * cbp + hl));
+                            }
+                        }
+                        bool moved = false;
+#pragma unroll
+                        for (int p = 0; p < NQH / 2; ++p) {
+                            uint32_t sc = cs[p], sf = cf[p];  // -> rows counted in the coarse / fine bins >= hl
+#pragma unroll
+                            for (int d = 1; d < 16; d <<= 1) {
+                                const uint32_t oc = __shfl_down_sync(FULL_MASK, sc, d, 16);
+                                const uint32_t of = __shfl_down_sync(FULL_MASK, sf, d, 16);
+                                if (hl + d < 16) {
+                                    sc += oc;
+                                    sf += of;
+                                }
+                            }
+                            const unsigned bc = (__ballot_sync(FULL_MASK, sc >= static_cast<uint32_t>(ksel)) >> (16 * half)) & 0xffffu;
+                            const int cb = bc != 0u ? 31 - __clz(bc) : -1;  // -1: fewer than k' rows counted so far
+                            const uint32_t nxt = __shfl_sync(FULL_MASK, sc, (half << 4) | ((cb + 1) & 15));
+                            const uint32_t above = (cb >= 0 && cb < 15) ? nxt : 0u;  // rows in the coarse bins above cb
+                            const int cbp = static_cast<int>(cb_prev >> (4 * p)) & 15;
+                            const bool same = cb == cbp;
+                            const unsigned bf = (__ballot_sync(FULL_MASK, same && above + sf >= static_cast<uint32_t>(ksel)) >> (16 * half)) & 0xffffu;
+                            // (no fine bin reaches k': the fine counters lag the coarse one, or belong to another bin --
+                            //  the coarse edge still holds)
+                            const int bin = cb < 0 ? 0 : 16 * cb + (bf != 0u ? 31 - __clz(bf) : 0);
+                            if (cb >= 0 && !same) {
+                                cb_prev = (cb_prev & ~(15ull << (4 * p))) | (static_cast<uint64_t>(cb) << (4 * p));
+                                moved = true;
+                            }
+                            const float edge = bin > 0 ? static_cast<float>(bin) * (1.0f / 256.0f) : -INFINITY;
+                            const float e0 = __shfl_sync(FULL_MASK, edge, 0), e1 = __shfl_sync(FULL_MASK, edge, 16);
+                            if (2 * p < nqw) tau[2 * p] = fmaxf(tau[2 * p], e0);
+                            if (2 * p + 1 < nqw) tau[2 * p + 1] = fmaxf(tau[2 * p + 1], e1);
+                        }
+                        if (!__any_sync(FULL_MASK, moved)) break;
+                    }
+                }
             }
             float cn = 0.0f;  // l2: this thread's row norm, requested before the accumulator wait hides its latency
-            if (norm2 != nullptr) {
+            if (norm2 != nullptr && have_tile) {
                 const int64_t nrow = t * TILE_ROWS_CTA + quarter * 32 + lane;
                 if (nrow < n_rows) cn = __ldg(norm2 + nrow);
             }
-            mbar_wait(bar_tfull + 8 * buf, bphase);
-            tc_fence_after();
-            uint32_t r[NQH * (1 + SPLIT)];  // this warp's queries: hi columns [qbase, +NQH), lo columns NQ further on
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * S_ACC_STRIDE + qbase;
-#pragma unroll
-            for (int c = 0; c < NQH / 16; ++c) tmem_ld16_nowait(taddr + c * 16, r + c * 16);
-            if (SPLIT) {
-#pragma unroll
-                for (int c = 0; c < NQH / 16; ++c) tmem_ld16_nowait(taddr + NQ + c * 16, r + NQH + c * 16);
+            if (have_tile) {
+                mbar_wait(bar_tfull + 8 * buf, bphase);
+                tc_fence_after();
             }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            // the scores are in registers: hand the accumulator back before looking at them
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+            // pass 0 replays the parked first tile (scores from the stash), pass 1 takes this tile's from the accumulator
+#pragma unroll 1
+            for (int pass = deferred ? 0 : 1; pass < (have_tile ? 2 : 1); ++pass) {
             float v[NQH];
+            uint32_t row0;
+            uint32_t count_lanes;  // lanes whose passing rows are still to be counted into the histogram
+            if (pass == 0) {
 #pragma unroll
-            for (int q = 0; q < NQH; ++q) v[q] = SPLIT ? __uint_as_float(r[q]) + __uint_as_float(r[NQH + q]) : __uint_as_float(r[q]);
-            if (norm2 != nullptr) {  // warp-uniform
+                for (int q = 0; q < NQH; ++q) v[q] = my_stash[q * 32 + lane];
+                __syncwarp();
+                row0 = deferred_row0;
+                count_lanes = ~FIRST_SAMPLE;
+                deferred = false;
+            } else {
+                uint32_t r[NQH * (1 + SPLIT)];  // this warp's queries: hi columns [qbase, +NQH), lo columns NQ further on
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * S_ACC_STRIDE + qbase;
 #pragma unroll
-                for (int q = 0; q < NQH; ++q) v[q] = fmaf(2.0f, v[q], -cn);
+                for (int c = 0; c < NQH / 16; ++c) tmem_ld16_nowait(taddr + c * 16, r + c * 16);
+                if (SPLIT) {
+#pragma unroll
+                    for (int c = 0; c < NQH / 16; ++c) tmem_ld16_nowait(taddr + NQ + c * 16, r + NQH + c * 16);
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // the scores are in registers: hand the accumulator back before looking at them
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+#pragma unroll
+                for (int q = 0; q < NQH; ++q) v[q] = SPLIT ? __uint_as_float(r[q]) + __uint_as_float(r[NQH + q]) : __uint_as_float(r[q]);
+                if (norm2 != nullptr) {  // warp-uniform
+#pragma unroll
+                    for (int q = 0; q < NQH; ++q) v[q] = fmaf(2.0f, v[q], -cn);
+                }
+                row0 = static_cast<uint32_t>(t * TILE_ROWS_CTA);
+                count_lanes = 0xffffffffu;
             }
-            if (it == 0u && LMODE != LM_SHARED) {
+            if (it == 0u && pass == 1 && defer_first) {
+                // park the first tile: scores to the stash, a quarter of the rows into the histogram
+                const uint32_t row = row0 + quarter * 32 + lane;
+                bool valid = row < n_rows;
+                if (valid && keys_or_null != nullptr) valid = keys_or_null[row] != KEY_TOMBSTONE;
+#pragma unroll
+                for (int q = 0; q < NQH; ++q) my_stash[q * 32 + lane] = v[q];
+                if (valid && ((FIRST_SAMPLE >> lane) & 1u))
+                    for (int q = 0; q < nqw; ++q)
+                        hist_count(hist_g + static_cast<size_t>(q0 + qbase + q) * SCORE_HIST_WORDS, my_stash[q * 32 + lane]);
+                __syncwarp();
+                deferred = true;
+                deferred_row0 = row0;
+                continue;
+            }
+            if (it == 0u && LMODE != LM_SHARED && !defer_first) {
                 // first tile of this warp: every list is empty and every row would pass one by one (32 x NQ sorted
                 // inserts).  Load the lists in bulk instead: per query one 32-key bitonic sort of the tile's scores.
-                const uint32_t row = static_cast<uint32_t>(t * TILE_ROWS_CTA) + quarter * 32 + lane;
+                const uint32_t row = row0 + quarter * 32 + lane;
                 bool valid = row < n_rows;
                 if (valid && keys_or_null != nullptr) valid = keys_or_null[row] != KEY_TOMBSTONE;
 #pragma unroll
@@ -396,7 +518,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             if (!__any_sync(FULL_MASK, mall > 0.0f) || (dbg & 2)) continue;  // the common case
             // ---- candidate path (one copy of the insert code whatever NQ: the queries with a passing row are
             //      walked with a run-time index, so the scores of the groups that hold one go through shared memory) ----
-            const uint32_t row = static_cast<uint32_t>(t * TILE_ROWS_CTA) + quarter * 32 + lane;
+            const uint32_t row = row0 + quarter * 32 + lane;
             bool valid = row < n_rows;  // rows past the end arrive as zeros from TMA
             if (valid && keys_or_null != nullptr) valid = keys_or_null[row] != KEY_TOMBSTONE;
             static_assert(NQH <= 32, "one mask word per epilogue warp");
@@ -412,6 +534,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 }
             }
             __syncwarp();
+            const bool count_me = hist_g != nullptr && ((count_lanes >> lane) & 1u) != 0u;
 #pragma unroll
             for (int h = 0; h < 1; ++h) {
                 uint32_t qm = __reduce_or_sync(FULL_MASK, pm[h]);  // queries with at least one passing row
@@ -425,6 +548,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     qm &= qm - 1;
                     const int q = h * 32 + qb;
                     const bool has = ((pm[h] >> qb) & 1u) != 0u;
+                    if (count_me && has) hist_count(hist_g + static_cast<size_t>(q0 + qbase + q) * SCORE_HIST_WORDS, my_stash[q * 32 + lane]);
                     unsigned mask = __ballot_sync(FULL_MASK, has);
                     uint64_t *lp = my_lists + q * CAP;
                     if (LMODE == LM_SHARED) {  // the other lane quarters' warps fold into the same list
@@ -438,8 +562,8 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
                     for (int j = 0; j < KPL; ++j) lst.e[j] = LMODE == LM_SHARED ? *(volatile uint64_t *)(lp + j * 32 + lane) : lp[j * 32 + lane];
                     const uint64_t mine = pack_key(my_stash[q * 32 + lane], row);
-                    if (LMODE == LM_SHARED && __popc(mask) > 3) {
-                        // many rows at once (the first tiles, before the thresholds bite): one sort + one fold network
+                    if (__popc(mask) > 3) {
+                        // many rows at once (before the thresholds bite): one sort + one fold network
                         const uint64_t p = bitonic_sort32_desc(has ? mine : 0ull, lane);
                         fold_sorted32<KPL>(lst.e, p, lane);
                     } else {
@@ -475,6 +599,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 }
             }
             __syncwarp();
+            }  // pass
         }
         // ---- merge the four warps' lists of each query, write the CTA's partial lists ----
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");  // epilogue warps only
@@ -523,7 +648,7 @@ cudaError_t launch_small(const MmaScanArgs &a, const CUtensorMap &tq, const CUte
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.alloc));
     if (e != cudaSuccess) return e;
     kern<<<a.plan.lists, mma::SmallPlan<NQ, KPL, SPLIT>::THREADS, plan.alloc, a.stream>>>(tq, tc, a.keys_or_null, a.n_rows, nq, a.ksel, a.partials,
-                                                                a.nq_total, a.tau_g, k_chunks, q0, a.nq_dev, a.norm2, a.dbg);
+                                                                a.nq_total, a.tau_g, k_chunks, q0, a.nq_dev, a.norm2, a.dbg, a.hist);
     count_launch();
     return cudaGetLastError();
     }

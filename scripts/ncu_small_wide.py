@@ -16,10 +16,12 @@ for c in range((n + 499_999) // 500_000):
     ix.append_device(torch.randn((rows, 384), generator=g, device=dev), None, first_key=c * 500_000)
 ix.set_path("mma")
 one = os.environ.get("FR_ONE")
-cases = [tuple(int(x) for x in one.split(","))] if one else [(64, 10, 0), (64, 32, 0), (64, 50, 0), (64, 50, 2), (64, 50, 128), (64, 10, 2), (32, 50, 128), (32, 100, 128), (32, 50, 0),
-                                                              (32, 50, 2), (16, 50, 0), (1, 50, 0), (32, 100, 0), (32, 100, 2), (16, 100, 0)]
-for b, k, *rest in cases:
-    dbg = rest[0] if rest else 0
+cases = [tuple(int(x) for x in one.split(","))] if one else [(64, 10, 0), (64, 32, 0), (64, 50, 0), (64, 50, 2), (32, 50, 0), (16, 50, 0), (16, 10, 0),
+                                                              (1, 10, 0), (1, 50, 0), (32, 100, 0), (16, 100, 0)]
+hists = [int(x) for x in os.environ.get("FR_HIST", "1,0").split(",")]   # 0: threshold slots only, first tile inserted at once
+for b, k, *rest in [c + (h,) if len(c) == 3 else c + (0, h) for c in cases for h in hists]:
+    dbg, hist = rest[0], rest[1]
+    ix.set_option("mma_score_hist", hist)
     ix.set_option("mma_debug", dbg)   # 2: gate only, nothing enters a list; 64: no threshold refresh (results wrong either way); 128: threshold slots start
     # from the previous (identical) search's final values -- what near-perfect sharing from the first tile would give
     q = torch.randn((b, 384), generator=g, device=dev)
@@ -38,5 +40,5 @@ for b, k, *rest in cases:
     e1.record(); torch.cuda.synchronize()
     ix.set_profile(False)
     ms, launches, searches = ix.profile_read()
-    print(json.dumps({"rows": n, "batch": b, "k": k, "dbg": dbg, "search_ms": round(e0.elapsed_time(e1) / 30, 4),
+    print(json.dumps({"hist": hist, "rows": n, "batch": b, "k": k, "dbg": dbg, "search_ms": round(e0.elapsed_time(e1) / 30, 4),
                       "scan_launch_ms": round(ms / max(launches, 1), 4), "hbm_floor_ms": round(n * 768 / 6547.2e6, 4)}), flush=True)
