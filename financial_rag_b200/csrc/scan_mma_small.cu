@@ -75,7 +75,7 @@ struct SmallPlan {
     static constexpr int THREADS = 64 + 32 * EW;
     static constexpr size_t LIST_ELEMS = LMODE == LM_SHARED ? size_t(NQ) * CAP          // [NQ][CAP] per CTA
                                                             : size_t(EW) * NQH * CAP;   // [EW warps][NQH][CAP] per CTA
-    static constexpr size_t LIST_BYTES = LIST_ELEMS * 8 + (LMODE == LM_SHARED ? size_t(NQ) * 4 : 0);
+    static constexpr size_t LIST_BYTES = LIST_ELEMS * 8 + size_t(NQ) * 4 * 2;   // + a spin lock and a shared threshold per query
     static constexpr size_t STASH_BYTES = size_t(EW) * NQH * 32 * 4;             // [EW warps][NQH][32 rows] fp32
     static_assert(Q_CHUNK % 1024 == 0, "query chunks must keep the 1024-byte swizzle alignment");
     size_t q_bytes, ring_off, list_off, stash_off, bar_off, alloc;
@@ -152,6 +152,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     static_assert(LMODE != LM_NONE, "this instance is not built");
     uint64_t *lists = reinterpret_cast<uint64_t *>(smem + plan.list_off);
     int *locks = reinterpret_cast<int *>(lists + Plan::LIST_ELEMS);  // LM_SHARED only: one spin lock per query
+    float *tau_s = reinterpret_cast<float *>(locks + NQ);            // thresholds as of the last refresh, shared by a group's warps
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + plan.bar_off);
     // barrier slots: full[8] | empty[8] | tmem_full[4] | tmem_empty[4] | q_full | tmem_ptr
     const uint32_t bar_full = smem_u32(bars);
@@ -186,8 +187,10 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     }
     if (warp >= 2) {
         for (int i = threadIdx.x - 64; i < static_cast<int>(Plan::LIST_ELEMS); i += 32 * EW) lists[i] = 0ull;
-        if (LMODE == LM_SHARED)
-            for (int i = threadIdx.x - 64; i < NQ; i += 32 * EW) locks[i] = 0;
+        for (int i = threadIdx.x - 64; i < NQ; i += 32 * EW) {
+            locks[i] = 0;
+            tau_s[i] = -INFINITY;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -300,7 +303,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         // histogram refresh: a half-warp per query, two queries per pass; cb_prev keeps, 4 bits per pass, the coarse bin
         // this half-warp's query had its threshold in at the last refresh (its fine counters are fetched speculatively)
         const int half = lane >> 4, hl = lane & 15;
-        uint64_t cb_prev = 0ull;
+        uint32_t cb_prev = 0u;
         // The FIRST tile is not inserted at once (hist_g only): with empty lists and no threshold every one of its
         // 32 x NQH scores would go through a sort + fold per query and warp -- 50 us per CTA at 64 queries, and again for
         // the second tile, whose thresholds come from one tile's worth of rows.  Instead the tile is parked in the stash,
@@ -328,43 +331,50 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             // the refresh in front of the replay first waits for this tile's scores: time for the other CTAs' counts to land
             if (refresh_now && deferred) mbar_wait(bar_tfull + 8 * buf, bphase);
             if (refresh_now) {
-                uint32_t x[NQH];
+                // The four warps of a group (one per lane quarter, same queries) split the work: each refreshes a quarter
+                // of the group's queries and leaves the result in shared memory; after a barrier of the group every warp
+                // picks up all of them.  (Each warp refreshing all its queries took 12 us a time at 64 queries -- five
+                // tile periods, more than the four accumulators buffer.)
+                constexpr int RQ = NQH / 4;
+                const int rq0 = quarter * RQ;  // this warp refreshes the group's queries [rq0, rq0 + RQ)
+                float *tau_sh = tau_s + qbase;
+                uint32_t x[RQ];
 #pragma unroll
-                for (int q = 0; q < NQH; ++q) {
-                    x[q] = 0u;
-                    if (q < nqw) {  // warp-uniform
-                        const uint32_t *sp = tau_g + static_cast<size_t>(q0 + qbase + q) * ksel + lane;
-                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(x[q]) : "l"(sp));
+                for (int i = 0; i < RQ; ++i) {
+                    x[i] = 0u;
+                    if (rq0 + i < nqw) {  // warp-uniform
+                        const uint32_t *sp = tau_g + static_cast<size_t>(q0 + qbase + rq0 + i) * ksel + lane;
+                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(x[i]) : "l"(sp));
 #pragma unroll
                         for (int j = 1; j < KPL; ++j) {  // k' = 32 KPL slots: lane l reads slots l, l + 32, ...
                             uint32_t y;
                             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(y) : "l"(sp + 32 * j));
-                            x[q] = min(x[q], y);
+                            x[i] = min(x[i], y);
                         }
                     }
                 }
+                float nv[RQ];
 #pragma unroll
-                for (int q = 0; q < NQH; ++q) {
-                    if (q < nqw) {
-                        const uint32_t m = __reduce_min_sync(FULL_MASK, x[q]);
-                        if (m != 0u) tau[q] = fmaxf(tau[q], unorder_bits(m));
-                    }
+                for (int i = 0; i < RQ; ++i) {
+                    const uint32_t m = __reduce_min_sync(FULL_MASK, x[i]);
+                    nv[i] = m != 0u ? unorder_bits(m) : -INFINITY;
                 }
                 if (hist_g != nullptr) {
                     // Per query: the 16 coarse counters give the coarse bin the k'-th best counted row lies in, that bin's 16
-                    // fine counters the fine bin; its lower edge is the threshold.  The fine counters are fetched along
-                    // with the coarse ones for the bin of the last refresh (one round trip); only when a query has
-                    // moved to another coarse bin is there a second round.  Counters only grow and each counts distinct
-                    // rows already scanned, so a stale or half-updated view only loosens the threshold.
+                    // fine counters the fine bin; its lower edge is the threshold.  A half-warp per query, two queries per
+                    // pass.  The fine counters are fetched along with the coarse ones for the bin of the last refresh
+                    // (one round trip); only when a query has moved to another coarse bin is there a second round.
+                    // Counters only grow and each counts distinct rows already scanned, so a stale or half-updated
+                    // view only loosens the threshold.
 #pragma unroll 1
                     for (int round = 0; round < 2; ++round) {
-                        uint32_t cs[NQH / 2], cf[NQH / 2];
+                        uint32_t cs[RQ / 2], cf[RQ / 2];
 #pragma unroll
-                        for (int p = 0; p < NQH / 2; ++p) {
+                        for (int p = 0; p < RQ / 2; ++p) {
                             cs[p] = 0u;
                             cf[p] = 0u;
-                            if (2 * p + half < nqw) {
-                                const uint32_t *hp = hist_g + static_cast<size_t>(q0 + qbase + 2 * p + half) * SCORE_HIST_WORDS;
+                            if (rq0 + 2 * p + half < nqw) {
+                                const uint32_t *hp = hist_g + static_cast<size_t>(q0 + qbase + rq0 + 2 * p + half) * SCORE_HIST_WORDS;
                                 const int cbp = static_cast<int>(cb_prev >> (4 * p)) & 15;
                                 asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(cs[p]) : "l"(hp + hl));
                                 asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(cf[p]) : "l"(hp + 16 + 16 * cbp + hl));
@@ -372,7 +382,7 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                         }
                         bool moved = false;
 #pragma unroll
-                        for (int p = 0; p < NQH / 2; ++p) {
+                        for (int p = 0; p < RQ / 2; ++p) {
                             uint32_t sc = cs[p], sf = cf[p];  // -> rows counted in the coarse / fine bins >= hl
 #pragma unroll
                             for (int d = 1; d < 16; d <<= 1) {
@@ -394,17 +404,23 @@ scan_mma_small_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                             //  the coarse edge still holds)
                             const int bin = cb < 0 ? 0 : 16 * cb + (bf != 0u ? 31 - __clz(bf) : 0);
                             if (cb >= 0 && !same) {
-                                cb_prev = (cb_prev & ~(15ull << (4 * p))) | (static_cast<uint64_t>(cb) << (4 * p));
+                                cb_prev = (cb_prev & ~(15u << (4 * p))) | (static_cast<uint32_t>(cb) << (4 * p));
                                 moved = true;
                             }
                             const float edge = bin > 0 ? static_cast<float>(bin) * (1.0f / 256.0f) : -INFINITY;
-                            const float e0 = __shfl_sync(FULL_MASK, edge, 0), e1 = __shfl_sync(FULL_MASK, edge, 16);
-                            if (2 * p < nqw) tau[2 * p] = fmaxf(tau[2 * p], e0);
-                            if (2 * p + 1 < nqw) tau[2 * p + 1] = fmaxf(tau[2 * p + 1], e1);
+                            nv[2 * p] = fmaxf(nv[2 * p], __shfl_sync(FULL_MASK, edge, 0));
+                            nv[2 * p + 1] = fmaxf(nv[2 * p + 1], __shfl_sync(FULL_MASK, edge, 16));
                         }
                         if (!__any_sync(FULL_MASK, moved)) break;
                     }
                 }
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < RQ; ++i) tau_sh[rq0 + i] = fmaxf(tau_sh[rq0 + i], nv[i]);  // (this warp is the only writer)
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + (ew >> 2)) : "memory");  // the group's four warps
+#pragma unroll
+                for (int q = 0; q < NQH; ++q) tau[q] = fmaxf(tau[q], tau_sh[q]);  // (padded queries stay at +inf)
             }
             float cn = 0.0f;  // l2: this thread's row norm, requested before the accumulator wait hides its latency
             if (norm2 != nullptr && have_tile) {
