@@ -11,7 +11,9 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libfrb200.so")
+# FRB200_LIB names another build of the same sources (scripts/build_variant.py: A/B runs of compile-time knobs);
+# it is loaded and checked exactly like the default library
+LIB_PATH = os.environ.get("FRB200_LIB") or os.path.join(_PKG, "libfrb200.so")
 
 FR_COSINE, FR_L2, FR_IP = 0, 1, 2
 FR_BF16, FR_F32 = 0, 1

@@ -56,7 +56,13 @@ constexpr int THREADS = 192;                   // warp 0 TMA, warp 1 MMA + TMEM 
 
 // unsorted pending candidates per query between compactions: 16 beside shared-memory lists, 32 (a full warp sort per
 // compaction, half as many compactions against L2) where the lists live in global memory and shared memory has room
-__host__ __device__ constexpr int pend_slots(int kpl) { return kpl >= 4 ? 32 : 16; }
+#ifndef FR_K2_PEND_K32
+#define FR_K2_PEND_K32 16   // experiment knobs (scripts/build_variant.py): pending slots and ring depth at k' = 32
+#endif
+#ifndef FR_K2_STAGES_K32
+#define FR_K2_STAGES_K32 5
+#endif
+__host__ __device__ constexpr int pend_slots(int kpl) { return kpl >= 4 ? 32 : (kpl == 1 ? FR_K2_PEND_K32 : 16); }
 constexpr int RETRY_MAX = M_TILE;              // uncertified queries that get a second tensor-core pass
 constexpr int RESCORE_MAX_DIM = 1024;          // widest vectors the rescoring kernel stages in shared memory
 
@@ -67,7 +73,7 @@ constexpr int RESCORE_MAX_DIM = 1024;          // widest vectors the rescoring k
 template <int KPL>
 struct SmemPlan {
     static constexpr bool LISTS_IN_SMEM = KPL <= 2;
-    static constexpr int STAGES = (KPL == 1) ? 5 : (KPL == 2 ? 3 : 6);  // KPL 4 and 8: lists are not in smem
+    static constexpr int STAGES = (KPL == 1) ? FR_K2_STAGES_K32 : (KPL == 2 ? 3 : 6);  // KPL 4 and 8: lists are not in smem
     static constexpr int CAP = 32 * KPL;
     static constexpr size_t A_OFF = 0;
     static constexpr size_t B_OFF = A_OFF + size_t(K_CHUNKS) * CHUNK_BYTES;
@@ -114,6 +120,115 @@ __device__ __forceinline__ uint64_t compact_query(uint64_t *list, const uint64_t
     const uint32_t lo = __shfl_sync(FULL_MASK, static_cast<uint32_t>(L[KPL - 1]), 31);
     const uint32_t hi = __shfl_sync(FULL_MASK, static_cast<uint32_t>(L[KPL - 1] >> 32), 31);
     return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// W queries at once: the W sorting networks are independent dependency chains in one basic block, so their shuffles
+// overlap.  One network is ~20 dependent stages of two shuffles each and issues an instruction every fifth cycle or so;
+// in the first tiles of a launch every lane of the warp fills its pending block at the same column, i.e. 32
+// compactions are due at once -- taken one by one they were most of the fixed cost of a launch.
+// kth[w] = the new k'-th key of query tq[w] (0 while the list is not full).
+template <int KPL, int W>
+__device__ __forceinline__ void compact_queries(uint64_t *lists, int cap, const uint64_t *pend_w, const int (&tq)[W],
+                                                const int (&n)[W], int lane, uint64_t (&kth)[W]) {
+    uint64_t p[W];
+    uint64_t L[W][KPL];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        p[w] = (lane < n[w]) ? pend_w[lane * 32 + ((tq[w] + lane) & 31)] : 0ull;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) L[w][j] = lists[static_cast<size_t>(tq[w]) * cap + j * 32 + lane];
+    }
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool keep_max = ((lane & j) == 0) == ((lane & k) == 0);
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const uint64_t y = shfl_xor_u64(p[w], j);
+                p[w] = keep_max ? umax64(p[w], y) : umin64(p[w], y);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+        uint64_t hi[W], lo[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const uint64_t r = reverse32(p[w], lane);
+            hi[w] = umax64(L[w][j], r);
+            lo[w] = umin64(L[w][j], r);
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const bool up = (lane & s) == 0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const uint64_t y = shfl_xor_u64(hi[w], s);
+                hi[w] = up ? umax64(hi[w], y) : umin64(hi[w], y);
+                if (j + 1 < KPL) {
+                    const uint64_t z = shfl_xor_u64(lo[w], s);
+                    lo[w] = up ? umax64(lo[w], z) : umin64(lo[w], z);
+                }
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            L[w][j] = hi[w];
+            p[w] = lo[w];
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        if (n[w] > 0) {  // warp-uniform; a way without pending entries (padding of a partial group) leaves its list alone
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) lists[static_cast<size_t>(tq[w]) * cap + j * 32 + lane] = L[w][j];
+        }
+        const uint32_t lo32 = __shfl_sync(FULL_MASK, static_cast<uint32_t>(L[w][KPL - 1]), 31);
+        const uint32_t hi32 = __shfl_sync(FULL_MASK, static_cast<uint32_t>(L[w][KPL - 1] >> 32), 31);
+        kth[w] = (static_cast<uint64_t>(hi32) << 32) | lo32;
+    }
+}
+
+// how many compactions the epilogue takes at once: bounded by the registers the lists occupy (KPL keys per lane each)
+__host__ __device__ constexpr int compact_ways(int kpl) { return kpl <= 2 ? 4 : 2; }
+
+// a[0..N) -> descending, in registers (a bitonic network with compile-time indices: N/4 log2 N (log2 N + 1) FMNMX pairs)
+template <int N>
+__device__ __forceinline__ void reg_sort_desc(float (&a)[N]) {
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const float hi = fmaxf(a[i], a[l]), lo = fminf(a[i], a[l]);
+                    const bool desc = (i & k) == 0;
+                    a[i] = desc ? hi : lo;
+                    a[l] = desc ? lo : hi;
+                }
+            }
+        }
+    }
+}
+
+// the 32nd largest of 64 values: sort the halves, then the elementwise maxima of one half against the other reversed are
+// the 32 largest of the union, and their minimum is the answer
+__device__ __forceinline__ float reg_select32_of64(const float (&g)[64]) {
+    float a[32], b[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        a[i] = g[i];
+        b[i] = g[32 + i];
+    }
+    reg_sort_desc<32>(a);
+    reg_sort_desc<32>(b);
+    float m = fmaxf(a[0], b[31]);
+#pragma unroll
+    for (int i = 1; i < 32; ++i) m = fminf(m, fmaxf(a[i], b[31 - i]));
+    return m;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -395,6 +510,38 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             if (g != 0u) tau = fmaxf(tau, unorder_bits(g));
             const uint32_t row0 = static_cast<uint32_t>(t * TILE_ROWS);
             const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * ACC_COLS;
+            if constexpr (KPL == 1) {
+                // ---- first tile: a threshold before anything is inserted.  The lists are empty, so every score of the
+                //      tile would pass the gate and go through the pending blocks: ACC_COLS / 16 rounds of 32 compactions
+                //      per warp, most of what a launch costs beyond its rows (profiles/r02_sweep_rows_*).  Instead the lane
+                //      first reads its query's tile once for the maxima of 64 column groups (of 4 columns, 2 for CG = 1):
+                //      the 32nd largest group maximum is reached by 32 DISTINCT rows, so it is a lower bound on the 32nd
+                //      best score of the tile, and only the ~40 scores at or above it (instead of all 256 / 128) are walked.
+                //      Every row has to be live for that (no tombstones, no zero-filled rows past the end), and a
+                //      second-chance pass keeps its fixed threshold. ----
+                if (it == 0 && tau0 == nullptr && keys_or_null == nullptr && !(dbg & (2 | 256)) &&  // dbg & 256: A/B switch, answers unchanged
+                    (t + 1) * TILE_ROWS <= n_rows) {
+                    constexpr int GROUP = ACC_COLS / 64;
+                    float gmax[64];
+#pragma unroll
+                    for (int c = 0; c < ACC_COLS / 64; ++c) {
+                        float v[64];
+                        tmem_ld64(tcol + c * 64, v);
+#pragma unroll
+                        for (int gi = 0; gi < 64 / GROUP; ++gi) {
+                            float m = v[gi * GROUP];
+#pragma unroll
+                            for (int e = 1; e < GROUP; ++e) m = fmaxf(m, v[gi * GROUP + e]);
+                            gmax[c * (64 / GROUP) + gi] = m;
+                        }
+                    }
+                    // the gate is "score > tau": step one ulp below so that the 32 rows AT the bound pass as well
+                    // (+0.0 steps down from -0.0: one step below +0.0 in key order IS -0.0, which compares equal)
+                    float bound = reg_select32_of64(gmax);
+                    bound = bound == 0.0f ? -0.0f : bound;
+                    tau = fmaxf(tau, unorder_bits(order_bits(bound) - 1u));
+                }
+            }
 #pragma unroll 1
             for (int c = 0; c < ACC_COLS / 64; ++c) {
                 if (dbg & 2) break;  // diagnostics: accumulators are never read
@@ -450,20 +597,55 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     unsigned fm = __ballot_sync(FULL_MASK, full);
                     if (fm == 0u) break;
                     __syncwarp();
+                    // Up to WAYS full blocks are folded at once (see compact_queries).  (Tried and dropped: ways that are
+                    // left over taking queries whose block is at least half full -- more folds of less, 390k-row launch
+                    // 0.885 -> 0.939 ms, 12.5M rows +1.2 %; profiles/r02_sweep_rows_fixed_cost_ab.jsonl.)
                     while (fm) {
-                        const int tq = __ffs(fm) - 1;
-                        fm &= fm - 1;
-                        uint64_t *lp = my_lists + static_cast<size_t>(tq) * CAP;
-                        const uint64_t kth = compact_query<KPL>(lp, pend_w, tq, PEND, lane);
-                        if (lane == tq) {
-                            cnt = 0;
-                            tau = fmaxf(tau, key_threshold(kth));
+                        constexpr int WAYS = compact_ways(KPL);
+                        int tqs[WAYS], ns[WAYS];
+                        uint64_t kths[WAYS];
+                        int taken = 0;
+#pragma unroll
+                        for (int w = 0; w < WAYS; ++w) {
+                            const bool on = fm != 0u && !(w > 0 && (dbg & 512));  // dbg & 512: one by one (A/B switch)
+                            tqs[w] = on ? __ffs(fm) - 1 : (w > 0 ? tqs[0] : 0);
+                            ns[w] = on ? PEND : 0;
+                            taken += on ? 1 : 0;
+                            if (on) fm &= fm - 1;
                         }
-                        if (my_ranks > 1 && lane < my_ranks) {  // lane r: entry r of the sorted list (its own store)
-                            const uint64_t e = lp[lane];
-                            if (e != 0ull)
-                                atomicMax(tau_g + static_cast<size_t>(pair + lane * npairs) * nq_total + q_cta0 + quarter * 32 + tq,
-                                          static_cast<uint32_t>(e >> 32));
+                        if (taken == 1) {
+                            kths[0] = compact_query<KPL>(my_lists + static_cast<size_t>(tqs[0]) * CAP, pend_w, tqs[0], PEND, lane);
+                        } else if (WAYS > 2 && taken <= 2) {
+                            const int tq2[2] = {tqs[0], tqs[1]}, n2[2] = {ns[0], ns[1]};
+                            uint64_t k2[2];
+                            compact_queries<KPL, 2>(my_lists, CAP, pend_w, tq2, n2, lane, k2);
+                            kths[0] = k2[0];
+                            kths[1] = k2[1];
+                        } else {
+                            // (a way without a query names query tqs[0] with no pending entries: it stores nothing)
+                            compact_queries<KPL, WAYS>(my_lists, CAP, pend_w, tqs, ns, lane, kths);
+                        }
+#pragma unroll
+                        for (int w = 0; w < WAYS; ++w) {
+                            if (w >= taken) break;
+                            const int tq = tqs[w];
+                            if (lane == tq) {
+                                cnt = 0;
+                                tau = fmaxf(tau, key_threshold(kths[w]));
+                            }
+                        }
+                        if (my_ranks > 1) {  // lane r: entry r of the sorted list (its own store)
+#pragma unroll
+                            for (int w = 0; w < WAYS; ++w) {
+                                if (w >= taken) break;
+                                const int tq = tqs[w];
+                                if (lane < my_ranks) {
+                                    const uint64_t e = my_lists[static_cast<size_t>(tq) * CAP + lane];
+                                    if (e != 0ull)
+                                        atomicMax(tau_g + static_cast<size_t>(pair + lane * npairs) * nq_total + q_cta0 + quarter * 32 + tq,
+                                                  static_cast<uint32_t>(e >> 32));
+                                }
+                            }
                         }
                     }
                     __syncwarp();
@@ -482,16 +664,30 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         // ---- fold what is still pending, then this CTA's list for each of its queries ----
         __syncwarp();
-        for (int q = 0; q < 32; ++q) {
-            const int qq = quarter * 32 + q;
-            if (qq >= nq_local) break;
-            const int n = __shfl_sync(FULL_MASK, cnt, q);
-            uint64_t *lp = my_lists + static_cast<size_t>(q) * CAP;
-            if (n > 0) compact_query<KPL>(lp, pend_w, q, n, lane);
-            __syncwarp();
-            if constexpr (Plan::LISTS_IN_SMEM) {
-                uint64_t *dst = partials + (static_cast<size_t>(pair) * nq_total + q_cta0 + qq) * ksel;
-                for (int i = lane; i < ksel; i += 32) dst[i] = lp[i];
+        {
+            constexpr int WAYS = compact_ways(KPL);
+            const int q_end = min(32, nq_local - quarter * 32);  // live queries of this warp (<= 0: none)
+            for (int q0 = 0; q0 < q_end; q0 += WAYS) {
+                int tqs[WAYS], ns[WAYS];
+                uint64_t kths[WAYS];
+#pragma unroll
+                for (int w = 0; w < WAYS; ++w) {
+                    const bool on = q0 + w < q_end;
+                    tqs[w] = on ? q0 + w : q0;
+                    const int n = __shfl_sync(FULL_MASK, cnt, tqs[w]);
+                    ns[w] = on ? n : 0;
+                }
+                compact_queries<KPL, WAYS>(my_lists, CAP, pend_w, tqs, ns, lane, kths);
+                __syncwarp();
+                if constexpr (Plan::LISTS_IN_SMEM) {
+#pragma unroll
+                    for (int w = 0; w < WAYS; ++w) {
+                        if (q0 + w >= q_end) break;
+                        const uint64_t *lp = my_lists + static_cast<size_t>(q0 + w) * CAP;
+                        uint64_t *dst = partials + (static_cast<size_t>(pair) * nq_total + q_cta0 + quarter * 32 + q0 + w) * ksel;
+                        for (int i = lane; i < ksel; i += 32) dst[i] = lp[i];
+                    }
+                }
             }
         }
     }

@@ -677,6 +677,57 @@ def test_huge_batch_is_sliced(frb):
     ix.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [100, 130, 600])
+def test_k2_first_tile_threshold_edge_cases(frb, B):
+    """K2 (k' = 32) derives a threshold from the maxima of column groups of the first tile before it inserts
+    anything.  The cases that bound can get wrong: a query whose scores are all exactly zero (one step below
+    +0.0 in key order is -0.0, which compares equal), a first tile of identical rows (every score AT the
+    bound), all-negative scores, corpora that end inside the first tile of a stream, tombstones in the first
+    tile -- and the option that switches the bound off must not change an answer."""
+    k = 10
+    for n in (256 * 40 + 17, 256 * 9, 700):
+        corpus = make_corpus(n, 384, seed=4000 + n)
+        corpus[0:300] = corpus[0]                    # the first tile of stream 0 holds one vector 256 (128) times
+        corpus[300:400, 200:] = 0.0                  # rows orthogonal to query 3: exact zeros in a live query's tile
+        queries = make_queries(B, corpus, seed=B)
+        queries[0] = 0.0                             # every score is +0.0
+        queries[1] = corpus[0]
+        queries[2] = -corpus[0]
+        queries[3] = 0.0
+        queries[3, 200:] = corpus[5, 200:]
+        ix = build_index(frb, corpus, "cosine", "bf16")
+        ix.set_path("stream")
+        d_s, k_s = ix.search(queries, k)
+        ix.set_path("mma")
+        d_m, k_m = ix.search(queries, k)
+        ix.set_option("mma_debug", 256 | 512)        # no first-tile bound, compactions one by one
+        d_p, k_p = ix.search(queries, k)
+        ix.set_option("mma_debug", 0)
+        np.testing.assert_array_equal(k_m, k_p)
+        np.testing.assert_array_equal(d_m, d_p)
+        np.testing.assert_allclose(d_m, d_s, rtol=0, atol=2e-6)
+        for i in (0, 1):                             # exact ties: insertion order decides, ids must be the stream path's
+            np.testing.assert_array_equal(k_m[i], k_s[i])
+        mism = k_m != k_s
+        if mism.any():
+            assert np.abs(d_m[mism] - d_s[mism]).max() <= 2e-6
+        np.testing.assert_array_equal(keys_to_rows(k_m[0], KEY_BASE), np.arange(k))
+        np.testing.assert_array_equal(keys_to_rows(k_m[1], KEY_BASE), np.arange(k))
+        assert_matches_oracle(d_m, keys_to_rows(k_m, KEY_BASE), queries, corpus, k, "cosine", "bf16",
+                              stored=stored_rows(ix), label=f"first tile n={n} B={B}")
+        # tombstones inside every stream's first tile: the bound is not used, answers follow the live rows
+        dead = np.arange(1, 600, 3) if n > 600 else np.arange(1, n, 3)
+        ix.delete((dead + KEY_BASE).astype(np.int64))
+        live = np.ones(n, dtype=bool)
+        live[dead] = False
+        d_d, k_d = ix.search(queries, k)
+        assert not np.isin(keys_to_rows(k_d, KEY_BASE), dead).any()
+        assert_matches_oracle(d_d, keys_to_rows(k_d, KEY_BASE), queries, corpus, k, "cosine", "bf16",
+                              stored=stored_rows(ix), live=live, label=f"first tile with deletes n={n} B={B}")
+        ix.close()
+
+
 def test_mma_certification_fallback_on_mass_ties(frb):
     """More exact duplicates than the k' = 32 selection slots: the tensor-core selection cannot be
     certified, so the query must be re-scanned by the stream kernel and still return the LOWEST
