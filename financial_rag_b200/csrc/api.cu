@@ -22,7 +22,31 @@
 #include "fr_host.h"
 #include "fr_kernels.h"
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 namespace {
+// FRB200_SEGV_TRACE=1: print the native backtrace of a crashing thread (python's faulthandler only sees the ctypes call)
+void segv_trace(int sig) {
+    void *frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "\n[libfrb200] fatal signal, native backtrace:\n";
+    if (write(2, msg, sizeof(msg) - 1) < 0) {}
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+struct SegvTraceInstall {
+    SegvTraceInstall() {
+        const char *e = getenv("FRB200_SEGV_TRACE");
+        if (e && e[0] == '1') {
+            signal(SIGSEGV, segv_trace);
+            signal(SIGBUS, segv_trace);
+            signal(SIGABRT, segv_trace);
+        }
+    }
+} g_segv_trace_install;
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
 std::mutex g_dev_mu;
@@ -39,6 +63,11 @@ int fail(int code, const char *fmt, ...) {
     va_end(ap);
     g_last_error = buf;
     return code;
+}
+
+std::shared_mutex &graph_wait_mutex() {
+    static std::shared_mutex m;
+    return m;
 }
 
 int check_device(int device, int *sm_count) {
@@ -167,6 +196,7 @@ struct fr_index {
     };
     std::unordered_map<uint64_t, SearchGraph> graphs;
     int use_graphs = 1;
+    int host_debug = 0;      // diagnostics (scripts/stress_concurrent.py): 1 = thread-local capture mode, 2 = the shard lock is held through the wait, 4 = graph work and waits may overlap (crashes)
     int64_t graph_max_bytes = int64_t(2) << 30;  // corpora above this are bandwidth-bound: launch gaps do not matter
     int64_t n_graph_replays = 0;
     std::unordered_map<int64_t, int64_t> keymap;  // key -> row (live rows only)
@@ -991,6 +1021,10 @@ int fr_index_set_option(fr_index *ix, const char *name, int64_t value) {
         ix->graph_max_bytes = value;
         return FR_OK;
     }
+    if (std::strcmp(name, "host_debug") == 0) {
+        ix->host_debug = static_cast<int>(value);
+        return FR_OK;
+    }
     if (std::strcmp(name, "small_rows_b1") == 0) {
         ix->small_rows_b1 = value;
         return FR_OK;
@@ -1406,15 +1440,21 @@ int fr_index_search(fr_index *ix, const float *queries, int B, int k, float *out
     const size_t db = static_cast<size_t>(B) * k * sizeof(float);
     const size_t kb = static_cast<size_t>(B) * k * sizeof(int64_t);
     const size_t db_al = (db + 15) & ~static_cast<size_t>(15), kb_al = (kb + 15) & ~static_cast<size_t>(15);
-    // the slot is ours alone and its previous search has been waited for: growing it needs no lock
-    if (!slot.done) FR_CUDA(cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
-    FR_CUDA(slot.pin.need(qb + db_al + kb_al));
+    // The slot is ours alone and its previous search has been waited for, but growing it frees and allocates pinned
+    // memory, which synchronises the device -- while another thread may be capturing this shard's stream into a graph
+    // (relaxed capture mode checks nothing).  So the rare growth and the event's creation take the shard lock, under
+    // which every capture runs; the common case (the block is large enough) takes none.
+    if (!slot.done || slot.pin.bytes < qb + db_al + kb_al) {
+        std::lock_guard<std::mutex> lk(ix->mu);
+        if (!slot.done) FR_CUDA(cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
+        FR_CUDA(slot.pin.need(qb + db_al + kb_al));
+    }
     uint8_t *pin = static_cast<uint8_t *>(slot.pin.p);
     // every block 16-byte aligned: the kernels may read the queries as float4 straight from the pinned block
     uint8_t *pin_keys = pin, *pin_dist = pin + kb_al, *pin_q = pin + kb_al + db_al;
     std::memcpy(pin_q, queries, qb);
     {
-    std::lock_guard<std::mutex> lk(ix->mu);
+    std::unique_lock<std::mutex> lk(ix->mu);
     FR_CUDA(ix->q_raw.need(qb));
     FR_CUDA(ix->out_dist.need(db));
     FR_CUDA(ix->out_keys.need(kb));
@@ -1437,8 +1477,11 @@ int fr_index_search(fr_index *ix, const float *queries, int B, int k, float *out
     };
     // Small collections: replay a captured graph of the call (same shape, same staging slot, nothing it baked in
     // changed).  The first call of a shape runs eagerly (it sizes the scratch), the second is captured, later ones replay.
-    const bool graphable = ix->use_graphs && !ix->profile && B <= 8192 &&
-                           static_cast<int64_t>(ix->rows) * static_cast<int64_t>(ix->row_bytes()) <= ix->graph_max_bytes;
+    bool graphable = ix->use_graphs && !ix->profile && B <= 8192 &&
+                     static_cast<int64_t>(ix->rows) * static_cast<int64_t>(ix->row_bytes()) <= ix->graph_max_bytes;
+    // graph work only while no other caller waits for its results (fr_host.h: graph_wait_mutex); eager otherwise
+    std::unique_lock<std::shared_mutex> graph_lk(fr::graph_wait_mutex(), std::defer_lock);
+    if (graphable && !(ix->host_debug & 4)) graphable = graph_lk.try_lock();
     fr_index::SearchGraph *sg = nullptr;
     auto hash_now = [&]() {  // what a graph bakes in: the shard's state and this slot's pinned block
         uint64_t h = state_hash(ix);
@@ -1459,7 +1502,7 @@ int fr_index_search(fr_index *ix, const float *queries, int B, int k, float *out
         if (!sg->exec && !sg->failed && sg->seen == h) {  // second stable call of this shape: capture it
             const int64_t l0 = fr_launch_count(), s0 = ix->n_searches, q0 = ix->n_queries, m0 = ix->n_mma_queries;
             cudaGraph_t graph = nullptr;
-            bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+            bool ok = cudaStreamBeginCapture(s, (ix->host_debug & 1) ? cudaStreamCaptureModeThreadLocal : cudaStreamCaptureModeRelaxed) == cudaSuccess;
             if (ok) {
                 const int r = enqueue();
                 ok = cudaStreamEndCapture(s, &graph) == cudaSuccess && r == FR_OK && graph != nullptr;
@@ -1502,11 +1545,17 @@ int fr_index_search(fr_index *ix, const float *queries, int B, int k, float *out
         }
         if (sg) sg->seen = hash_now();
     }
+    if (graph_lk.owns_lock()) graph_lk.unlock();
     rc = end_use(ix, s);
     if (rc != FR_OK) return rc;
     FR_CUDA(cudaEventRecord(slot.done, s));
+    if (ix->host_debug & 2) FR_CUDA(cudaEventSynchronize(slot.done));
     }  // the shard is free for the next caller's enqueue; this call waits for its own results only
-    FR_CUDA(cudaEventSynchronize(slot.done));
+    {
+        std::shared_lock<std::shared_mutex> wait_lk(fr::graph_wait_mutex(), std::defer_lock);
+        if (!(ix->host_debug & 4)) wait_lk.lock();
+        FR_CUDA(cudaEventSynchronize(slot.done));
+    }
     std::memcpy(out_dist, pin_dist, db);
     std::memcpy(out_keys, pin_keys, kb);
     return FR_OK;

@@ -805,7 +805,9 @@ int fr_encoder_forward(fr_encoder *e, const int32_t *ids, const int32_t *lens, i
         return h;
     };
     fr_encoder::Graph *gr = nullptr;
-    if (!hidden_or_null && static_cast<int64_t>(M) <= e->m_cap) {  // (the first call of a size runs eagerly: it grows the buffers)
+    // graph work only while no caller of the library waits for results (fr_host.h: graph_wait_mutex); eager otherwise
+    std::unique_lock<std::shared_mutex> graph_lk(fr::graph_wait_mutex(), std::try_to_lock);
+    if (graph_lk.owns_lock() && !hidden_or_null && static_cast<int64_t>(M) <= e->m_cap) {  // (the first call of a size runs eagerly: it grows the buffers)
         if (e->graphs.size() > 64) {
             for (auto &kv : e->graphs)
                 if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -852,7 +854,11 @@ int fr_encoder_forward(fr_encoder *e, const int32_t *ids, const int32_t *lens, i
         if (gr) gr->seen = state();
         if (hidden_or_null) FR_CUDA(cudaMemcpyAsync(hidden_or_null, e->hid.p, M * H * 4, cudaMemcpyDeviceToHost, s));
     }
-    FR_CUDA(cudaStreamSynchronize(s));
+    if (graph_lk.owns_lock()) graph_lk.unlock();
+    {
+        std::shared_lock<std::shared_mutex> wait_lk(fr::graph_wait_mutex());
+        FR_CUDA(cudaStreamSynchronize(s));
+    }
     std::memcpy(out, pin + ib + lb, ob);
     return FR_OK;
 }

@@ -84,20 +84,45 @@ __device__ __forceinline__ uint64_t reverse32(uint64_t x, int lane) {
     return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
+// Sort a BITONIC sequence of 32 KPL keys held striped over a warp (entry i in lane i & 31, slot i >> 5) descending:
+// the strides of 32 and more pair slots of the same lane (plain register compare-exchanges), the strides below 32 are
+// one shuffle stage per slot, and the slots of a stage are independent of each other (their shuffles overlap).
+template <int KPL>
+__device__ __forceinline__ void bitonic_merge_striped_desc(uint64_t (&L)[KPL], int lane) {
+#pragma unroll
+    for (int s = KPL / 2; s > 0; s >>= 1) {
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+            if ((j & s) == 0) {
+                const uint64_t hi = umax64(L[j], L[j + s]), lo = umin64(L[j], L[j + s]);
+                L[j] = hi;
+                L[j + s] = lo;
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const bool up = (lane & s) == 0;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) {
+            const uint64_t y = shfl_xor_u64(L[j], s);
+            L[j] = up ? umax64(L[j], y) : umin64(L[j], y);
+        }
+    }
+}
+
 // Fold 32 keys sorted descending (one per lane, 0 = none) into a sorted list of 32 KPL entries held in registers
-// (entry i in lane i & 31, slot i >> 5): the elementwise max / min of a descending block and the reversed carry are
-// bitonic sequences holding the top / bottom 32 of their union; the bottom half carries on to the next block and what
-// falls off the end is dropped.
+// (entry i in lane i & 31, slot i >> 5), keeping the best 32 KPL of the union.  Pad the block with zeros to the length of
+// the list: the elementwise maxima of the list against the reversed padded block are the best 32 KPL of the union and
+// form a bitonic sequence -- and only the LAST 32 entries meet a key of the block -- so the fold is one reversal, 32
+// maxima and ONE merge network of log2(32 KPL) stages, of which only five shuffle.  (The first version pushed the
+// block down the list 32 entries at a time, a chain of KPL x 11 dependent shuffle stages: 4 us per fold at k' = 256,
+// during which the CTA pair's other seven epilogue warps and the tensor pipe wait for the accumulator to be handed
+// back; profiles/r02_ncu_src_lines_scan_mma_k100_b1024_10m_before.txt.)
 template <int KPL>
 __device__ __forceinline__ void fold_sorted32(uint64_t (&L)[KPL], uint64_t p_sorted, int lane) {
-    uint64_t carry = p_sorted;
-#pragma unroll
-    for (int j = 0; j < KPL; ++j) {
-        const uint64_t r = reverse32(carry, lane);
-        const uint64_t hi = bitonic_merge32_desc(umax64(L[j], r), lane);
-        if (j + 1 < KPL) carry = bitonic_merge32_desc(umin64(L[j], r), lane);
-        L[j] = hi;
-    }
+    L[KPL - 1] = umax64(L[KPL - 1], reverse32(p_sorted, lane));
+    bitonic_merge_striped_desc<KPL>(L, lane);
 }
 
 // A top-K list held by one warp in registers: entry i lives in lane (i & 31), slot (i >> 5).

@@ -5,6 +5,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <shared_mutex>
+
 #include "../../include/fr_index.h"
 
 namespace fr {
@@ -13,6 +15,15 @@ namespace fr {
 int fail(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
 // FR_OK when `device` is an sm_100 device (asks the runtime once per device); optionally its SM count.
 int check_device(int device, int *sm_count);
+
+// CUDA-graph work (stream capture, instantiation, graph launch) and host waits on events of other callers never run at
+// the same time.  Measured on B200 / driver 580 (scripts/stress_concurrent.py): seven threads searching one shard, each
+// holding the shard lock only while it enqueues, crash inside cuGraphLaunch within seconds when one thread replays or
+// captures a search graph while others sit in cudaEventSynchronize on events of the same stream; with the waits
+// serialised, or without graphs, nothing happens.  So graph work takes this lock exclusively -- by try_lock only: when
+// somebody is waiting the call simply runs its kernels eagerly, graphs are a latency optimisation for the lone caller
+// -- and host waits outside an object's own lock take it shared.
+std::shared_mutex &graph_wait_mutex();
 
 // cudaGetDeviceProperties costs milliseconds; the answer never changes, so ask once per device.
 struct DevInfo {

@@ -843,7 +843,10 @@ int fr_group_search(fr_group *g, const float *queries, int B, int k, float *out_
     const size_t qb = static_cast<size_t>(B) * g->dim * sizeof(float);
     const size_t db = static_cast<size_t>(B) * k * sizeof(float), kb = static_cast<size_t>(B) * k * sizeof(int64_t);
     const size_t db_al = (db + 15) & ~static_cast<size_t>(15), kb_al = (kb + 15) & ~static_cast<size_t>(15);
-    {
+    if (!slot.done || slot.pin.bytes < qb + db_al + kb_al) {
+        // rare: growing the block frees and allocates pinned memory (device-wide synchronisation) -- not beside another
+        // caller's enqueue (see fr_index_search)
+        std::lock_guard<std::mutex> lk(g->mu);
         DeviceGuard dg(g->dev[0]);
         if (!slot.done) FR_CUDA(cudaEventCreateWithFlags(&slot.done, cudaEventDisableTiming));
         FR_CUDA(slot.pin.need(qb + db_al + kb_al));
@@ -901,6 +904,7 @@ int fr_group_search(fr_group *g, const float *queries, int B, int k, float *out_
     {
         // stream 0's merge waited for every shard's lists, so every device has also finished READING this slot's queries
         DeviceGuard dg(g->dev[0]);
+        std::shared_lock<std::shared_mutex> wait_lk(fr::graph_wait_mutex());  // not beside another object's graph work
         FR_CUDA(cudaEventSynchronize(slot.done));
     }
     std::memcpy(out_dist, pin_dist, db);

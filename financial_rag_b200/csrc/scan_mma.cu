@@ -150,32 +150,33 @@ __device__ __forceinline__ void compact_queries(uint64_t *lists, int cap, const 
             }
         }
     }
+    // the fold of fold_sorted32 (fr_common.cuh), W lists at a time
 #pragma unroll
-    for (int j = 0; j < KPL; ++j) {
-        uint64_t hi[W], lo[W];
+    for (int w = 0; w < W; ++w) L[w][KPL - 1] = umax64(L[w][KPL - 1], reverse32(p[w], lane));
+#pragma unroll
+    for (int s = KPL / 2; s > 0; s >>= 1) {
 #pragma unroll
         for (int w = 0; w < W; ++w) {
-            const uint64_t r = reverse32(p[w], lane);
-            hi[w] = umax64(L[w][j], r);
-            lo[w] = umin64(L[w][j], r);
-        }
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            const bool up = (lane & s) == 0;
-#pragma unroll
-            for (int w = 0; w < W; ++w) {
-                const uint64_t y = shfl_xor_u64(hi[w], s);
-                hi[w] = up ? umax64(hi[w], y) : umin64(hi[w], y);
-                if (j + 1 < KPL) {
-                    const uint64_t z = shfl_xor_u64(lo[w], s);
-                    lo[w] = up ? umax64(lo[w], z) : umin64(lo[w], z);
+            for (int j = 0; j < KPL; ++j) {
+                if ((j & s) == 0) {
+                    const uint64_t hi = umax64(L[w][j], L[w][j + s]), lo = umin64(L[w][j], L[w][j + s]);
+                    L[w][j] = hi;
+                    L[w][j + s] = lo;
                 }
             }
         }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const bool up = (lane & s) == 0;
 #pragma unroll
         for (int w = 0; w < W; ++w) {
-            L[w][j] = hi[w];
-            p[w] = lo[w];
+#pragma unroll
+            for (int j = 0; j < KPL; ++j) {
+                const uint64_t y = shfl_xor_u64(L[w][j], s);
+                L[w][j] = up ? umax64(L[w][j], y) : umin64(L[w][j], y);
+            }
         }
     }
 #pragma unroll

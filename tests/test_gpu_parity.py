@@ -1121,3 +1121,20 @@ def test_concurrent_host_searches_share_a_shard(frb):
     assert not errors, errors
     assert ix.stat("searches") >= 7 * 26
     ix.close()
+
+
+@pytest.mark.gpu
+def test_concurrent_host_searches_in_a_fresh_process(frb):
+    """The same load in a process of its own (scripts/stress_concurrent.py), one shard and two: there the first graph
+    captures and replays of the process meet other threads' waits -- the combination that crashed inside cuGraphLaunch
+    before graph work and host waits excluded each other (fr_host.h: graph_wait_mutex)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in ({}, {"FR_STRESS_TWO": "1"}):
+        env = dict(os.environ, FRB200_SEGV_TRACE="1", **extra)
+        r = subprocess.run([sys.executable, os.path.join(root, "scripts", "stress_concurrent.py"), "8"], env=env,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (r.returncode, r.stdout[-500:], r.stderr[-1500:])
