@@ -153,7 +153,7 @@ struct fr_index {
     int mma_split_max = 32;  // (measured: free up to 32 queries -- one MMA of N = 2 x 32 per K step; 64 do not fit an accumulator)
     int64_t small_rows_b1 = 2000000, small_rows_b4 = 200000;  // FR_PATH_AUTO: below these sizes batch 1 / batch <= 4 take K1
     int mma_bound_scale_pct = 100;  // diagnostics / tests: certification error bounds x this / 100 (>= 100: stricter, still exact)
-    int mma_score_hist = 1; // K2s: share a score histogram between the CTAs (0 = threshold slots only; for A/B timing)
+    int mma_score_hist = 1; // K2 / K2s: share a score histogram between the CTAs (0 = threshold slots only; for A/B timing)
     int mma_debug = 0;      // diagnostics (scripts/ablate_mma.py): results are wrong when non-zero
     int mma_wide_lists = 1; // k in (64, 100]: keep 256 candidates per query instead of 128
     int mma_max_lead = 6;   // K2 co-resident groups: tiles a group may run ahead of the slowest group of its stream (0 = unthrottled)
@@ -494,8 +494,8 @@ int search_mma(fr_index *ix, const float *d_raw_queries, int B, int k, float *d_
     // 2 counters (+2 pad) | fail_list [B] | fail_list2 [B] | retry_n [slices]
     FR_CUDA(ix->fail.need((4 + 2 * static_cast<size_t>(B) + static_cast<size_t>(slices)) * sizeof(int)));
     FR_CUDA(ix->tau.need(static_cast<size_t>(B) * ksel * sizeof(uint32_t)));
-    // K2s on a cosine collection: the CTAs also share a score histogram per query (scan_mma_small.cu)
-    const bool use_hist = small && ix->metric == FR_COSINE && ix->mma_score_hist != 0;
+    // cosine collections: the CTAs also share a score histogram per query (scan_mma_small.cu, scan_mma.cu)
+    const bool use_hist = ix->metric == FR_COSINE && ix->mma_score_hist != 0;
     if (use_hist) FR_CUDA(ix->hist.need(static_cast<size_t>(B) * fr::SCORE_HIST_WORDS * sizeof(uint32_t)));
     FR_CUDA(ix->q_prep.need(static_cast<size_t>(B) * ix->dim * sizeof(float)));
     if (!ix->stats.p) {
@@ -831,7 +831,7 @@ uint64_t state_hash(const fr_index *ix) {
     };
     const DevBuf *bufs[] = {&ix->q_raw, &ix->q_prep, &ix->q_keys, &ix->partials, &ix->out_dist, &ix->out_keys, &ix->q_bf16,
                             &ix->err_bound, &ix->sel, &ix->sel_keys, &ix->flags, &ix->fail, &ix->fb_partials, &ix->tau,
-                            &ix->progress, &ix->s_lists, &ix->cmax, &ix->norm2, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau, &ix->r_partials, &ix->r_sel,
+                            &ix->progress, &ix->s_lists, &ix->hist, &ix->cmax, &ix->norm2, &ix->stats, &ix->kth_exact, &ix->r_q, &ix->r_misc, &ix->r_tau, &ix->r_partials, &ix->r_sel,
                             &ix->r_sel_keys};
     for (const DevBuf *b : bufs) mix(reinterpret_cast<uintptr_t>(b->p));
     mix(reinterpret_cast<uintptr_t>(ix->fail_mirror));
@@ -844,7 +844,7 @@ uint64_t state_hash(const fr_index *ix) {
     mix(ix->n_deleted > 0 ? 1u : 0u);
     for (int v : {ix->path, ix->mma_min_batch, ix->mma_small_max, ix->mma_co_groups, ix->mma_split, ix->mma_split_max,
                   ix->mma_debug, ix->mma_bound_scale_pct, ix->mma_max_lead, ix->mma_wide_lists, ix->mma_f32_shadow,
-                  ix->retry_blocks_cur})
+                  ix->retry_blocks_cur, ix->mma_score_hist})
         mix(static_cast<uint64_t>(static_cast<int64_t>(v)));
     mix(static_cast<uint64_t>(ix->small_rows_b1));
     mix(static_cast<uint64_t>(ix->small_rows_b4));

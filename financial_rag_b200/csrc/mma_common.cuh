@@ -198,5 +198,15 @@ static bool make_row_major_map(CUtensorMap *map, const void *base, int64_t rows,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// one row of score `v` into a query's histogram (scan_mma_small.cu; K2 counts the rows it appends the same way): scores
+// below 1/16 are not counted -- their bins' edges are too low to ever matter and the first tile of every CTA would
+// hammer the same few counters
+__device__ __forceinline__ void hist_count(uint32_t *hq, float v) {
+    const int bin = min(255, static_cast<int>(v * 256.0f));  // v >= bin / 256 exactly (a power-of-two scale, truncation)
+    if (bin < 16) return;
+    atomicAdd(hq + 16 + bin, 1u);
+    atomicAdd(hq + (bin >> 4), 1u);
+}
+
 }  // namespace mma
 }  // namespace fr

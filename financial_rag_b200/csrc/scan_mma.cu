@@ -246,7 +246,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 const int64_t *__restrict__ keys_or_null, int64_t n_rows, int nq_launch, int q_row0_launch, int ksel,
                 uint64_t *__restrict__ partials, int nq_total, int co, uint32_t *__restrict__ tau_g, int dbg,
                 const int *__restrict__ nq_dev, const float *__restrict__ tau0, uint32_t *__restrict__ progress,
-                int max_lead) {
+                int max_lead, uint32_t *__restrict__ hist_g) {
     using Plan = SmemPlan<KPL>;
     constexpr int STAGES = Plan::STAGES;
     constexpr int CAP = Plan::CAP;
@@ -480,6 +480,9 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         uint32_t *my_slot = tau_g + static_cast<size_t>(pair % ksel) * nq_total + q_cta0 + (live ? my_q : 0);
         // slots this stream owns (tiny corpora with fewer than k'/32 streams leave some slots empty: no sharing)
         const int my_ranks = npairs >= ksel ? 1 : min(32, (ksel - pair + npairs - 1) / npairs);
+        // cosine collections: the score histogram of this lane's query, shared by all CTAs (see the refresh below)
+        uint32_t *hist_q = (hist_g != nullptr && live && !(dbg & 2048))
+                               ? hist_g + static_cast<size_t>(q_cta0 + my_q) * SCORE_HIST_WORDS : nullptr;
         uint32_t best = 0, published = 0;          // order bits of the best score appended / published
         const uint32_t l_tempty = (CG == 2) ? map_to_cta(bar_tempty, 0) : bar_tempty;
         uint32_t it = 0;
@@ -506,9 +509,55 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     g = min(g, x);
                 }
             }
+            // The same refresh reads the query's score histogram (16 coarse + 256 fine counters over [0, 1), filled by
+            // every CTA with the rows it appends): the lower edge of the highest bin with k' counted rows at or above it
+            // is a score k' distinct live rows reach -- as valid a bound as the slots' minimum, and tighter: the slots give
+            // a minimum over per-stream bests, the histogram the k'-th best of everything counted to within a bin.
+            // Counters only grow, so a stale or half-updated view only loosens the bound.  Two dependent round trips
+            // of four 16-byte loads; the fine counters that lag their coarse bin leave the coarse edge.
+            float edge = -INFINITY;
+            if (hist_q != nullptr && refresh_now) {
+                uint32_t cc[16];
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4)
+                    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(cc[4 * v4]), "=r"(cc[4 * v4 + 1]), "=r"(cc[4 * v4 + 2]), "=r"(cc[4 * v4 + 3])
+                                 : "l"(hist_q + 4 * v4));
+                int cb = -1;
+                uint32_t acc = 0u, above = 0u;
+#pragma unroll
+                for (int b = 15; b >= 1; --b) {  // (bin 0 is never counted)
+                    const uint32_t nacc = acc + cc[b];
+                    if (cb < 0 && nacc >= static_cast<uint32_t>(ksel)) {
+                        cb = b;
+                        above = acc;
+                    }
+                    acc = nacc;
+                }
+                if (cb >= 1) {
+                    uint32_t cf[16];
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4)
+                        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(cf[4 * v4]), "=r"(cf[4 * v4 + 1]), "=r"(cf[4 * v4 + 2]), "=r"(cf[4 * v4 + 3])
+                                     : "l"(hist_q + 16 + 16 * cb + 4 * v4));
+                    int fb = 0;
+                    bool found = false;
+#pragma unroll
+                    for (int j = 15; j >= 1; --j) {
+                        above += cf[j];
+                        if (!found && above >= static_cast<uint32_t>(ksel)) {
+                            fb = j;
+                            found = true;
+                        }
+                    }
+                    edge = static_cast<float>(16 * cb + fb) * (1.0f / 256.0f);
+                }
+            }
             mbar_wait(bar_tfull + 8 * buf, bphase);
             tc_fence_after();
             if (g != 0u) tau = fmaxf(tau, unorder_bits(g));
+            tau = fmaxf(tau, edge);
             const uint32_t row0 = static_cast<uint32_t>(t * TILE_ROWS);
             const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * ACC_COLS;
             if constexpr (KPL == 1) {
@@ -589,6 +638,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                                     pend_w[cnt * 32 + ((lane + cnt) & 31)] = pack_key(x, row);
                                     ++cnt;
                                     best = max(best, order_bits(x));
+                                    if (hist_q != nullptr) hist_count(hist_q, x);
                                 }
                                 m &= m - 1;
                             }
@@ -1135,7 +1185,7 @@ cudaError_t launch_one(const MmaScanArgs &a, const CUtensorMap &tq, const CUtens
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     e = cudaLaunchKernelEx(&cfg, kern, tq, tc, a.keys_or_null, a.n_rows, nq, q0, a.ksel, a.partials, a.nq_total, co,
-                           a.tau_g, a.dbg, a.nq_dev, a.tau0, co > 1 ? a.progress : nullptr, a.max_lead);
+                           a.tau_g, a.dbg, a.nq_dev, a.tau0, co > 1 ? a.progress : nullptr, a.max_lead, a.hist);
     count_launch();
     return e != cudaSuccess ? e : cudaGetLastError();
 }

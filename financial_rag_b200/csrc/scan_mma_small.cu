@@ -104,15 +104,6 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t *r) {
         : "r"(taddr));
 }
 
-// one row of score `v` into a query's histogram (see the kernel): scores below 1/16 are not counted -- their bins' edges are
-// too low to ever matter and the first tile of every CTA would hammer the same few counters
-__device__ __forceinline__ void hist_count(uint32_t *hq, float v) {
-    const int bin = min(255, static_cast<int>(v * 256.0f));  // v >= bin / 256 exactly (a power-of-two scale, truncation)
-    if (bin < 16) return;
-    atomicAdd(hq + 16 + bin, 1u);
-    atomicAdd(hq + (bin >> 4), 1u);
-}
-
 // grid = P CTAs (P = partial lists per query); CTA p takes corpus tiles p, p + P, ... of 128 rows.
 // partials: [P][nq_total][ksel].
 // SPLIT: the queries are read as TWO bf16 terms, q ~ hi + lo with lo = bf16(q - bf16(q)): the operand holds the NQ
