@@ -483,6 +483,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         // cosine collections: the score histogram of this lane's query, shared by all CTAs (see the refresh below)
         uint32_t *hist_q = (hist_g != nullptr && live && !(dbg & 2048))
                                ? hist_g + static_cast<size_t>(q_cta0 + my_q) * SCORE_HIST_WORDS : nullptr;
+        bool hist_on = false;                      // the histogram has produced a bound for this query
         uint32_t best = 0, published = 0;          // order bits of the best score appended / published
         const uint32_t l_tempty = (CG == 2) ? map_to_cta(bar_tempty, 0) : bar_tempty;
         uint32_t it = 0;
@@ -500,7 +501,10 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             // epilogue in the refresh for half of its time.
             const bool refresh_now = it >= next_refresh;
             if (refresh_now) next_refresh = it + 1u + min(it >> 1, refresh_cap - 1u);
-            if (live && refresh_now) {
+            // (once the histogram bounds every live query of the warp -- k' of its rows counted above 1/16 -- the slots
+            //  have nothing to add and their k' loads per lane, 32 round trips at k' = 256, are skipped)
+            const bool read_slots = !__all_sync(FULL_MASK, !live || hist_on) || (dbg & 4096);
+            if (live && refresh_now && read_slots) {
                 g = 0xffffffffu;
 #pragma unroll 8
                 for (int j = 0; j < ksel; ++j) {
@@ -552,6 +556,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                         }
                     }
                     edge = static_cast<float>(16 * cb + fb) * (1.0f / 256.0f);
+                    hist_on = true;
                 }
             }
             mbar_wait(bar_tfull + 8 * buf, bphase);

@@ -1,5 +1,7 @@
 """A/B of K2's shared score histogram (option mma_score_hist 1 / 0), scan-launch time per (rows, batch, k):
-    python scripts/ab_k2_hist.py"""
+    python scripts/ab_k2_hist.py
+FR_AB_MODE=slots: histogram on, threshold slots skipped once the histogram bounds the warp's queries (mma_debug 0) vs
+always read (mma_debug 4096)."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -23,7 +25,10 @@ for n in sizes:
         ref = None
         for rep in range(2):
             for hist in (1, 0):
-                ix.set_option("mma_score_hist", hist)
+                if os.environ.get("FR_AB_MODE") == "slots":
+                    ix.set_option("mma_debug", 0 if hist else 4096)
+                else:
+                    ix.set_option("mma_score_hist", hist)
                 for _ in range(3):
                     d, kk = ix.search_device(q, k)
                 torch.cuda.synchronize()
@@ -37,7 +42,7 @@ for n in sizes:
                 torch.cuda.synchronize()
                 ix.set_profile(False)
                 ms, launches, searches = ix.profile_read()
-                print(json.dumps({"rows": n, "batch": batch, "k": k, "hist": hist, "rep": rep, "ids_equal": same,
+                print(json.dumps({"rows": n, "batch": batch, "k": k, "hist": hist, "mode": os.environ.get("FR_AB_MODE", "hist"), "rep": rep, "ids_equal": same,
                                   "scan_ms_per_search": round(ms / searches, 4), "launches_per_search": launches / searches,
                                   "uncertified": ix.stat("mma_uncertified_queries")}), flush=True)
                 time.sleep(0.2)
