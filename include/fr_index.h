@@ -101,8 +101,16 @@ int fr_index_set_option(fr_index *idx, const char *name, int64_t value);
  * "graph_max_bytes", "small_rows_b1" / "small_rows_b4" (FR_PATH_AUTO: collections up to this many rows send
  * batch 1 / batch <= 4 to the 3-launch streaming kernel), "mma_bound_scale_pct" (diagnostics: inflate the
  * certification bounds), "mma_wide_lists", "mma_max_lead", "mma_f32_shadow" (fp32 cosine collections of width 384:
- * tensor-core scans select on a lazily built bf16 copy of the rows, +50 % memory; default 1).
- * Further stat: "graph_replays". */
+ * tensor-core scans select on a lazily built bf16 copy of the rows, +50 % memory; default 1), "mma_score_hist" (cosine:
+ * the CTAs of a tensor-core scan share a per-query score histogram for their thresholds; default 1, 0 for A/B timing),
+ * "mma_debug" (bit mask, diagnostics; the bits 256 / 512 / 2048 / 4096 switch single optimisations off and leave every
+ * answer unchanged, the others make results wrong), "host_debug" (diagnostics of the host path, scripts/stress_concurrent.py).
+ * Further stat: "graph_replays".
+ * Threading: any number of threads may call fr_index_search / fr_group_search on one object; a call holds the object's
+ * lock only while it enqueues its work and then waits for its own results.  CUDA-graph replay (use_graphs) is used only
+ * while no other caller of the library is waiting for results -- graph launches beside cudaEventSynchronize calls of
+ * other threads crashed inside the driver (csrc/fr_host.h: graph_wait_mutex) -- otherwise the same kernels run eagerly.
+ * Environment: FRB200_SEGV_TRACE=1 prints the native backtrace of a crashing thread. */
 int fr_index_get_stat(fr_index *idx, const char *name, int64_t *out);
 
 /* Replaces Collection.count()                     parent_child/chroma_child_store.py:76-80
