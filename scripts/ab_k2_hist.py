@@ -27,6 +27,8 @@ for n in sizes:
             for hist in (1, 0):
                 if os.environ.get("FR_AB_MODE") == "slots":
                     ix.set_option("mma_debug", 0 if hist else 4096)
+                elif os.environ.get("FR_AB_MODE") == "masks":  # pass masks built per group of 8 columns vs all 64
+                    ix.set_option("mma_debug", 0 if hist else 8192)
                 elif os.environ.get("FR_AB_MODE") == "refresh":  # geometric schedule up to every 64th tile vs every 8th
                     ix.set_option("mma_debug", 0 if hist else 16)
                 else:
