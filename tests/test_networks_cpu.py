@@ -85,3 +85,60 @@ def test_first_tile_bound_is_reached_by_32_distinct_rows(cols, group):
         # lower bound on the tile's 32nd best score -- and every row of the true top 32 passes the gate "score >= bound"
         assert int((scores >= bound).sum()) >= 32
         assert bound <= np.sort(scores)[::-1][31]
+
+
+def hist_count_model(hist, v):
+    """mma_common.cuh: hist_count -- 16 coarse counters followed by 256 fine ones over [0, 1), scores below 1/16 skipped."""
+    b = min(255, int(np.float32(v) * np.float32(256.0)))
+    if b < 16:
+        return
+    hist[16 + b] += 1
+    hist[b >> 4] += 1
+
+
+def hist_edge_model(hist, ksel):
+    """scan_mma.cu, the refresh: the lower edge of the highest bin with ksel counted rows at or above it (coarse bin
+    first, then its 16 fine bins; fine counters that do not reach ksel leave the coarse edge); None = no bound yet."""
+    cb, acc, above = -1, 0, 0
+    for b in range(15, 0, -1):
+        nacc = acc + hist[b]
+        if cb < 0 and nacc >= ksel:
+            cb, above = b, acc
+        acc = nacc
+    if cb < 1:
+        return None
+    fb, found = 0, False
+    for j in range(15, 0, -1):
+        above += hist[16 + 16 * cb + j]
+        if not found and above >= ksel:
+            fb, found = j, True
+    return (16 * cb + fb) / 256.0
+
+
+@pytest.mark.parametrize("ksel", [32, 128, 256])
+def test_score_histogram_edge_is_a_score_ksel_counted_rows_reach(ksel):
+    """The threshold K2 / K2s read off the shared histogram must never exceed the ksel-th best counted score (or a row
+    of the final top-k' could be dropped), and it is the lower edge of that score's own bin when that score is above 1/8 -- also
+    while the fine counters lag their coarse counter (a half-updated view), which may only loosen it."""
+    rng = np.random.default_rng(ksel)
+    for trial in range(60):
+        n = int(rng.integers(ksel, 40 * ksel))
+        sigma = [0.05, 0.15, 0.4][trial % 3]
+        scores = np.clip(rng.standard_normal(n) * sigma + (0.0 if trial % 2 else 0.3), -1.0, 1.004).astype(np.float32)
+        hist = [0] * (16 + 256)
+        for v in scores:
+            hist_count_model(hist, v)
+        kth = float(np.sort(scores)[::-1][ksel - 1])
+        edge = hist_edge_model(hist, ksel)
+        if edge is None:
+            assert int((scores >= 1.0 / 16.0).sum()) < ksel or kth < 2.0 / 16.0
+            continue
+        assert int((scores >= edge).sum()) >= ksel and edge <= kth
+        if kth >= 2.0 / 16.0:  # with complete counters the edge is exactly the lower edge of the ksel-th best score's bin
+            assert edge == min(255, int(np.float32(kth) * np.float32(256.0))) / 256.0
+        # a lagging view: some fine increments have not landed yet -- the edge may only move down
+        lag = list(hist)
+        for b in rng.integers(16, 272, size=20):
+            lag[b] = max(0, lag[b] - int(rng.integers(0, 3)))
+        e2 = hist_edge_model(lag, ksel)
+        assert e2 is None or e2 <= edge
