@@ -309,9 +309,20 @@ def cpu_scan_qps(n_rows_full, batch, k, sample_rows, steps, warmup, torch=None, 
     def run_c():
         return cscan.exact_topk_prepared(corpus, q, k, "cosine", nthreads=cores)
 
+    def run_numpy_mt():  # queries dealt to one worker thread per core in slices, BLAS single-threaded inside each
+        try:
+            from threadpoolctl import threadpool_limits as tl
+
+            with tl(limits=1):
+                return ox.exact_topk_thresholded_mt(q, corpus, k, "cosine", threads=cores)
+        except ImportError:
+            return ox.exact_topk_thresholded_mt(q, corpus, k, "cosine", threads=cores)
+
     results = {}
-    arms = [("numpy_sgemm", run_numpy)]
-    if batch <= 16:  # the C port scans row by row for each query: the bandwidth regime's algorithm
+    # large batches: the sliced scan (one big sgemm leaves the element-wise passes on one core, 3-4 x slower);
+    # small ones: one sgemm with all BLAS threads, and the C port, which scans row by row for each query
+    arms = [("numpy_sgemm_sliced", run_numpy_mt)] if batch >= 256 else [("numpy_sgemm", run_numpy)]
+    if batch <= 16:
         arms.append(("c_openmp", run_c))
     for name, fn in arms:
         try:

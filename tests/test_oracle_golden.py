@@ -177,6 +177,9 @@ def test_thresholded_cpu_scan_equals_exact_scan():
         d1, r1 = ox.exact_topk_thresholded(q, corpus, k, "cosine", chunk_rows=700)
         # sgemm over a different chunk shape may round the last bit differently
         assert (r0 == r1).all() and np.abs(d0 - d1).max() <= 5e-7
+        # the same scan with the queries dealt to worker threads in slices (the CPU arm at large batches)
+        d4, r4 = ox.exact_topk_thresholded_mt(q, corpus, k, "cosine", threads=3, slice_queries=2, chunk_rows=700)
+        assert (r0 == r4).all() and np.abs(d0 - d4).max() <= 5e-7
     d2, r2 = ox.exact_topk_thresholded(q, corpus[:7], 10, "cosine", chunk_rows=3)
     d3, r3 = ox.exact_topk(q, corpus[:7], 10, "cosine", "f32", prepared=True)
     assert (r2 == r3).all() and np.allclose(d2, d3, rtol=0, atol=5e-7)
